@@ -1,0 +1,409 @@
+"""Drop-in for Inference/sampling_tool.py: same classes, kwargs and return values, but
+``Sampling.decode`` runs a KV-cached decoder on the device (gct_decode_begin / gct_decode_steps)
+instead of re-running the whole decoder on the growing prefix every step.
+
+What stays identical to the reference (sampling_tool.py:140-184): one token per step for every
+row, finished rows are not frozen, the loop stops after the first step at which every row has
+emitted <eos> at least once (checked every ``sync_every`` steps; the tail is cut off afterwards so
+the returned ``ys`` has exactly the reference's length), greedy = first maximal index.
+Multinomial draws come from the device (inverse CDF on U(0,1)) -- statistically, not bitwise,
+equal to torch.multinomial.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..Model.modules import get_src_mask, get_trg_mask
+from .toklen_sampling import tokenlen_gen_from_data_distribution
+
+
+class Sampling:
+    def __init__(self, model, kwargs, top_k=None):
+        self.batch_size = 512
+        self.model = model
+        self.top_k = top_k          # dead in the reference too: no subclass passes it
+
+        self.SRC = kwargs['SRC']
+        self.TRG = kwargs['TRG']
+        self.pad_id = self.SRC.vocab.stoi['<pad>']
+        self.sos_id = self.TRG.vocab.stoi['<sos>']
+        self.eos_id = self.TRG.vocab.stoi['<eos>']
+        self.sep_id = self.TRG.vocab.stoi['<sep>'] if '<sep>' in self.TRG.vocab.stoi else None
+
+        self.cond_dim = kwargs['cond_dim']
+        self.latent_dim = kwargs['latent_dim']
+        self.max_strlen = kwargs['max_strlen']
+        self.use_cond2dec = kwargs['use_cond2dec']
+        self.decode_algo = kwargs['decode_algo']
+        self.toklen_data = kwargs['toklen_data']
+        self.scaler = kwargs['scaler']
+        self.device = kwargs['device']
+        self.n_jobs = kwargs['n_jobs']
+
+        # knobs that do not exist in the reference
+        self.sync_every = kwargs.get('sync_every', 16)        # steps between <eos> checks (one D2H read each)
+        self.use_cuda_graph = kwargs.get('use_cuda_graph', True)
+        self.latent_bucket = kwargs.get('latent_bucket', 8)   # latent length padded (masked) to a multiple of this
+        self._graphs = {}
+        self._static = {}
+        self._itos = np.array(self.TRG.vocab.itos, dtype=object)
+        model.pad_id = self.pad_id
+        self.last_decode_steps = 0
+
+    # ------------------------------------------------------------------ small helpers (reference :43-137)
+    def init_y(self, n, add_sos=True, sca_ids=None, add_sep=False):
+        start_ids = []
+        if add_sos:
+            start_ids.append(self.sos_id)
+        if sca_ids is not None:
+            start_ids.extend(sca_ids)
+        if add_sep:
+            start_ids.append(self.sep_id)
+        return torch.from_numpy(np.stack([start_ids] * n))
+
+    def id_to_smi(self, ids):
+        smi = ''
+        for i in ids:
+            if i == self.eos_id:
+                break
+            if i != self.sos_id:
+                smi += self.TRG.vocab.itos[i]
+        return smi
+
+    def ids_to_smiles(self, outs: np.ndarray):
+        """Batch version of id_to_smi: cut each row at its first <eos>, drop <sos>, join."""
+        is_eos = outs == self.eos_id
+        end = np.where(is_eos.any(axis=1), is_eos.argmax(axis=1), outs.shape[1])
+        itos, sos = self._itos, self.sos_id
+        res = []
+        for row, e in zip(outs, end):
+            r = row[:e]
+            res.append(''.join(itos[r[r != sos]]))
+        return res
+
+    def smi_to_id(self, smi, add_sos=False, add_sep=False, add_eos=False):
+        ids = []
+        if add_sos:
+            ids.append(self.sos_id)
+        if add_sep:
+            ids.append(self.sep_id)
+        ids.extend(self.TRG.vocab.stoi[t] for t in self.TRG.tokenize(smi))
+        if add_eos:
+            ids.append(self.eos_id)
+        return ids
+
+    def sample_toklen(self, n):
+        n_bin = int(self.toklen_data.max() - self.toklen_data.min())
+        toklens = tokenlen_gen_from_data_distribution(data=self.toklen_data, size=n, nBins=n_bin)
+        toklens = toklens.reshape((-1,)) + self.cond_dim
+        return np.rint(toklens).astype(int)
+
+    def tokenize_smiles(self, smiles_list, field='SRC'):
+        if field != 'SRC':
+            raise ValueError('only the SRC field is tokenised by the reference')
+        p = self.SRC.process([self.SRC.tokenize(smi) for smi in smiles_list])
+        return p if self.SRC.batch_first else p.T
+
+    def sample_z(self, toklen, n):
+        return torch.normal(mean=0, std=1, size=(n, toklen, self.latent_dim))
+
+    def transform(self, prop):
+        return torch.from_numpy(self.scaler.transform(prop)).float()
+
+    def encoder_input(self, smiles_list, transform=False, econds=None):
+        kwargs = {'src': self.tokenize_smiles(smiles_list).to(self.device)}
+        if econds is not None:
+            if transform:
+                econds = self.transform(econds)
+            if not torch.is_tensor(econds):
+                econds = torch.from_numpy(np.array(econds))
+            kwargs['econds'] = econds.float().to(self.device)
+        return kwargs
+
+    def decoder_input(self, ys, z, dconds=None, transform=False):
+        kwargs = {'z': z.to(self.device), 'trg': ys.to(self.device)}
+        if dconds is not None:
+            if transform:
+                dconds = self.transform(dconds)
+            if not torch.is_tensor(dconds):
+                dconds = torch.from_numpy(np.array(dconds))
+            kwargs['dconds'] = dconds.to(self.device)
+        return kwargs
+
+    # ------------------------------------------------------------------ the decode loop
+    def decode(self, **kwargs):
+        """kwargs: zs (n,Lz,lat), ys (n,t0) int64 prefix, src_mask (n,1,Lz) bool[, dconds (n,nc)].
+        Returns ys (n, t0 + steps_run) exactly like the reference's loop."""
+        if self.use_cond2dec and self.cond_dim > 0:
+            return self._decode_recompute(**kwargs)
+        with torch.no_grad():
+            return self._decode_cached(**kwargs)
+
+    def _decode_recompute(self, **kwargs):
+        """use_cond2dec puts non-causal condition rows in front of the target, which a per-token KV
+        cache cannot express; this path re-runs model.decode on the prefix like the reference."""
+        ys = kwargs['ys'].to(self.device)
+        done = torch.zeros(ys.size(0), dtype=torch.bool)
+        with torch.no_grad():
+            for _ in range(self.max_strlen - 1):
+                trg_mask = get_trg_mask(ys, self.pad_id, self.use_cond2dec, kwargs['dconds'])
+                out = self.model.decode(trg=ys, z=kwargs['zs'].to(self.device), src_mask=kwargs['src_mask'],
+                                        trg_mask=trg_mask, dconds=kwargs['dconds'])
+                prob = torch.softmax(out[:, self.cond_dim:, :][:, -1, :].float(), dim=-1)
+                if self.decode_algo == 'greedy':
+                    nxt = prob.max(dim=1)[1]
+                else:
+                    nxt = torch.multinomial(prob, 1).squeeze(-1)
+                ys = torch.cat([ys, nxt.unsqueeze(-1)], dim=1)
+                done |= (nxt.cpu() == self.eos_id)
+                if bool(done.all()):
+                    break
+        return ys
+
+    def _decode_cached(self, zs, ys, src_mask, dconds=None, uniforms=None):
+        lib, model, dev = L.lib(), self.model, torch.device(self.device)
+        cfg = model._cfg()
+        n, t0 = ys.shape
+        steps = self.max_strlen - 1
+        max_len = t0 + steps
+        Lz = zs.size(1)
+        Lzp = (Lz + self.latent_bucket - 1) // self.latent_bucket * self.latent_bucket
+        greedy = int(self.decode_algo == 'greedy')
+        nc = self.cond_dim
+
+        key = (n, Lzp, max_len, t0, greedy, nc, model.compute_dtype)
+        st = self._static.get(key)
+        if st is None:
+            st = dict(zs=torch.zeros((n, Lzp, self.latent_dim), device=dev, dtype=torch.float32),
+                      mask=torch.zeros((n, Lzp), device=dev, dtype=torch.uint8),
+                      ys=torch.zeros((n, max_len), device=dev, dtype=torch.int64),
+                      status=torch.zeros(2, device=dev, dtype=torch.int32),
+                      uni=torch.zeros((steps, n), device=dev, dtype=torch.float32),
+                      dconds=torch.zeros((n, max(nc, 1)), device=dev, dtype=torch.float32),
+                      status_host=torch.zeros(2, dtype=torch.int32).pin_memory())
+            self._static[key] = st
+        st['zs'][:, :Lz].copy_(zs, non_blocking=True)
+        if Lzp > Lz:
+            st['zs'][:, Lz:].zero_()
+            st['mask'][:, Lz:].zero_()
+        st['mask'][:, :Lz].copy_(src_mask.reshape(n, Lz).to(torch.uint8), non_blocking=True)
+        st['ys'][:, :t0].copy_(ys, non_blocking=True)
+        if nc > 0:
+            st['dconds'].copy_(dconds.float(), non_blocking=True)
+        if not greedy:
+            if uniforms is not None:
+                st['uni'].copy_(uniforms, non_blocking=True)
+            else:
+                st['uni'].uniform_()
+        ws_bytes = lib.gct_decode_workspace_bytes(C.byref(cfg), n, Lzp, max_len)
+        ws = model._ws.get('decode', ws_bytes, dev)
+        w = model._weights()
+        dec = L.GctDecode(B=n, Lz=Lzp, max_len=max_len, prefix_len=t0, greedy=greedy, eos_id=int(self.eos_id), seed=0,
+                          zs=st['zs'].data_ptr(), src_mask=st['mask'].data_ptr(),
+                          dconds=st['dconds'].data_ptr() if nc > 0 else None,
+                          uniforms=None if greedy else st['uni'].data_ptr(), ys=st['ys'].data_ptr(),
+                          status=st['status'].data_ptr())
+
+        def begin():
+            L.check(lib.gct_decode_begin(C.byref(cfg), C.byref(w), C.byref(dec), L.ptr(ws), ws.numel(), L.stream_ptr()),
+                    "gct_decode_begin")
+
+        def run(s0, s1):
+            L.check(lib.gct_decode_steps(C.byref(cfg), C.byref(w), C.byref(dec), s0, s1, L.ptr(ws), ws.numel(),
+                                         L.stream_ptr()), "gct_decode_steps")
+
+        chunks = [(s, min(steps, s + self.sync_every)) for s in range(0, steps, self.sync_every)]
+        gkey = key + (ws.data_ptr(), w.params_f32, w.params_bf16, self.sync_every)
+        graphs = self._graphs.get(gkey) if self.use_cuda_graph else None
+        if self.use_cuda_graph and graphs is None and st.get('warm'):
+            # second call with this shape: capture begin + every chunk once, replay from now on
+            graphs = []
+            for fn in [begin] + [(lambda a=a, b=b: run(a, b)) for a, b in chunks]:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                graphs.append(g)
+            self._graphs[gkey] = graphs
+            # capture does not execute: fall through to replay below
+        st['warm'] = True
+        steps_run = steps
+        if graphs is not None:
+            graphs[0].replay()
+        else:
+            begin()
+        for ci, (s0, s1) in enumerate(chunks):
+            if graphs is not None:
+                graphs[1 + ci].replay()
+            else:
+                run(s0, s1)
+            if s1 < steps:
+                st['status_host'].copy_(st['status'], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if int(st['status_host'][0]) >= n:
+                    break
+        st['status_host'].copy_(st['status'], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if int(st['status_host'][0]) >= n:
+            steps_run = int(st['status_host'][1]) + 1
+        self.last_decode_steps = steps_run
+        return st['ys'][:, :t0 + steps_run].clone()
+
+    # ------------------------------------------------------------------ shared tail of sample_smiles
+    def _finish(self, outs, strip):
+        outs = outs.cpu().numpy()
+        smiles = self.ids_to_smiles(outs[:, strip:])
+        toklen_gen = [len(self.TRG.tokenize(smi)) for smi in smiles]
+        return smiles, toklen_gen
+
+    def _latent_mask(self, toklen, n, width, offset=0):
+        stop = torch.LongTensor(np.asarray(toklen)).view(n, 1, 1) + offset
+        return torch.arange(width).expand(n, 1, width) < stop
+
+    def _attention_maps(self, src, src_mask, ys, econds=None, dconds=None):
+        """encoder self-attention, decoder self- and cross-attention probabilities (lists of N
+        tensors (n,H,Lq,Lk)) with z = mu, as get_attention_map of the reference computes them."""
+        m = self.model
+        _, mu, _, _, att = m._run(src, None, src_mask, None, econds, None, run_decoder=False, want_attn=True)
+        n, Lz = mu.size(0), mu.size(1)
+        smask = torch.ones((n, 1, Lz), dtype=torch.bool, device=mu.device)
+        trg_mask = get_trg_mask(ys, self.pad_id, self.use_cond2dec, dconds)
+        _, _, _, _, att2 = m._run(None, ys, smask, trg_mask, None, dconds, run_encoder=False, z_in=mu, want_attn=True)
+        return list(att[0]), list(att2[1]), list(att2[2])
+
+
+class VaetfSampling(Sampling):
+    def get_attention_map(self, smiles):
+        kws = self.encoder_input([smiles])
+        ids = [self.TRG.vocab.stoi[t] for t in ['<sos>'] + self.TRG.tokenize(smiles) + ['<eos>']]
+        ys = torch.tensor([ids], dtype=torch.long, device=self.device)
+        return self._attention_maps(kws['src'], get_src_mask(kws['src'], self.pad_id), ys)
+
+    def encode_smiles(self, smiles_list):
+        kwargs = self.encoder_input(smiles_list)
+        kwargs['src_mask'] = get_src_mask(kwargs['src'], self.pad_id)
+        return self.model.encode(**kwargs)
+
+    def encode_batch(self, batch):
+        batch['src'] = batch['src'].to(self.device)
+        return self.model.encode(src=batch['src'], src_mask=get_src_mask(batch['src'], self.pad_id))
+
+    def sample_smiles(self, n, zs=None, toklen=None):
+        ys = self.init_y(n, add_sos=True)
+        if zs is not None:
+            assert n == zs.size(0)
+            if toklen is None:
+                toklen = [zs.size(1)] * zs.size(0)
+        elif toklen is None:
+            toklen = self.sample_toklen(n)
+        max_toklen = max(toklen)
+        if zs is None:
+            zs = self.sample_z(max_toklen, n)
+        src_mask = self._latent_mask(toklen, n, max_toklen)
+        outs = self.decode(zs=zs.to(self.device, non_blocking=True), ys=ys.to(self.device),
+                           src_mask=src_mask.to(self.device))
+        smiles, toklen_gen = self._finish(outs, 0)
+        return smiles, toklen, toklen_gen
+
+
+class CvaetfSampling(Sampling):
+    def encode_smiles(self, smiles_list, econds, transform=True):
+        kwargs = self.encoder_input(smiles_list, transform, econds)
+        kwargs['src_mask'] = get_src_mask(kwargs['src'], self.pad_id, kwargs['econds'])
+        return self.model.encode(**kwargs)
+
+    def encode_batch(self, batch, transform=True):
+        if transform:
+            batch['econds'] = self.transform(batch['econds'].cpu())
+        batch['src'] = batch['src'].to(self.device)
+        batch['econds'] = batch['econds'].to(self.device)
+        batch['src_mask'] = get_src_mask(batch['src'], self.pad_id, batch['econds'])
+        return self.model.encode(**batch)
+
+    def sample_smiles(self, dconds, zs=None, toklen=None, transform=True):
+        if zs is not None:
+            assert len(dconds) == len(zs), "The number of 'dconds' and 'zs' should be the same!"
+        n = len(dconds)
+        ys = self.init_y(n, add_sos=True)
+        if transform:
+            dconds = self.transform(dconds)
+        if zs is not None:
+            if toklen is None:
+                toklen = [zs.size(1)] * zs.size(0)
+        elif toklen is None:
+            toklen = self.sample_toklen(n)
+        else:
+            toklen = [t + self.cond_dim for t in toklen]
+        max_toklen = max(toklen)
+        if zs is None:
+            zs = self.sample_z(max_toklen, n)
+        src_mask = self._latent_mask(toklen, n, max_toklen)
+        outs = self.decode(zs=zs.to(self.device, non_blocking=True), ys=ys.to(self.device),
+                           dconds=torch.as_tensor(dconds).float().to(self.device), src_mask=src_mask.to(self.device))
+        smiles, toklen_gen = self._finish(outs, 0)
+        return smiles, toklen, toklen_gen
+
+
+class _ScaffoldMixin:
+    def _sample_with_scaffold(self, n, scaffold, zs, toklen, dconds=None):
+        sca_ids = [self.TRG.vocab.stoi[e] for e in self.TRG.tokenize(scaffold)]
+        ys = self.init_y(n, add_sos=True, sca_ids=sca_ids, add_sep=True)
+        if zs is not None:
+            if toklen is None:
+                toklen = [zs.size(1) - len(sca_ids) - 1] * zs.size(0)
+        elif toklen is None:
+            toklen = self.sample_toklen(n)
+        max_toklen = max(toklen)
+        lat_toklen = len(sca_ids) + 1 + max_toklen
+        if zs is None:
+            zs = self.sample_z(lat_toklen, n)
+        src_mask = self._latent_mask(toklen, n, lat_toklen, offset=len(sca_ids) + 1)
+        kw = dict(zs=zs.to(self.device, non_blocking=True), ys=ys.to(self.device), src_mask=src_mask.to(self.device))
+        if dconds is not None:
+            kw['dconds'] = torch.as_tensor(dconds).float().to(self.device)
+        outs = self.decode(**kw)
+        smiles, toklen_gen = self._finish(outs, 1 + len(sca_ids) + 1)
+        return smiles, toklen, toklen_gen
+
+
+class PscavaetfSampling(_ScaffoldMixin, Sampling):
+    def encode_smiles(self, smiles_list, scaffold_list, econds, transform=True):
+        concat = [s1 + '<sep>' + s2 for s1, s2 in zip(smiles_list, scaffold_list)]
+        kwargs = self.encoder_input(concat, transform, econds)
+        kwargs['src_mask'] = get_src_mask(kwargs['src'], self.pad_id, kwargs['econds'])
+        return self.model.encode(**kwargs)
+
+    def sample_smiles(self, dconds, scaffold, zs=None, toklen=None, transform=True):
+        n = len(dconds)
+        if transform:
+            dconds = self.transform(dconds)
+        return self._sample_with_scaffold(n, scaffold, zs, toklen, dconds)
+
+
+class ScaVaeSampling(_ScaffoldMixin, Sampling):
+    def get_attention_map(self, smiles, scaffold):
+        kws = self.encoder_input([smiles + '<sep>' + scaffold])
+        toks = ['<sos>'] + self.TRG.tokenize(scaffold + '<sep>' + smiles) + ['<eos>']
+        ys = torch.tensor([[self.TRG.vocab.stoi[t] for t in toks]], dtype=torch.long, device=self.device)
+        return self._attention_maps(kws['src'], get_src_mask(kws['src'], self.pad_id), ys)
+
+    def encode_smiles(self, smiles_list, scaffold_list, transform=True):
+        concat = [s1 + '<sep>' + s2 for s1, s2 in zip(smiles_list, scaffold_list)]
+        kwargs = self.encoder_input(concat, transform)
+        kwargs['src_mask'] = get_src_mask(kwargs['src'], self.pad_id)
+        return self.model.encode(**kwargs)
+
+    def sample_smiles(self, n, scaffold, zs=None, toklen=None):
+        return self._sample_with_scaffold(n, scaffold, zs, toklen)
+
+
+sampling_tool_dict = {
+    'vaetf': VaetfSampling,
+    'pvaetf': CvaetfSampling,
+    'scavaetf': ScaVaeSampling,
+    'ctf': CvaetfSampling,
+    'pscavaetf': PscavaetfSampling,
+}

@@ -1,0 +1,150 @@
+// Shared device/host helpers for the gct_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#ifndef __CUDA_ARCH__
+#define GCT_HOST_SIDE 1
+#endif
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: every C-ABI entry returns 0 / negative, message in a thread-local buffer
+// ------------------------------------------------------------------------------------------
+#define GCT_OK 0
+#define GCT_ERR_ARG (-1)
+#define GCT_ERR_CUDA (-2)
+#define GCT_ERR_UNSUPPORTED (-3)
+
+extern thread_local char g_gct_err[512];
+
+#define GCT_FAIL(code, ...)                                   \
+    do {                                                      \
+        snprintf(g_gct_err, sizeof(g_gct_err), __VA_ARGS__);  \
+        return (code);                                        \
+    } while (0)
+
+#define GCT_REQUIRE(cond, ...)                                \
+    do {                                                      \
+        if (!(cond)) GCT_FAIL(GCT_ERR_ARG, __VA_ARGS__);      \
+    } while (0)
+
+#define GCT_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            GCT_FAIL(GCT_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,                 \
+                     cudaGetErrorString(_e));                                                   \
+    } while (0)
+
+#define GCT_LAUNCH_CHECK() GCT_CUDA(cudaGetLastError())
+
+#define GCT_TRY(expr)                 \
+    do {                              \
+        int _r = (expr);              \
+        if (_r != GCT_OK) return _r;  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// type helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+
+// 8-wide vector load/store (bf16: 16 B, float: 2 x 16 B); pointers must be 16 B aligned
+struct f8 { float v[8]; };
+
+__device__ __forceinline__ f8 ld8(const float* p) {
+    f8 r;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ f8 ld8(const bf16* p) {
+    f8 r;
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ void st8(float* p, const f8& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const f8& r) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum for blockDim.x <= 1024 (result valid in every thread)
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? smem32[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+
+// exact-erf GELU (Model/sublayers.py:86 uses F.gelu default) and its derivative
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ------------------------------------------------------------------------------------------
+// counter-based dropout RNG: keep(seed, site, idx) is a pure function, so backward regenerates
+// the same mask without storing it.  (Parity with torch's Philox stream is statistical only.)
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+struct DropCtx {
+    uint32_t seed;       // per-step seed
+    uint32_t thresh;     // drop iff hash < thresh  (thresh = p * 2^32); 0 disables dropout
+    float scale;         // 1/(1-p)
+};
+__host__ __device__ __forceinline__ DropCtx drop_site(DropCtx c, uint32_t site) {
+    c.seed = mix32(c.seed ^ (0x9e3779b9U * (site + 1)));
+    return c;
+}
+__device__ __forceinline__ float drop_apply(const DropCtx& c, uint64_t idx, float v) {
+    if (c.thresh == 0) return v;
+    uint32_t h = mix32(c.seed ^ mix32((uint32_t)idx) ^ (uint32_t)(idx >> 32) * 0x85ebca6bU);
+    return (h < c.thresh) ? 0.f : v * c.scale;
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

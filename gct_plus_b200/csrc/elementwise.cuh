@@ -1,0 +1,457 @@
+// Memory-bound kernels: embedding + positional encoding, the reference's non-standard Norm,
+// reparameterisation + KL, cross-entropy, mask builders, casts, column sums, Adam.
+// All are coalesced / vectorised warp-shuffle kernels; HBM roofline applies.
+#pragma once
+#include "common.cuh"
+
+// ==========================================================================================
+// a2 + a3 (+ cond tokens of a11/a12): x[b,l,:] = value*sqrt(d) + pe[l,:], dropout
+//   value = l < nc ? cond_W[l*d+c,:] . conds[b,:] + cond_B[l*d+c]  :  table[tok[b,l-nc], c]
+// Reference: Model/modules.py:101-144, Model/cvaetf.py:36-43,98-112.
+// ==========================================================================================
+__global__ void embed_pe_kernel(const int64_t* __restrict__ tok, int Ltok, const float* __restrict__ table,
+                                int vocab, const float* __restrict__ conds, const float* __restrict__ cond_W,
+                                const float* __restrict__ cond_B, int nc, const float* __restrict__ pe,
+                                float* __restrict__ out, int d, float scale, DropCtx drop) {
+    const int L = nc + Ltok;
+    const int row = blockIdx.x;            // b*L + l
+    const int b = row / L, l = row % L;
+    float* o = out + (size_t)row * d;
+    const float* per = pe + (size_t)l * d;
+    if (l < nc) {
+        float cv[8];
+        for (int k = 0; k < nc; ++k) cv[k] = conds[(size_t)b * nc + k];
+        for (int c = threadIdx.x; c < d; c += blockDim.x) {
+            const float* w = cond_W + ((size_t)l * d + c) * nc;
+            float v = cond_B[(size_t)l * d + c];
+            for (int k = 0; k < nc; ++k) v = fmaf(w[k], cv[k], v);
+            o[c] = drop_apply(drop, (uint64_t)row * d + c, v * scale + per[c]);
+        }
+    } else {
+        long long t = tok[(size_t)b * Ltok + (l - nc)];
+        if (t < 0 || t >= vocab) t = 0;    // out-of-range ids are a caller bug; stay in bounds
+        const float* e = table + (size_t)t * d;
+        for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+            float4 ev = *reinterpret_cast<const float4*>(e + c);
+            float4 pv = *reinterpret_cast<const float4*>(per + c);
+            float4 r;
+            const uint64_t base = (uint64_t)row * d + c;
+            r.x = drop_apply(drop, base + 0, ev.x * scale + pv.x);
+            r.y = drop_apply(drop, base + 1, ev.y * scale + pv.y);
+            r.z = drop_apply(drop, base + 2, ev.z * scale + pv.z);
+            r.w = drop_apply(drop, base + 3, ev.w * scale + pv.w);
+            *reinterpret_cast<float4*>(o + c) = r;
+        }
+    }
+}
+
+// backward of the above: scatter-free reduction.  dx is the gradient w.r.t. `out`.
+// One block per (vocab id | cond slot) column-chunk; loops over all rows and accumulates rows whose
+// token matches.  The tables are tiny (<= 64 ids), rows are ~40k: every block streams the token
+// array (8 B/row) and reads only the matching dx rows.
+__global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, int B, int Ltok, int nc, const float* __restrict__ dx,
+                                 int d, float scale, DropCtx drop, float* __restrict__ dtable, int vocab) {
+    const int v = blockIdx.x;              // vocab id
+    const int L = nc + Ltok;
+    const int c0 = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c0 >= d) return;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const int64_t* tr = tok + (size_t)b * Ltok;
+        for (int l = 0; l < Ltok; ++l) {
+            if (tr[l] == v) {
+                const size_t row = (size_t)b * L + nc + l;
+                acc += drop_apply(drop, (uint64_t)row * d + c0, dx[row * d + c0]);
+            }
+        }
+    }
+    dtable[(size_t)v * d + c0] += acc * scale;
+}
+
+// cond-token linear backward: dW[l*d+c, k] += scale * sum_b dx[b,l,c]*conds[b,k]; dB[l*d+c] += scale*sum_b dx
+__global__ void cond_embed_bwd_kernel(const float* __restrict__ dx, int B, int L, int nc, int d,
+                                      const float* __restrict__ conds, float scale, DropCtx drop, int use_drop_index,
+                                      float* __restrict__ dW, float* __restrict__ dB) {
+    const int l = blockIdx.x;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    float aw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float ab = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const size_t row = (size_t)b * L + l;
+        float g = dx[row * d + c];
+        if (use_drop_index) g = drop_apply(drop, (uint64_t)row * d + c, g);
+        ab += g;
+        for (int k = 0; k < nc; ++k) aw[k] = fmaf(g, conds[(size_t)b * nc + k], aw[k]);
+    }
+    dB[(size_t)l * d + c] += ab * scale;
+    for (int k = 0; k < nc; ++k) dW[((size_t)l * d + c) * nc + k] += aw[k] * scale;
+}
+
+// cond2lat tokens written into the decoder memory: mem[b, j, :] = W[j*d+c,:].conds[b] + B[j*d+c]
+template <typename T>
+__global__ void cond_tokens_kernel(const float* __restrict__ conds, const float* __restrict__ W,
+                                   const float* __restrict__ Bv, int nc, int d, T* __restrict__ mem, int Lmem) {
+    const int b = blockIdx.x / nc, j = blockIdx.x % nc;
+    T* o = mem + ((size_t)b * Lmem + j) * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float* w = W + ((size_t)j * d + c) * nc;
+        float v = Bv[(size_t)j * d + c];
+        for (int k = 0; k < nc; ++k) v = fmaf(w[k], conds[(size_t)b * nc + k], v);
+        o[c] = from_f<T>(v);
+    }
+}
+
+// ==========================================================================================
+// a1 Norm: y = alpha*(x-mean)/(std_unbiased+eps)+bias     (Model/modules.py:80-95)
+// one warp per row; d % 128 == 0, d <= 1024.  Optionally also writes an fp32 copy (the encoder
+// keeps the *normalised* value as its residual stream, Model/layers.py:23,28).
+// ==========================================================================================
+template <typename T, int NV /* float4 per lane */>
+__global__ void norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                const float* __restrict__ bias, T* __restrict__ y, float* __restrict__ y32,
+                                int rows, float eps) {
+    const int d = NV * 128;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * d;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float stdv = sqrtf(warp_sum(q) / (d - 1));
+    const float r = 1.f / (stdv + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        float4 a = *reinterpret_cast<const float4*>(alpha + c);
+        float4 b = *reinterpret_cast<const float4*>(bias + c);
+        float4 o;
+        o.x = a.x * v[i].x * r + b.x; o.y = a.y * v[i].y * r + b.y;
+        o.z = a.z * v[i].z * r + b.z; o.w = a.w * v[i].w * r + b.w;
+        if (y32) *reinterpret_cast<float4*>(y32 + (size_t)row * d + c) = o;
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)row * d + c) = o;
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(y) + (size_t)row * d + c) = u;
+        }
+    }
+}
+
+// Norm backward.  dx = r*(g - mean(g)) - c*xc,  g = dy*alpha, c = r^2*sum(g*xc)/((d-1)*std)
+//   (+ `add` : gradient arriving on the residual path).  dalpha/dbias accumulated with atomics.
+template <int NV>
+__global__ void norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                const float* __restrict__ dy, const float* __restrict__ add,
+                                float* __restrict__ dx, float* __restrict__ dalpha, float* __restrict__ dbias,
+                                int rows, float eps) {
+    const int d = NV * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float4 da[NV], db[NV], al[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        da[i] = make_float4(0, 0, 0, 0);
+        db[i] = make_float4(0, 0, 0, 0);
+        al[i] = *reinterpret_cast<const float4*>(alpha + (i * 32 + lane) * 4);
+    }
+    for (int row = blockIdx.x * nwarp + warp; row < rows; row += gridDim.x * nwarp) {
+        const float* xr = x + (size_t)row * d;
+        const float* gr = dy + (size_t)row * d;
+        float4 v[NV], g[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+            g[i] = *reinterpret_cast<const float4*>(gr + (i * 32 + lane) * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) / d;
+        float q = 0.f, sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+        const float stdv = sqrtf(warp_sum(q) / (d - 1));
+        const float r = 1.f / (stdv + eps);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            // parameter grads use the raw dy
+            db[i].x += g[i].x; db[i].y += g[i].y; db[i].z += g[i].z; db[i].w += g[i].w;
+            da[i].x += g[i].x * v[i].x * r; da[i].y += g[i].y * v[i].y * r;
+            da[i].z += g[i].z * v[i].z * r; da[i].w += g[i].w * v[i].w * r;
+            g[i].x *= al[i].x; g[i].y *= al[i].y; g[i].z *= al[i].z; g[i].w *= al[i].w;
+            sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+        }
+        const float mg = warp_sum(sg) / d;
+        const float c = (stdv > 0.f) ? r * r * warp_sum(sgx) / ((d - 1) * stdv) : 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const size_t off = (size_t)row * d + (i * 32 + lane) * 4;
+            float4 o;
+            o.x = r * (g[i].x - mg) - c * v[i].x; o.y = r * (g[i].y - mg) - c * v[i].y;
+            o.z = r * (g[i].z - mg) - c * v[i].z; o.w = r * (g[i].w - mg) - c * v[i].w;
+            if (add) {
+                float4 a = *reinterpret_cast<const float4*>(add + off);
+                o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+            }
+            *reinterpret_cast<float4*>(dx + off) = o;
+        }
+    }
+    // block reduce of the parameter partials through shared memory, then one atomic per column
+    extern __shared__ float sm[];              // [2][d]
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        atomicAdd(&sm[c + 0], da[i].x); atomicAdd(&sm[c + 1], da[i].y);
+        atomicAdd(&sm[c + 2], da[i].z); atomicAdd(&sm[c + 3], da[i].w);
+        atomicAdd(&sm[d + c + 0], db[i].x); atomicAdd(&sm[d + c + 1], db[i].y);
+        atomicAdd(&sm[d + c + 2], db[i].z); atomicAdd(&sm[d + c + 3], db[i].w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        atomicAdd(dalpha + c, sm[c]);
+        atomicAdd(dbias + c, sm[d + c]);
+    }
+}
+
+// ==========================================================================================
+// a8 reparameterisation (Model/sublayers.py:11-18, Model/cvaetf.py:63-69) on the fused
+// [rows, 2*lat] head output:  mu | log_var -> z = mu + eps*exp(0.5*log_var).
+// Also emits the padded decoder-memory operand zpad[b, off + s, :] (type T) used by fc_z.
+// ==========================================================================================
+template <typename T>
+__global__ void reparam_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps, int rows, int lat,
+                                   int Se, int Sm, float* __restrict__ mu, float* __restrict__ lv,
+                                   float* __restrict__ z, T* __restrict__ zpad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * lat) return;
+    const size_t row = i / lat;
+    const int c = (int)(i % lat);
+    const float m = mulv[row * 2 * lat + c], l = mulv[row * 2 * lat + lat + c];
+    const float zz = eps ? fmaf(eps[i], __expf(0.5f * l), m) : m;
+    mu[i] = m; lv[i] = l; z[i] = zz;
+    if (zpad) {
+        const size_t b = row / Se, s = row % Se;
+        zpad[((b * Sm) + (Sm - Se) + s) * lat + c] = from_f<T>(zz);
+    }
+}
+
+// d(mulv) from dz (decoder path) + external dmu/dlv (loss path, may be null) :
+//   dmu_tot = dz + dmu ;  dlv_tot = dz*eps*0.5*exp(0.5 lv) + dlv
+template <typename T>
+__global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ dmu_ext,
+                                   const float* __restrict__ dlv_ext, const float* __restrict__ eps,
+                                   const float* __restrict__ lv, int rows, int lat, T* __restrict__ dmulv) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * lat) return;
+    const size_t row = i / lat;
+    const int c = (int)(i % lat);
+    const float g = dz ? dz[i] : 0.f;
+    float dm = g + (dmu_ext ? dmu_ext[i] : 0.f);
+    float dl = (dlv_ext ? dlv_ext[i] : 0.f);
+    if (eps) dl += g * eps[i] * 0.5f * __expf(0.5f * lv[i]);
+    dmulv[row * 2 * lat + c] = from_f<T>(dm);
+    dmulv[row * 2 * lat + lat + c] = from_f<T>(dl);
+}
+
+// ==========================================================================================
+// a15 loss (Train/trainer1.py:19-30): per-row CE with ignore_index, KL partials, final reduce.
+// ==========================================================================================
+// one warp per row, V <= 128.  row_loss[r] = ignored ? 0 : logsumexp - logit[target]
+// dlogits (optional) = gscale * (softmax - onehot) or 0 for ignored rows.
+__global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int rows, int V,
+                               int ld, int pad_id, float* __restrict__ row_loss, float* __restrict__ dlogits,
+                               float gscale) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* lr = logits + (size_t)row * ld;
+    float v[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = i * 32 + lane;
+        v[i] = (c < V) ? lr[c] : -INFINITY;
+        mx = fmaxf(mx, v[i]);
+    }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += (i * 32 + lane < V) ? expf(v[i] - mx) : 0.f;
+    s = warp_sum(s);
+    const long long t = target[row];
+    const bool ign = (t == pad_id) || t < 0 || t >= V;
+    const float lse = mx + logf(s);
+    if (lane == 0) row_loss[row] = ign ? 0.f : (lse - lr[t]);
+    if (dlogits) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = i * 32 + lane;
+            if (c < V) {
+                float p = expf(v[i] - lse);
+                dlogits[(size_t)row * ld + c] = ign ? 0.f : gscale * (p - (c == t ? 1.f : 0.f));
+            }
+        }
+    }
+}
+
+// KL partial sums: part[block] = sum over its slice of -0.5*(1 + lv - mu^2 - exp(lv))
+__global__ void kl_partial_kernel(const float* __restrict__ mu, const float* __restrict__ lv, size_t n,
+                                  float* __restrict__ part) {
+    __shared__ float sm[32];
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float m = mu[i], l = lv[i];
+        acc += -0.5f * (1.f + l - m * m - expf(l));
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// deterministic single-block sum of n floats -> out[0] (double accumulation)
+__global__ void final_sum_kernel(const float* __restrict__ in, size_t n, float* __restrict__ out) {
+    __shared__ double sm[32];
+    double acc = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)in[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double r = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (threadIdx.x == 0) out[0] = (float)r;
+    }
+}
+
+// d(KL)/dmu = beta*mu ; d(KL)/dlv = beta*0.5*(exp(lv)-1)   (scaled by upstream gscale)
+__global__ void kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, size_t n, float g,
+                              float* __restrict__ dmu, float* __restrict__ dlv) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dmu[i] = g * mu[i];
+    dlv[i] = g * 0.5f * (expf(lv[i]) - 1.f);
+}
+
+// ==========================================================================================
+// a4 masks (Model/modules.py:10-66) as byte arrays.
+// ==========================================================================================
+// key mask [B, nc+L]: first nc entries 1, then tok != pad
+__global__ void src_mask_kernel(const int64_t* __restrict__ tok, int B, int L, int nc, int pad, uint8_t* __restrict__ m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = nc + L;
+    if (i >= B * W) return;
+    const int b = i / W, j = i % W;
+    m[i] = (j < nc) ? 1 : (tok[(size_t)b * L + (j - nc)] != pad);
+}
+// dense target mask [B, nc+T, nc+T] (nc = 0 unless cond2dec): keypad(j) & nopeak(i,j)
+__global__ void trg_mask_kernel(const int64_t* __restrict__ tok, int B, int T, int nc, int pad, uint8_t* __restrict__ m) {
+    const int W = nc + T;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * W * W) return;
+    const int j = (int)(i % W), q = (int)((i / W) % W), b = (int)(i / ((size_t)W * W));
+    const bool key_ok = (j < nc) ? true : (tok[(size_t)b * T + (j - nc)] != pad);
+    bool peek;
+    if (q < nc) peek = (j < nc) || (j == nc);            // cond rows: all cond cols + first target col
+    else peek = (j < nc) || ((j - nc) <= (q - nc));      // target rows: cond cols + causal
+    m[i] = key_ok && peek;
+}
+// generic "nonzero" cast of a caller-supplied mask (bool/uint8: esize 1, int32: 4, int64: 8)
+__global__ void mask_cast_kernel(const void* __restrict__ in, int esize, size_t n, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool nz;
+    if (esize == 1) nz = reinterpret_cast<const uint8_t*>(in)[i] != 0;
+    else if (esize == 4) nz = reinterpret_cast<const int32_t*>(in)[i] != 0;
+    else nz = reinterpret_cast<const int64_t*>(in)[i] != 0;
+    out[i] = nz;
+}
+
+// ==========================================================================================
+// casts / column sums / optimiser
+// ==========================================================================================
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[i + k] = from_f<TO>(to_f(in[i + k]));
+    } else {
+        for (size_t k = i; k < n; ++k) out[k] = from_f<TO>(to_f(in[k]));
+    }
+}
+
+// out[r,c] = T(dropmask(site, r*ld_idx + c) * in[r,c]); optionally accumulates column sums (bias grad)
+template <typename T>
+__global__ void cast_drop_colsum_kernel(const float* __restrict__ in, T* __restrict__ out, int rows, int cols,
+                                        DropCtx drop, float* __restrict__ colsum) {
+    // block: 128 threads -> 128*4 columns chunk? generic: each thread owns 4 consecutive columns
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+    if (c >= cols) return;
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const size_t off = (size_t)r * cols + c;
+        float4 v = *reinterpret_cast<const float4*>(in + off);
+        v.x = drop_apply(drop, off + 0, v.x); v.y = drop_apply(drop, off + 1, v.y);
+        v.z = drop_apply(drop, off + 2, v.z); v.w = drop_apply(drop, off + 3, v.w);
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = v;
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0);
+            u.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + off) = u;
+        }
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (colsum) {
+        atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
+        atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
+    }
+}
+
+// colsum[c] += sum_r in[r, c]  (in has leading dimension ld)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ colsum) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float acc = 0.f;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) acc += to_f(in[(size_t)r * ld + c]);
+    atomicAdd(colsum + c, acc);
+}
+
+// Fused Adam over the flat parameter buffer (torch.optim.Adam semantics, train1.py:116-119),
+// with the 1/world_size gradient averaging folded in and the bf16 shadow refreshed in place.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, bf16* __restrict__ shadow, size_t n, float lr, float b1, float b2,
+                            float eps, float bc1, float bc2_sqrt, float gscale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gr = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gr;
+    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float pi = p[i] - (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+}

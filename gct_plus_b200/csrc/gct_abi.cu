@@ -1,0 +1,296 @@
+// C-ABI entry points of libgct_b200.so (declared in include/gct_b200.h).
+#include "model.cuh"
+#ifdef GCT_WITH_NCCL
+#include <nccl.h>
+#endif
+
+thread_local char g_gct_err[512] = {0};
+int g_gct_simt_only = 0;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* gct_last_error(void) { return g_gct_err; }
+int gct_version(void) { return 100; }
+int gct_sm(void) {
+#ifdef GCT_SM_TARGET
+    return GCT_SM_TARGET;
+#else
+    return 0;
+#endif
+}
+int gct_num_slots(int n_layers) { return GCT_NUM_GLOBAL_SLOTS + n_layers * (GCT_ENC_LAYER_SLOTS + GCT_DEC_LAYER_SLOTS); }
+int gct_set_gemm_backend(int simt_only) { g_gct_simt_only = simt_only; return GCT_OK; }
+
+int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
+                 void* stream) {
+    GCT_REQUIRE(d % 128 == 0 && d <= 1024, "norm: d=%d must be a multiple of 128, <= 1024", d);
+    if (rows <= 0) return GCT_OK;
+    dim3 grid(cdiv(rows, 8));
+    const int nv = d / 128;
+#define CASE(NV)                                                                                                       \
+    case NV:                                                                                                           \
+        if (dtype == GCT_DTYPE_F32) norm_fwd_kernel<float, NV><<<grid, 256, 0, ST(stream)>>>(x, alpha, bias, (float*)y, y32, rows, 1e-6f); \
+        else norm_fwd_kernel<bf16, NV><<<grid, 256, 0, ST(stream)>>>(x, alpha, bias, (bf16*)y, y32, rows, 1e-6f);      \
+        break;
+    switch (nv) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
+#undef CASE
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
+int gct_norm_bwd(const float* x, const float* alpha, const float* dy, const float* add, float* dx, float* dalpha,
+                 float* dbias, int rows, int d, void* stream) {
+    GCT_REQUIRE(d % 128 == 0 && d <= 1024, "norm: d=%d must be a multiple of 128, <= 1024", d);
+    if (rows <= 0) return GCT_OK;
+    dim3 grid(min(cdiv(rows, 8), 148 * 4));
+    const size_t sm = 2 * d * sizeof(float);
+#define CASE(NV) case NV: norm_bwd_kernel<NV><<<grid, 256, sm, ST(stream)>>>(x, alpha, dy, add, dx, dalpha, dbias, rows, 1e-6f); break;
+    switch (d / 128) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
+#undef CASE
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
+int gct_gemm(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
+             const float* bias, const float* res32, const void* aux_in, void* aux_out, float* out32, void* outT, int ldc,
+             int flags, int split_k, int bn_hint, int dtype, void* stream) {
+    Epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.res32 = res32; e.aux_in = aux_in; e.aux_out = aux_out; e.out32 = out32; e.outT = outT; e.ldc = ldc;
+    e.flags = flags; e.alpha = 1.f; e.drop.thresh = 0; e.drop.scale = 1.f;
+    GCT_REQUIRE(out32 || outT, "gemm: no output");
+    if (dtype == GCT_DTYPE_F32) {
+        return launch_gemm_simt<float, float, float>((const float*)A, a_mn ? 1 : lda, a_mn ? lda : 1, (const float*)B,
+                                                     b_mn ? 1 : ldb, b_mn ? ldb : 1, M, N, K, split_k, e, ST(stream));
+    }
+    if (g_gct_simt_only)
+        return launch_gemm_simt<bf16, bf16, bf16>((const bf16*)A, a_mn ? 1 : lda, a_mn ? lda : 1, (const bf16*)B, b_mn ? 1 : ldb,
+                                                  b_mn ? ldb : 1, M, N, K, split_k, e, ST(stream));
+    return tc::launch_gemm_tc((const bf16*)A, a_mn != 0, lda, (const bf16*)B, b_mn != 0, ldb, M, N, K, split_k, bn_hint, e,
+                              ST(stream));
+}
+
+static AttnParams make_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
+                            int64_t mb, int mr, void* out, int ldo, float* lse, float* probs, int B, int H, int Lq, int Lk) {
+    AttnParams p;
+    p.Q = q; p.K = k; p.V = v; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.mask = mask; p.mask_bstride = mb; p.mask_rstride = mr;
+    p.O = out; p.ldo = ldo; p.lse = lse; p.probs = probs; p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.scale = 0.125f;
+    p.drop.seed = 0; p.drop.thresh = 0; p.drop.scale = 1.f;
+    return p;
+}
+
+int gct_attention_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
+                      int64_t mask_bstride, int mask_rstride, void* out, int ldo, float* lse, float* probs, int B, int H,
+                      int Lq, int Lk, int dtype, void* stream) {
+    AttnParams p = make_attn(q, ldq, k, ldk, v, ldv, mask, mask_bstride, mask_rstride, out, ldo, lse, probs, B, H, Lq, Lk);
+    return dtype == GCT_DTYPE_F32 ? launch_attn_fwd<float>(p, ST(stream)) : launch_attn_fwd<bf16>(p, ST(stream));
+}
+
+int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
+                      int64_t mask_bstride, int mask_rstride, const float* lse, const void* dout, int lddo, void* dq, int lddq,
+                      void* dk, int lddk, void* dv, int lddv, int B, int H, int Lq, int Lk, int dtype, void* stream) {
+    AttnBwdParams bp;
+    bp.f = make_attn(q, ldq, k, ldk, v, ldv, mask, mask_bstride, mask_rstride, nullptr, 0, const_cast<float*>(lse), nullptr, B, H,
+                     Lq, Lk);
+    bp.dO = dout; bp.lddo = lddo; bp.dQ = dq; bp.dK = dk; bp.dV = dv; bp.lddq = lddq; bp.lddk = lddk; bp.lddv = lddv;
+    return dtype == GCT_DTYPE_F32 ? launch_attn_bwd<float>(bp, ST(stream)) : launch_attn_bwd<bf16>(bp, ST(stream));
+}
+
+int gct_src_mask(const int64_t* tok, int B, int L, int nc, int pad, uint8_t* out, void* stream) {
+    const int n = B * (nc + L);
+    if (n <= 0) return GCT_OK;
+    src_mask_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(tok, B, L, nc, pad, out);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+int gct_trg_mask(const int64_t* tok, int B, int T, int nc, int pad, uint8_t* out, void* stream) {
+    const size_t n = (size_t)B * (nc + T) * (nc + T);
+    if (n == 0) return GCT_OK;
+    trg_mask_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(tok, B, T, nc, pad, out);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+int gct_mask_cast(const void* in, int elem_size, int64_t n, uint8_t* out, void* stream) {
+    GCT_REQUIRE(elem_size == 1 || elem_size == 4 || elem_size == 8, "mask_cast: element size %d", elem_size);
+    if (n <= 0) return GCT_OK;
+    mask_cast_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(in, elem_size, (size_t)n, out);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+int gct_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+    if (n <= 0) return GCT_OK;
+    cast_kernel<float, bf16><<<cdiv(n, 1024), 256, 0, ST(stream)>>>(in, (bf16*)out, (size_t)n);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+int gct_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream) {
+    if (n <= 0) return GCT_OK;
+    cast_kernel<bf16, float><<<cdiv(n, 1024), 256, 0, ST(stream)>>>((const bf16*)in, out, (size_t)n);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
+// ---------------- loss ----------------
+static const int KL_BLOCKS = 592;
+size_t gct_loss_scratch_bytes(int64_t rows, int64_t n_latent) { (void)n_latent; return (size_t)(rows + KL_BLOCKS + 64) * sizeof(float); }
+
+__global__ void loss_combine_kernel(const float* rce, const float* kld, float beta, float* out4) {
+    out4[0] = rce[0] + beta * kld[0]; out4[1] = rce[0]; out4[2] = 0.f; out4[3] = kld[0];
+}
+
+int gct_loss_fwd_bwd(const float* logits, int ld, int V, const int64_t* target, int64_t rows, int pad_id, const float* mu,
+                     const float* log_var, int64_t n_latent, float beta, float gscale, float* out4, float* dlogits, float* dmu,
+                     float* dlv, void* scratch, void* stream) {
+    GCT_REQUIRE(V <= 128, "loss: vocabulary %d > 128", V);
+    GCT_REQUIRE(scratch && out4, "loss: scratch / out missing");
+    float* row_loss = reinterpret_cast<float*>(scratch);
+    float* part = row_loss + rows;
+    float* sums = part + KL_BLOCKS;       // [0] = RCE, [1] = KLD
+    cudaStream_t st = ST(stream);
+    ce_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(logits, target, (int)rows, V, ld, pad_id, row_loss, dlogits, gscale);
+    GCT_LAUNCH_CHECK();
+    final_sum_kernel<<<1, 1024, 0, st>>>(row_loss, (size_t)rows, sums);
+    GCT_LAUNCH_CHECK();
+    kl_partial_kernel<<<KL_BLOCKS, 256, 0, st>>>(mu, log_var, (size_t)n_latent, part);
+    GCT_LAUNCH_CHECK();
+    final_sum_kernel<<<1, 1024, 0, st>>>(part, (size_t)KL_BLOCKS, sums + 1);
+    GCT_LAUNCH_CHECK();
+    loss_combine_kernel<<<1, 1, 0, st>>>(sums, sums + 1, beta, out4);
+    GCT_LAUNCH_CHECK();
+    if (dmu && dlv) {
+        kl_bwd_kernel<<<cdiv(n_latent, 256), 256, 0, st>>>(mu, log_var, (size_t)n_latent, beta * gscale, dmu, dlv);
+        GCT_LAUNCH_CHECK();
+    }
+    return GCT_OK;
+}
+
+// ---------------- model ----------------
+}  // extern "C"
+template <typename T>
+static int forward_impl(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, void* ws, size_t ws_bytes,
+                        void* stream) {
+    Model<T> m;
+    GCT_TRY(m.init(cfg, w, io->seed, io->train, stream));
+    Acts<T> A;
+    A.carve(*cfg, io->B, io->S, io->T, ws);
+    GCT_REQUIRE(A.bytes <= ws_bytes, "forward: workspace too small (%zu < %zu)", ws_bytes, A.bytes);
+    return model_forward<T>(m, *io, A);
+}
+template <typename T>
+static int backward_impl(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, const float* dlogits,
+                         const float* dmu, const float* dlv, const float* dz, void* ws, size_t ws_bytes, void* scratch,
+                         size_t scratch_bytes, void* stream) {
+    Model<T> m;
+    GCT_TRY(m.init(cfg, w, io->seed, io->train, stream));
+    Acts<T> A;
+    A.carve(*cfg, io->B, io->S, io->T, ws);
+    GCT_REQUIRE(A.bytes <= ws_bytes, "backward: workspace too small");
+    BwdScratch<T> S;
+    S.carve(*cfg, A, scratch);
+    GCT_REQUIRE(S.bytes <= scratch_bytes, "backward: scratch too small (%zu < %zu)", scratch_bytes, S.bytes);
+    return model_backward<T>(m, *io, A, S, dlogits, dmu, dlv, dz);
+}
+
+extern "C" {
+size_t gct_forward_workspace_bytes(const gct_config_t* cfg, int B, int S, int T) {
+    if (cfg->dtype == GCT_DTYPE_F32) { Acts<float> A; A.carve(*cfg, B, S, T, nullptr); return A.bytes; }
+    Acts<bf16> A; A.carve(*cfg, B, S, T, nullptr); return A.bytes;
+}
+size_t gct_backward_scratch_bytes(const gct_config_t* cfg, int B, int S, int T) {
+    if (cfg->dtype == GCT_DTYPE_F32) { Acts<float> A; A.carve(*cfg, B, S, T, nullptr); BwdScratch<float> X; X.carve(*cfg, A, nullptr); return X.bytes; }
+    Acts<bf16> A; A.carve(*cfg, B, S, T, nullptr); BwdScratch<bf16> X; X.carve(*cfg, A, nullptr); return X.bytes;
+}
+int gct_forward(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    GCT_REQUIRE(cfg && w && io && workspace, "forward: null argument");
+    return cfg->dtype == GCT_DTYPE_F32 ? forward_impl<float>(cfg, w, io, workspace, workspace_bytes, stream)
+                                       : forward_impl<bf16>(cfg, w, io, workspace, workspace_bytes, stream);
+}
+int gct_backward(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, const float* dlogits, const float* dmu,
+                 const float* dlog_var, const float* dz, void* workspace, size_t workspace_bytes, void* scratch,
+                 size_t scratch_bytes, void* stream) {
+    GCT_REQUIRE(cfg && w && io && workspace && scratch, "backward: null argument");
+    return cfg->dtype == GCT_DTYPE_F32
+               ? backward_impl<float>(cfg, w, io, dlogits, dmu, dlog_var, dz, workspace, workspace_bytes, scratch, scratch_bytes, stream)
+               : backward_impl<bf16>(cfg, w, io, dlogits, dmu, dlog_var, dz, workspace, workspace_bytes, scratch, scratch_bytes, stream);
+}
+
+// ---------------- optimiser ----------------
+int gct_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow, int64_t n, int step,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    GCT_REQUIRE(step >= 1, "adam: step must start at 1");
+    if (n <= 0) return GCT_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    adam_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, (bf16*)bf16_shadow, (size_t)n, lr, beta1,
+                                                      beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+double gct_noam_lr(int64_t step, int d_model, int64_t warmup) {
+    const double head = pow((double)step, -0.5), tail = (double)step * pow((double)warmup, -1.5);
+    return pow((double)d_model, -0.5) * (head < tail ? head : tail);
+}
+
+// ---------------- decode ----------------
+size_t gct_decode_workspace_bytes(const gct_config_t* cfg, int B, int Lz, int max_len) {
+    if (cfg->dtype == GCT_DTYPE_F32) { DecodeWs<float> W; W.carve(*cfg, B, Lz, max_len, nullptr); return W.bytes; }
+    DecodeWs<bf16> W; W.carve(*cfg, B, Lz, max_len, nullptr); return W.bytes;
+}
+}  // extern "C"
+template <typename T>
+static int decode_begin_impl(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, void* ws, size_t ws_bytes,
+                             void* stream) {
+    Model<T> m;
+    GCT_TRY(m.init(cfg, w, 0, 0, stream));
+    DecodeWs<T> W;
+    W.carve(*cfg, d->B, d->Lz, d->max_len, ws);
+    GCT_REQUIRE(W.bytes <= ws_bytes, "decode: workspace too small (%zu < %zu)", ws_bytes, W.bytes);
+    GCT_TRY(decode_begin<T>(m, *d, W));
+    for (int pos = 0; pos + 1 < d->prefix_len; ++pos) GCT_TRY(decode_one<T>(m, *d, W, pos, 0, false));
+    return GCT_OK;
+}
+template <typename T>
+static int decode_steps_impl(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, int s0, int s1, void* ws,
+                             size_t ws_bytes, void* stream) {
+    Model<T> m;
+    GCT_TRY(m.init(cfg, w, 0, 0, stream));
+    DecodeWs<T> W;
+    W.carve(*cfg, d->B, d->Lz, d->max_len, ws);
+    GCT_REQUIRE(W.bytes <= ws_bytes, "decode: workspace too small");
+    for (int s = s0; s < s1; ++s) {
+        const int pos = d->prefix_len - 1 + s;
+        GCT_REQUIRE(pos + 1 < d->max_len, "decode: step %d overflows ys (max_len %d)", s, d->max_len);
+        GCT_TRY(decode_one<T>(m, *d, W, pos, s, true));
+    }
+    return GCT_OK;
+}
+extern "C" {
+int gct_decode_begin(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    GCT_REQUIRE(cfg && w && d && workspace, "decode_begin: null argument");
+    return cfg->dtype == GCT_DTYPE_F32 ? decode_begin_impl<float>(cfg, w, d, workspace, workspace_bytes, stream)
+                                       : decode_begin_impl<bf16>(cfg, w, d, workspace, workspace_bytes, stream);
+}
+int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, int step_begin, int step_end,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    GCT_REQUIRE(cfg && w && d && workspace, "decode_steps: null argument");
+    return cfg->dtype == GCT_DTYPE_F32 ? decode_steps_impl<float>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream)
+                                       : decode_steps_impl<bf16>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream);
+}
+int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
+
+int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream) {
+#ifdef GCT_WITH_NCCL
+    ncclResult_t r = ncclAllReduce(grads, grads, (size_t)n, ncclFloat, ncclSum, reinterpret_cast<ncclComm_t>(nccl_comm), ST(stream));
+    if (r != ncclSuccess) GCT_FAIL(GCT_ERR_CUDA, "ncclAllReduce: %s", ncclGetErrorString(r));
+    return GCT_OK;
+#else
+    (void)nccl_comm; (void)grads; (void)n; (void)stream;
+    GCT_FAIL(GCT_ERR_UNSUPPORTED, "built without NCCL");
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation in TMEM.
+//
+//   * operands are staged in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a
+//     STAGES-deep mbarrier ring; one elected thread issues tcgen05.mma (UMMA 128 x BN x 16), and
+//     tcgen05.commit releases the ring slot / publishes the accumulator;
+//   * the 128 x BN fp32 accumulator lives in TMEM (BN columns); four epilogue warps read it back
+//     with tcgen05.ld (32 lanes x 32 columns per instruction) and apply the fused epilogue
+//     (bias / GELU / dropout / residual / dGELU / split-K accumulate) straight from registers;
+//   * either operand may be K-major (row = M/N index, K contiguous) or MN-major (row = K index),
+//     so fprop (K,K), dgrad (K,MN) and wgrad (MN,MN) all run without transposed copies.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+// (warp 2 also owns the TMEM allocation).  Shared-memory use is kept <= ~100 KB so two CTAs are
+// co-resident per SM: one CTA's epilogue overlaps the other's main loop.
+#pragma once
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include "epilogue.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a mis-programmed pipeline traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, majorness bits, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 8 consecutive columns of one row through the fused epilogue, vectorised when aligned
+template <typename T>
+__device__ __forceinline__ void epilogue_vec8(const Epilogue& e, int row, int col, const float* acc, int N, bool atomic) {
+    const bool fast = (col + 8 <= N) && ((e.ldc & 7) == 0) && !(e.flags & EPI_BIAS_ROW);
+    if (!fast) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (col + j < N) epilogue_apply<T>(e, row, col + j, acc[j], atomic);
+        return;
+    }
+    const size_t idx = (size_t)row * e.ldc + col;
+    f8 v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = acc[j] * e.alpha;
+    if (e.bias) {
+        f8 b = ld8(e.bias + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] += b.v[j];
+    }
+    if (e.flags & EPI_GELU) {
+        if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = gelu_erf(v.v[j]);
+    }
+    if (e.drop.thresh) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = drop_apply(e.drop, idx + j, v.v[j]);
+    }
+    if (e.flags & EPI_DGELU) {
+        f8 h = ld8(reinterpret_cast<const T*>(e.aux_in) + idx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] *= gelu_erf_grad(h.v[j]);
+    }
+    if (e.res32) {
+        f8 r = ld8(e.res32 + idx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] += r.v[j];
+    }
+    if (e.flags & EPI_ACCUM) {
+        if (atomic) {
+            atomicAdd(reinterpret_cast<float4*>(e.out32 + idx), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+            atomicAdd(reinterpret_cast<float4*>(e.out32 + idx + 4), make_float4(v.v[4], v.v[5], v.v[6], v.v[7]));
+        } else {
+            f8 o = ld8(e.out32 + idx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] += v.v[j];
+            st8(e.out32 + idx, o);
+        }
+        return;
+    }
+    if (e.out32) st8(e.out32 + idx, v);
+    if (e.outT) st8(reinterpret_cast<T*>(e.outT) + idx, v);
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024 /* alignment slack */;
+};
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(192)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               int kb_per_split, Epilogue epi) {
+    using L = SmemLayout<BN, A_MN, B_MN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + L::BAR_OFF;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+    uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_kb = (K + BK - 1) / BK;
+    const int kb_begin = blockIdx.z * kb_per_split;
+    const int kb_end = min(num_kb, kb_begin + kb_per_split);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)(BN < 32 ? 32 : BN))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(empty_bar(s), phase ^ 1u);
+                mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
+                const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+                if constexpr (!A_MN) {
+                    tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, kb * BK, full_bar(s));
+                }
+                if constexpr (!B_MN) {
+                    tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(s));
+                }
+                if (++s == STAGES) { s = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+            int s = 0;
+            uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                mbar_wait(full_bar(s), phase);
+                tcgen05_fence_after();
+                const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+                    const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(s));       // frees the ring slot once these MMAs have read it
+                if (++s == STAGES) { s = 0; phase ^= 1u; }
+            }
+            umma_commit(tmem_full_bar);          // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int q = warp & 3;
+        if (kb_end > kb_begin) {
+            mbar_wait(tmem_full_bar, 0);
+            tcgen05_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool atomic = gridDim.z > 1;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = n0 + c * 32 + j * 8;
+                        if (col < N) epilogue_vec8<bf16>(epi, row, col, acc + j * 8, N, atomic);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(BN < 32 ? 32 : BN))
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launcher
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapKey {
+    const void* p; uint64_t d0, d1, stride; uint32_t b0, b1;
+    bool operator==(const MapKey& o) const {
+        return p == o.p && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = (size_t)k.p;
+        h = h * 1000003u ^ k.d0; h = h * 1000003u ^ k.d1; h = h * 1000003u ^ k.stride;
+        h = h * 1000003u ^ k.b0; h = h * 1000003u ^ k.b1;
+        return h;
+    }
+};
+
+static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_bytes, uint32_t box_inner,
+                          uint32_t box_outer, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    static PFN_encodeTiled encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GCT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) GCT_FAIL(GCT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    MapKey key{ptr, inner, outer, stride_bytes, box_inner, box_outer};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return GCT_OK; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride_bytes & 15))
+        GCT_FAIL(GCT_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p pitch=%llu)",
+                 ptr, (unsigned long long)stride_bytes);
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) GCT_FAIL(GCT_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d (dims %llu x %llu pitch %llu box %u x %u)",
+                                    (int)r, (unsigned long long)inner, (unsigned long long)outer,
+                                    (unsigned long long)stride_bytes, box_inner, box_outer);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return GCT_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int split_k, const Epilogue& epi,
+                      cudaStream_t st) {
+    using L = SmemLayout<BN, A_MN, B_MN, STAGES>;
+    auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int num_kb = (K + BK - 1) / BK;
+    int kps = (num_kb + split_k - 1) / split_k;
+    split_k = (num_kb + kps - 1) / kps;
+    dim3 grid(cdiv(N, BN), cdiv(M, BM), split_k);
+    kern<<<grid, 192, L::TOTAL, st>>>(ta, tb, M, N, K, kps, epi);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
+// A: K-major -> storage [M rows, K cols] with pitch lda; MN-major -> storage [K rows, M cols] with pitch lda.
+// B: K-major -> storage [N rows, K cols] with pitch ldb; MN-major -> storage [K rows, N cols] with pitch ldb.
+static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B, bool b_mn, long long ldb, int M, int N,
+                          int K, int split_k, int bn_hint, const Epilogue& epi, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0) return GCT_OK;
+    if (split_k < 1) split_k = 1;
+    if (split_k > 1 && !(epi.flags & EPI_ACCUM)) GCT_FAIL(GCT_ERR_ARG, "split-K needs an accumulating epilogue");
+    int BN = bn_hint;
+    if (BN == 0) BN = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
+    if (b_mn && BN < 64) BN = 64;
+    CUtensorMap ta, tb;
+    if (!a_mn) GCT_TRY(get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, &ta));
+    else GCT_TRY(get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, &ta));
+    if (!b_mn) GCT_TRY(get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)BN, &tb));
+    else GCT_TRY(get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, &tb));
+
+#define GCT_TC_CASE(bn, amn, bmn, st_)                                                                   \
+    if (BN == bn && a_mn == amn && b_mn == bmn) return launch_cfg<bn, amn, bmn, st_>(ta, tb, M, N, K, split_k, epi, st);
+    GCT_TC_CASE(32, false, false, 4)
+    GCT_TC_CASE(64, false, false, 4)
+    GCT_TC_CASE(128, false, false, 3)
+    GCT_TC_CASE(256, false, false, 4)
+    GCT_TC_CASE(64, false, true, 4)
+    GCT_TC_CASE(128, false, true, 3)
+    GCT_TC_CASE(256, false, true, 4)
+    GCT_TC_CASE(64, true, true, 4)
+    GCT_TC_CASE(128, true, true, 3)
+    GCT_TC_CASE(256, true, true, 4)
+    GCT_TC_CASE(32, true, false, 4)
+    GCT_TC_CASE(64, true, false, 4)
+    GCT_TC_CASE(128, true, false, 3)
+#undef GCT_TC_CASE
+    GCT_FAIL(GCT_ERR_UNSUPPORTED, "no tcgen05 GEMM instantiation for BN=%d a_mn=%d b_mn=%d", BN, (int)a_mn, (int)b_mn);
+}
+
+}  // namespace tc

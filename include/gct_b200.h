@@ -1,0 +1,189 @@
+/* gct_b200 -- C ABI of the B200-native GCT-Plus Transformer-VAE hot path.
+ *
+ * The reference (chaoting-sun/GCT-Plus) has no FFI: its boundary is the Python call surface
+ *   Model/build_model.py:79-116, Model/forward_propagation1.py:4-48, Model/{vaetf,cvaetf}.py
+ *   (forward / encode / decode), Train/trainer1.py:19-30,71-157, Inference/sampling_tool.py:140-184.
+ * This header is the C-ABI those Python entry points bind to in gct_plus_b200 (ctypes); each
+ * function names the reference code it replaces.  See INTEGRATION.md for the binding stubs.
+ *
+ * Conventions
+ *   - every pointer is a raw CUDA device pointer unless the name ends in _host;
+ *   - the library never allocates or frees device memory: parameters, activations, KV cache and
+ *     scratch all live in caller-owned buffers (PyTorch tensors) sized by the *_bytes queries;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no hidden syncs, so the
+ *     calls can be captured into CUDA graphs;
+ *   - return 0 on success, negative on error; gct_last_error() returns a thread-local message;
+ *   - dtype 0 = fp32 parity tier (SIMT FFMA GEMMs), 1 = bf16 operands / fp32 accumulate (tcgen05).
+ */
+#ifndef GCT_B200_H
+#define GCT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCT_DTYPE_F32 0
+#define GCT_DTYPE_BF16 1
+
+/* parameter slots of the flat parameter buffer (element offsets are supplied by the host) */
+#define GCT_SLOT_ENC_EMB 0      /* encoder.embed_sentence.embed.weight [Vs,d]      modules.py:101-110 */
+#define GCT_SLOT_ENC_C2E_W 1    /* encoder.embed_cond2enc.weight [nc*d,nc]         cvaetf.py:25-26   */
+#define GCT_SLOT_ENC_C2E_B 2
+#define GCT_SLOT_ENC_NORM_A 3   /* encoder.norm.alpha                               modules.py:80-95  */
+#define GCT_SLOT_ENC_NORM_B 4
+#define GCT_SLOT_MULV_W 5       /* fc_mu.weight ; fc_log_var.weight  [2*lat,d]      sublayers.py:7-26 */
+#define GCT_SLOT_MULV_B 6
+#define GCT_SLOT_DEC_EMB 7      /* decoder.embed.embed.weight [Vt,d] */
+#define GCT_SLOT_DEC_C2D_W 8    /* decoder.embed_cond2dec.*                         cvaetf.py:86-87   */
+#define GCT_SLOT_DEC_C2D_B 9
+#define GCT_SLOT_DEC_C2L_W 10   /* decoder.embed_cond2lat.*                         cvaetf.py:88-89   */
+#define GCT_SLOT_DEC_C2L_B 11
+#define GCT_SLOT_FCZ_W 12       /* decoder.fc_z.weight [d,lat]                      cvaetf.py:91      */
+#define GCT_SLOT_FCZ_B 13
+#define GCT_SLOT_DEC_NORM_A 14
+#define GCT_SLOT_DEC_NORM_B 15
+#define GCT_SLOT_OUT_W 16       /* out.weight [Vt,d]                                cvaetf.py:156     */
+#define GCT_SLOT_OUT_B 17
+#define GCT_SLOT_PROP_W 18      /* prop_fc.weight [1,Vt]                            cvaetf.py:155     */
+#define GCT_SLOT_PROP_B 19
+#define GCT_SLOT_ENC_PE 20      /* encoder.pe.pe [200,d] (buffer)                   modules.py:116-131*/
+#define GCT_SLOT_DEC_PE 21
+#define GCT_NUM_GLOBAL_SLOTS 22
+/* encoder layer l: GCT_NUM_GLOBAL_SLOTS + 12*l + {N1A,N1B,QKV_W,QKV_B,O_W,O_B,N2A,N2B,F1_W,F1_B,F2_W,F2_B}
+ * decoder layer l: GCT_NUM_GLOBAL_SLOTS + 12*N + 20*l +
+ *   {N1A,N1B,QKV_W,QKV_B,O1_W,O1_B,N2A,N2B,Q2_W,Q2_B,KV2_W,KV2_B,O2_W,O2_B,N3A,N3B,F1_W,F1_B,F2_W,F2_B}
+ * QKV_W is [3d,d] = q_linear ; k_linear ; v_linear rows, KV2_W is [2d,d] = k_linear ; v_linear. */
+#define GCT_ENC_LAYER_SLOTS 12
+#define GCT_DEC_LAYER_SLOTS 20
+
+typedef struct {
+    int32_t src_vocab, trg_vocab;
+    int32_t n_layers, d_model, d_ff, heads, latent_dim;
+    int32_t nconds;            /* number of property tokens (0 for vaetf / scavaetf)            */
+    int32_t use_cond2dec;      /* cond tokens prepended to the decoder input  (cvaetf.py:103-105) */
+    int32_t use_cond2lat;      /* cond tokens prepended to the decoder memory (cvaetf.py:107-116) */
+    int32_t dtype;             /* GCT_DTYPE_*                                                   */
+    int32_t pad_id;
+    float dropout;             /* p of every nn.Dropout on the path; applied only when train!=0 */
+} gct_config_t;
+
+typedef struct {
+    const float* params_f32;       /* flat fp32 master parameters                                 */
+    const void* params_bf16;       /* flat bf16 shadow with identical offsets (dtype bf16) or NULL */
+    float* grads_f32;              /* flat fp32 gradient buffer (backward accumulates into it)     */
+    const int64_t* slot_offsets_host;   /* HOST array [gct_num_slots()] of element offsets, -1 = absent */
+} gct_weights_t;
+
+/* ---- library queries ------------------------------------------------------------------- */
+const char* gct_last_error(void);
+int gct_version(void);
+int gct_sm(void);                                   /* compiled SM target: must be 100 */
+int gct_num_slots(int n_layers);
+int gct_set_gemm_backend(int simt_only);            /* test hook: 1 routes bf16 GEMMs through the SIMT kernel */
+
+/* ---- operator level (used by the unit tests and by the Python autograd wrappers) -------- */
+/* Norm: Model/modules.py:80-95.  y (dtype T) [, y32] = alpha*(x-mean)/(std+eps)+bias ; x fp32 [rows,d] */
+int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d,
+                 int dtype, void* stream);
+int gct_norm_bwd(const float* x, const float* alpha, const float* dy, const float* add, float* dx, float* dalpha,
+                 float* dbias, int rows, int d, void* stream);
+/* Generic GEMM C[M,N] = A(m,k)*B(n,k) (+bias, GELU, residual): nn.Linear of Model/sublayers.py:54-88.
+ * a_mn/b_mn: 0 = K-major storage ([M|N rows, K cols]), 1 = MN-major ([K rows, M|N cols]).
+ * flags: 1 GELU, 2 dGELU(aux), 4 accumulate into out32.  dtype 1 -> tcgen05, 0 -> SIMT fp32. */
+int gct_gemm(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
+             const float* bias, const float* res32, const void* aux_in, void* aux_out, float* out32, void* outT,
+             int ldc, int flags, int split_k, int bn_hint, int dtype, void* stream);
+/* attention: Model/sublayers.py:29-41.  q/k/v [B,L,ld] with head h at column 64*h; mask bytes. */
+int gct_attention_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
+                      int64_t mask_bstride, int mask_rstride, void* out, int ldo, float* lse, float* probs, int B,
+                      int H, int Lq, int Lk, int dtype, void* stream);
+int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
+                      int64_t mask_bstride, int mask_rstride, const float* lse, const void* dout, int lddo, void* dq,
+                      int lddq, void* dk, int lddk, void* dv, int lddv, int B, int H, int Lq, int Lk, int dtype,
+                      void* stream);
+/* masks: Model/modules.py:33-58 as byte arrays */
+int gct_src_mask(const int64_t* tok, int B, int L, int nc, int pad, uint8_t* out, void* stream);
+int gct_trg_mask(const int64_t* tok, int B, int T, int nc_cond2dec, int pad, uint8_t* out, void* stream);
+int gct_mask_cast(const void* in, int elem_size, int64_t n, uint8_t* out, void* stream);
+int gct_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+int gct_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);
+
+/* ---- loss: Train/trainer1.py:19-30 -------------------------------------------------------- */
+/* out4 = {loss, RCE_mol, RCE_prop(=0), KLD}.  When dlogits/dmu/dlv are non-null they receive
+ * d loss / d{logits,mu,log_var} (scaled by gscale).  scratch: gct_loss_scratch_bytes(). */
+size_t gct_loss_scratch_bytes(int64_t rows, int64_t n_latent);
+int gct_loss_fwd_bwd(const float* logits, int ld, int V, const int64_t* target, int64_t rows, int pad_id,
+                     const float* mu, const float* log_var, int64_t n_latent, float beta, float gscale, float* out4,
+                     float* dlogits, float* dmu, float* dlv, void* scratch, void* stream);
+
+/* ---- whole-model forward / backward: Vaetf.forward / Cvaetf.forward (+ .encode/.decode) ------ */
+typedef struct {
+    const int64_t* src;        /* [B,S]                                  */
+    const int64_t* trg;        /* [B,T]  decoder input (already [:, :-1]) */
+    const uint8_t* src_mask;   /* [B,Se] key mask, Se = nconds+S          */
+    const uint8_t* trg_mask;   /* [B,Ld,Ld] dense mask, Ld = T (+nconds if cond2dec) */
+    const float* econds;       /* [B,nconds] or NULL                      */
+    const float* dconds;       /* [B,nconds] or NULL                      */
+    const float* eps;          /* [B,Se,lat] N(0,1) draw for z, or NULL for z = mu */
+    const float* z_in;         /* decode-only: latent [B,Se,lat] supplied by the caller */
+    int32_t B, S, T;
+    int32_t train;             /* 1: dropout active                        */
+    uint32_t seed;             /* dropout seed of this step                */
+    int32_t run_encoder, run_decoder;
+    float* logits;             /* [B,Ld,Vt] fp32                           */
+    float* mu; float* log_var; float* z;      /* [B,Se,lat] fp32           */
+    float* enc_attn; float* dec_attn1; float* dec_attn2;   /* optional get_attn outputs [N,B,H,Lq,Lk] */
+} gct_io_t;
+
+size_t gct_forward_workspace_bytes(const gct_config_t* cfg, int B, int S, int T);
+int gct_forward(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* backward of the forward that last filled `workspace`; gradients of the four outputs may be NULL */
+size_t gct_backward_scratch_bytes(const gct_config_t* cfg, int B, int S, int T);
+int gct_backward(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, const float* dlogits,
+                 const float* dmu, const float* dlog_var, const float* dz, void* workspace, size_t workspace_bytes,
+                 void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- optimiser: Adam + the trainer's LR rule (Train/trainer1.py:112-127, train1.py:116-119) --- */
+int gct_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow, int64_t n,
+                  int step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+double gct_noam_lr(int64_t step, int d_model, int64_t warmup);
+
+/* ---- KV-cached sampler: Sampling.decode, Inference/sampling_tool.py:140-184 ------------------ */
+typedef struct {
+    int32_t B;                 /* sequences in this batch                                  */
+    int32_t Lz;                /* latent length (before cond2lat tokens)                   */
+    int32_t max_len;           /* capacity of ys per row: prefix + generated tokens        */
+    int32_t prefix_len;        /* tokens already in ys (1 = <sos>, or 2+len(scaffold))      */
+    int32_t greedy;            /* 1 greedy (torch.max), 0 multinomial                       */
+    int32_t eos_id;
+    uint32_t seed;             /* multinomial RNG seed when `uniforms` is NULL              */
+    const float* zs;           /* [B,Lz,lat] fp32                                           */
+    const uint8_t* src_mask;   /* [B,Lz] latent key mask                                    */
+    const float* dconds;       /* [B,nconds] or NULL                                        */
+    const float* uniforms;     /* optional [max_steps,B] U(0,1) numbers for multinomial     */
+    int64_t* ys;               /* [B,max_len] int64, prefix filled by the caller            */
+    int32_t* status;           /* device int[2]: {#rows that emitted <eos>, first step at which all had} */
+} gct_decode_t;
+
+size_t gct_decode_workspace_bytes(const gct_config_t* cfg, int B, int Lz, int max_len);
+/* projects the latent to the cross-attention K/V of every layer, resets the caches, consumes the prefix */
+int gct_decode_begin(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* runs decode steps [step_begin, step_end): step i reads ys[:, prefix_len-1+i] and writes ys[:, prefix_len+i] */
+int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, int step_begin,
+                     int step_end, void* workspace, size_t workspace_bytes, void* stream);
+/* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
+int gct_decode_launches_per_step(const gct_config_t* cfg);
+
+/* ---- data-parallel gradient exchange (train1.py:111-112 DDP) --------------------------------- */
+/* in-place sum over ranks through NCCL; comm is an ncclComm_t created by the host.  Returns
+ * GCT_ERR_UNSUPPORTED if the library was built without NCCL (the host then uses torch.distributed). */
+int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCT_B200_H */

@@ -1,0 +1,61 @@
+"""tcgen05 GEMM (gemm_tc.cuh) against torch fp32 matmul on the same bf16-rounded operands.
+Tolerance 2e-3 relative to the output scale: only the fp32 accumulation order differs."""
+import pytest
+import torch
+
+from gpu_common import DEV, gemm
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops(M, N, K, a_mn, b_mn, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    B = torch.randn(N, K, generator=g).to(DEV).bfloat16()
+    ref = A.float() @ B.float().t()
+    As = A.t().contiguous() if a_mn else A
+    Bs = B.t().contiguous() if b_mn else B
+    return As, Bs, ref
+
+
+def _close(out, ref, tol=2e-3):
+    err = float((out.float() - ref).abs().max() / ref.abs().max())
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 0), (256, 128, 128, 0), (512, 1536, 512, 0), (300, 96, 200, 64),
+                                      (512, 512, 2048, 32), (1024, 256, 512, 256), (384, 64, 320, 64)])
+def test_majorness(a_mn, b_mn, M, N, K, bn):
+    if b_mn and bn == 32:
+        bn = 64
+    As, Bs, ref = _ops(M, N, K, a_mn, b_mn)
+    out, _, _ = gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, bn=bn)
+    _close(out, ref)
+
+
+def test_small_vocab_tile():
+    As, Bs, ref = _ops(512, 28, 512, False, False, seed=3)      # N = 28 < BN = 32, ldc = 28
+    out, _, _ = gemm(As, Bs, 512, 28, 512)
+    _close(out, ref)
+
+
+def test_epilogue_bias_gelu_residual():
+    M, N, K = 256, 256, 128
+    As, Bs, ref = _ops(M, N, K, False, False, seed=1)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    out, _, _ = gemm(As, Bs, M, N, K, bias=bias, res=res)
+    _close(out, ref + bias + res)
+    out2, outT, aux = gemm(As, Bs, M, N, K, bias=bias, flags=1, want_T=True)
+    pre = ref + bias
+    _close(aux, pre, 1e-2)
+    _close(outT, torch.nn.functional.gelu(pre), 1e-2)
+
+
+def test_split_k_accumulate():
+    M, N, K = 256, 512, 4096
+    As, Bs, ref = _ops(M, N, K, True, True, seed=2)
+    acc = torch.ones((M, N), device=DEV)
+    gemm(As, Bs, M, N, K, a_mn=True, b_mn=True, flags=4, split_k=8, out32=acc)
+    _close(acc, ref + 1.0)
