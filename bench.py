@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py -- sampled SMILES/s (BASELINE cfg 2) and train tokens/s (cfg 3 / cfg 4) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
+  * sampling: one 512-draw batch decoded to max_strlen=100 (99 KV-cached multinomial steps), vaetf;
+  * training (reported under "train"): one optimiser step (fwd + loss + bwd [+ allreduce] + Adam),
+    pvaetf B=512 S=78 T=79 at N=1 (cfg 3), pscavaetf B=512/GPU S=98 T=99 data-parallel at N>1 (cfg 4).
+`value` is timed with inputs resident in HBM; `e2e` goes through the public API
+(sampler.sample_smiles with pinned HOST latents in, Python strings out).
+`--impl reference` times the CPU oracle port of the reference's un-cached sampler on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ARCH = dict(N=6, d_model=512, dff=2048, h=8, latent_dim=128)
+VOCAB = 32
+MAX_STRLEN = 100
+BATCH = 512
+ITOS = ["<unk>", "<pad>", "<sos>", "<eos>", "<sep>"] + list("CcNnOoSsFIBrl()[]=#123456+-H@/")[:27]
+
+
+class _Vocab:
+    def __init__(self):
+        self.itos = ITOS
+        self.stoi = {t: i for i, t in enumerate(ITOS)}
+
+    def __len__(self):
+        return len(self.itos)
+
+
+class _Field:
+    batch_first = True
+
+    def __init__(self):
+        self.vocab = _Vocab()
+
+    def tokenize(self, smi):
+        return list(smi)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+def toklen_data():
+    """Stand-in for the absent toklen_list.csv: round(N(35,7^2)) clipped to [13,55] (BASELINE.md cfg 2)."""
+    rng = np.random.RandomState(7)
+    return np.clip(np.rint(rng.normal(35, 7, size=20000)), 13, 55)
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.p, self.rows = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =============================================================================================
+# our arm
+# =============================================================================================
+def build_sampler(dev, dtype="bf16"):
+    from gct_plus_b200.Model import Vaetf
+    from gct_plus_b200.Inference.sampling_tool import VaetfSampling
+    torch.manual_seed(0)
+    model = Vaetf(VOCAB, VOCAB, dropout=0.1, nconds=0, compute_dtype=dtype, **ARCH).to(dev).eval()
+    kwargs = dict(top_k=None, latent_dim=ARCH["latent_dim"], max_strlen=MAX_STRLEN, use_cond2dec=False, decode_algo="multinomial",
+                  n_jobs=1, toklen_data=toklen_data(), cond_dim=0, scaler=None, device=dev, SRC=_Field(), TRG=_Field(),
+                  sync_every=33, latent_bucket=64)
+    return VaetfSampling(model, kwargs)
+
+
+def sample_inputs(sampler, n_batches, seed, pinned=True):
+    """Per-batch latent lengths and N(0,1) latents on the HOST (pinned), like the reference's sample_z."""
+    np.random.seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_batches):
+        toklen = sampler.sample_toklen(BATCH)
+        Lz = int(max(toklen))
+        zs = torch.randn(BATCH, Lz, ARCH["latent_dim"], generator=g)
+        out.append((toklen, zs.pin_memory() if pinned else zs))
+    return out
+
+
+def decode_alg_bytes(cfg_layers, B, Sm, steps, esize, d=512, dff=2048):
+    """sum over steps of KV read + KV write + weight read."""
+    kv = sum(cfg_layers * B * (2 * (t + 1) * d + 2 * Sm * d) * esize for t in range(steps))
+    kvw = steps * cfg_layers * B * 2 * d * esize
+    wr = steps * cfg_layers * (8 * d * d + 2 * d * dff) * esize
+    return kv + kvw + wr
+
+
+def time_decode_attention(sampler, dev, steps, Sm):
+    """Roofline leg: the KV-cache attention kernel alone, one launch per (step, layer), self-attention shapes of a real
+    decode (n_cached = t), caches of all layers in rotation (6 x 2 x 52 MB bf16 > L2).  CUDA events on the launch stream."""
+    import gct_plus_b200._lib as L
+    lib = L.lib()
+    d, H, N, B = 512, 8, 6, BATCH
+    Lmax = steps + 1
+    kc = torch.randn(N, B, Lmax, d, device=dev).bfloat16()
+    vc = torch.randn(N, B, Lmax, d, device=dev).bfloat16()
+    qkv = torch.randn(B, 3 * d, device=dev).bfloat16()
+    out = torch.empty(B, d, device=dev, dtype=torch.bfloat16)
+    valid = torch.ones(B, Lmax, device=dev, dtype=torch.uint8)
+    st = L.stream_ptr()
+
+    def launch(l, t):
+        L.check(lib.gct_decode_attention(L.ptr(qkv), 3 * d, qkv[:, d:].data_ptr(), qkv[:, 2 * d:].data_ptr(), 3 * d,
+                                         kc[l].data_ptr(), vc[l].data_ptr(), Lmax * d, d, t, L.ptr(valid), Lmax, L.ptr(out), d, B, H,
+                                         L.DTYPE_BF16, st))
+    for t in (10, 50, 90):
+        for l in range(N):
+            launch(l, t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        for l in range(N):
+            launch(l, t)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = steps * N
+    # algorithmic bytes of one launch at step t: read t cached K and V rows + this step's q,k,v, write k,v rows and the output
+    alg = sum(B * (2 * t * d + 3 * d + 2 * d + d) * 2 for t in range(steps)) * N
+    return alg / launches, ms / launches, launches
+
+
+def run_sampling(args, rank, world, dev):
+    import gct_plus_b200._lib as L
+    sampler = build_sampler(dev)
+    steps = MAX_STRLEN - 1
+    K, W = args.steps, args.warmup
+    inputs = sample_inputs(sampler, K + W, seed=1000 + rank)
+    # ---- device-resident leg (value) ----
+    dev_in = []
+    for toklen, zs in inputs:
+        Lz = zs.size(1)
+        mask = (torch.arange(Lz).expand(BATCH, 1, Lz) < torch.LongTensor(toklen).view(BATCH, 1, 1))
+        dev_in.append((zs.to(dev), mask.to(dev)))
+    ys0 = torch.full((BATCH, 1), 2, dtype=torch.long, device=dev)
+    torch.cuda.synchronize()
+    for i in range(W):
+        sampler.decode(zs=dev_in[i][0], ys=ys0, src_mask=dev_in[i][1])
+    clocks = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else rank)
+    barrier(world)
+    torch.cuda.synchronize()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_steps_run = 0
+    for i in range(W, W + K):
+        sampler.decode(zs=dev_in[i][0], ys=ys0, src_mask=dev_in[i][1])
+        n_steps_run += sampler.last_decode_steps
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ck = clocks.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    value = world * K * BATCH / (ms / 1e3)
+    # ---- end-to-end leg through the public API: pinned host latents in, strings out ----
+    for i in range(min(W, 2)):
+        sampler.sample_smiles(BATCH, zs=inputs[i][1], toklen=list(inputs[i][0]))
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_out = 0
+    for i in range(W, W + K):
+        smiles, _, _ = sampler.sample_smiles(BATCH, zs=inputs[i][1], toklen=list(inputs[i][0]))
+        n_out += len(smiles)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    assert n_out == K * BATCH
+    h2d = int(np.mean([z.numel() * 4 + BATCH * z.size(1) + BATCH * 8 for _, z in inputs[W:]]))
+    d2h = BATCH * MAX_STRLEN * 8
+    cfg = sampler.model._cfg()
+    per_step = L.lib().gct_decode_launches_per_step(cfg)
+    launches = K * (9 + n_steps_run // max(K, 1) * per_step)
+    Sm_mean = float(np.mean([z.size(1) for _, z in inputs[W:]]))
+    return dict(value=value, ms_per_step=ms / K, e2e_value=world * K * BATCH / (t_e2e / 1e3), h2d=h2d, d2h=d2h, clocks=ck,
+                launches=launches, sampler=sampler, Sm_mean=Sm_mean, decode_steps=n_steps_run / K)
+
+
+def make_train_batch(B, S, nc, scaffold, seed, dev=None, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(int(S * 0.6), S + 1, (B,), generator=g)
+    lens[0] = S
+    toks = torch.randint(5, VOCAB, (B, S), generator=g)
+    if scaffold:
+        toks[:, scaffold] = 4
+    ar = torch.arange(S)[None, :]
+    src = torch.where(ar < lens[:, None], toks, torch.ones_like(toks))
+    trg = torch.ones(B, S + 2, dtype=torch.long)
+    trg[:, 0] = 2
+    trg[:, 1:S + 1] = src
+    trg[torch.arange(B), lens + 1] = 3
+    batch = {"src": src, "trg": trg}
+    if nc:
+        batch["econds"] = torch.randn(B, nc, generator=g)
+        batch["dconds"] = batch["econds"].clone()
+    if pinned:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if dev is not None:
+        batch = {k: v.to(dev) for k, v in batch.items()}
+    return batch
+
+
+def run_training(args, rank, world, dev):
+    from gct_plus_b200.Model import Cvaetf
+    from gct_plus_b200.Train.trainer1 import FusedTrainer
+    from oracle.gct_oracle import ModelCfg, flops_forward
+    torch.manual_seed(0)
+    if world == 1:
+        mt, S, sca, name = "pvaetf", 78, 0, "cfg3 pvaetf B=512 S=78 T=79"
+    else:
+        mt, S, sca, name = "pscavaetf", 98, 19, "cfg4 pscavaetf B=512/GPU S=98 T=99 DP"
+    B, nc = args.train_batch, 3
+    model = Cvaetf(VOCAB, VOCAB, dropout=0.1, nconds=nc, use_cond2lat=True, compute_dtype="bf16", **ARCH).to(dev).train()
+    tr = FusedTrainer(model, mt, pad_id=1, lr=1e-4, warmup=8000)
+    K, W = min(args.steps, args.train_steps), args.warmup
+    host = [make_train_batch(B, S, nc, sca, 50 + rank * 1000 + i, pinned=True) for i in range(4)]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    tokens = [int((b["trg"][:, 1:] != 1).sum()) for b in host]
+    for i in range(W):
+        tr.step(devb[i % 4], 0.5)
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ntok = 0
+    for i in range(K):
+        tr.step(devb[i % 4], 0.5)
+        ntok += tokens[i % 4]
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    # e2e: pinned host batch -> device each step, loss read back each step
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % 4].items()}
+        tr.step(b, 0.5)
+        tr.read_losses()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    cfg = ModelCfg(model_type=mt, src_vocab=VOCAB, trg_vocab=VOCAB, nconds=nc, use_cond2lat=True)
+    flops = 3.0 * flops_forward(cfg, B, S, S + 1)
+    _, tf_peak, src = peaks()
+    loss = tr.read_losses()[0]
+    return {"workload": name, "tokens_per_sec": world * ntok / (ms / 1e3), "padded_tokens_per_sec": world * K * B * (S + 1) / (ms / 1e3),
+            "ms_per_step": ms / K, "steps": K, "e2e_tokens_per_sec": world * ntok / (t_e2e / 1e3),
+            "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host[0].values())), "d2h_bytes_per_step": 16,
+            "algorithmic_tflop_per_step": flops / 1e12, "tensor_frac_of_sustained_peak": flops / (ms / K / 1e3) / (tf_peak * 1e12),
+            "peak_source": src, "dtype": "bf16", "loss_finite": bool(np.isfinite(loss))}
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def max_over_ranks(v, world, dev):
+    if world == 1:
+        return v
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+# =============================================================================================
+# CPU arm: the oracle port of the reference's un-cached Sampling.decode on the host cores
+# =============================================================================================
+def cpu_sampler_setup():
+    from oracle import gct_oracle as O
+    from gct_plus_b200.Model import Vaetf          # only to reproduce the reference's init (no compute on this path)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in Vaetf(VOCAB, VOCAB, dropout=0.1, nconds=0, **ARCH).state_dict().items()}
+    cfg = O.ModelCfg(model_type="vaetf", src_vocab=VOCAB, trg_vocab=VOCAB)
+    return O, sd, cfg
+
+
+def cpu_decode(O, sd, cfg, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    toklen = np.clip(np.rint(rng.normal(35, 7, size=n)), 13, 55).astype(int)
+    Lz = int(toklen.max())
+    zs = torch.randn(n, Lz, ARCH["latent_dim"], generator=g)
+    mask = torch.arange(Lz).expand(n, 1, Lz) < torch.LongTensor(toklen).view(n, 1, 1)
+    ys0 = torch.full((n, 1), 2, dtype=torch.long)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ys = O.sampling_decode(sd, cfg, zs, ys0, mask, max_strlen=MAX_STRLEN, algo="multinomial")
+    dt = time.perf_counter() - t0
+    [O.id_to_smi(r.tolist(), ITOS) for r in ys]
+    return dt, ys.size(1) - 1
+
+
+def cpu_baseline(budget_s=20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, sd, cfg = cpu_sampler_setup()
+    dt1, _ = cpu_decode(O, sd, cfg, 2, 1)               # calibration + warm-up
+    n = int(max(2, min(64, budget_s / max(dt1 / 2, 1e-3) * 0.6)))
+    dt, steps = cpu_decode(O, sd, cfg, n, 2)
+    return {"value": n / dt, "unit": "SMILES/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port of the reference's un-cached multinomial Sampling.decode, one batch of {n} latents, "
+                      f"{steps} steps (max_strlen {MAX_STRLEN}), fp32, torch {torch.__version__} CPU with {cores} threads"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O, sd, cfg = cpu_sampler_setup()
+    K, W = args.steps, args.warmup
+    dt1, _ = cpu_decode(O, sd, cfg, 1, 1)
+    n = int(max(1, min(32, 150.0 / (K + W) / max(dt1, 1e-3) * 0.7)))
+    for i in range(W):
+        cpu_decode(O, sd, cfg, n, 10 + i)
+    t0 = time.perf_counter()
+    for i in range(K):
+        cpu_decode(O, sd, cfg, n, 100 + i)
+    dt = time.perf_counter() - t0
+    v = K * n / dt
+    sample = (f"each step = oracle port of the reference's un-cached multinomial Sampling.decode on {n} latent draw(s), "
+              f"{MAX_STRLEN - 1} steps, fp32 CPU, {cores} threads")
+    print(json.dumps({"impl": "reference", "metric": "sampled_smiles_per_sec", "value": v, "unit": "SMILES/s", "n_gpus": args.gpus,
+                      "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "cfg2 vaetf unconditioned sampling, multinomial, max_strlen 100 (CPU, bounded sample)",
+                                 "batch": n},
+                      "cpu_baseline": {"value": v, "unit": "SMILES/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": "SMILES/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=59)       # 59 x 512 = 30 208 latent draws (cfg 2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--train-batch", type=int, default=512)
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (gct_plus_b200 has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    hbm_peak, tf_peak, peak_src = peaks()
+    s = run_sampling(args, rank, world, dev)
+    steps = MAX_STRLEN - 1
+    alg_per_launch, ms_per_launch, nl = time_decode_attention(s["sampler"], dev, steps, s["Sm_mean"])
+    achieved = alg_per_launch / (ms_per_launch / 1e3) / 1e9
+    total_alg = decode_alg_bytes(6, BATCH, s["Sm_mean"], steps, 2)
+    train = None
+    if not args.no_train:
+        s.pop("sampler")
+        torch.cuda.empty_cache()
+        train = run_training(args, rank, world, dev)
+    if rank == 0:
+        cpu = None if args.no_cpu else cpu_baseline()
+        line = {"metric": "sampled_smiles_per_sec", "value": s["value"], "unit": "SMILES/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "cfg2 vaetf unconditioned sampling: 512-draw batches, KV-cached multinomial decode, max_strlen 100 "
+                                       "(99 steps/batch), latent lengths round(N(35,7^2)) in [13,55], random-init weights (no <eos> early stop)",
+                           "batch": BATCH, "d_model": 512, "layers": "6+6", "heads": 8, "latent": 128, "vocab": VOCAB,
+                           "l2": "working set (KV cache 0.9 GB per batch) larger than L2, no flush needed",
+                           "sharding": f"{world} independent rank(s), no data-path collective"},
+                "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"]},
+                "gpu_launches": s["launches"], "clocks": s["clocks"],
+                "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",
+                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                             "peak_source": peak_src, "launches_timed": nl, "us_per_launch": ms_per_launch * 1e3,
+                             "whole_decode": {"algorithmic_bytes_per_batch": total_alg,
+                                              "achieved_GBps": total_alg / (s["ms_per_step"] / 1e3) / 1e9,
+                                              "frac": total_alg / (s["ms_per_step"] / 1e3) / 1e9 / hbm_peak}},
+                "cpu_baseline": cpu, "train": train}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,8 @@ _PROTOS = {
     "gct_decode_steps": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), C.c_int, C.c_int,
                                    vp, sz, vp]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
+    "gct_decode_attention": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, vp]),
     "gct_allreduce_grads": (C.c_int, [vp, vp, i64, vp]),
 }
 

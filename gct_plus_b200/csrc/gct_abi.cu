@@ -282,6 +282,20 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
 }
 int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
 
+int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,
+                         int64_t cache_bstride, int pitch, int n_cached, const uint8_t* key_valid, int kv_stride, void* out,
+                         int ldo, int B, int H, int dtype, void* stream) {
+    GCT_REQUIRE(H >= 1 && H <= 8, "decode attention: H=%d outside [1,8]", H);
+    DecAttnParams p;
+    p.q = q; p.ldq = ldq; p.knew = knew; p.vnew = vnew; p.ldnew = ldnew; p.kcache = kcache; p.vcache = vcache;
+    p.cache_bstride = cache_bstride; p.pitch = pitch; p.n_cached = n_cached; p.key_valid = key_valid; p.kv_stride = kv_stride;
+    p.out = out; p.ldo = ldo; p.H = H; p.scale = 0.125f;
+    if (dtype == GCT_DTYPE_F32) decode_attn_kernel<float><<<B, H * 32, 0, ST(stream)>>>(p);
+    else decode_attn_kernel<bf16><<<B, H * 32, 0, ST(stream)>>>(p);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
 int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream) {
 #ifdef GCT_WITH_NCCL
     ncclResult_t r = ncclAllReduce(grads, grads, (size_t)n, ncclFloat, ncclSum, reinterpret_cast<ncclComm_t>(nccl_comm), ST(stream));

@@ -387,6 +387,7 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
     GCT_TC_CASE(32, true, false, 4)
     GCT_TC_CASE(64, true, false, 4)
     GCT_TC_CASE(128, true, false, 3)
+    GCT_TC_CASE(256, true, false, 4)
 #undef GCT_TC_CASE
     GCT_FAIL(GCT_ERR_UNSUPPORTED, "no tcgen05 GEMM instantiation for BN=%d a_mn=%d b_mn=%d", BN, (int)a_mn, (int)b_mn);
 }
