@@ -363,9 +363,11 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
     if (M <= 0 || N <= 0 || K <= 0) return GCT_OK;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && !(epi.flags & EPI_ACCUM)) GCT_FAIL(GCT_ERR_ARG, "split-K needs an accumulating epilogue");
-    int BN = bn_hint;
+    // bn_hint = BN + 1000*STAGES (either part may be 0 = choose here)
+    int BN = bn_hint % 1000, ST = bn_hint / 1000;
     if (BN == 0) BN = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
     if (b_mn && BN < 64) BN = 64;
+    if (ST == 0) ST = (BN == 128) ? 3 : 4;
     CUtensorMap ta, tb;
     if (!a_mn) GCT_TRY(get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, &ta));
     else GCT_TRY(get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, &ta));
@@ -373,23 +375,30 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
     else GCT_TRY(get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, &tb));
 
 #define GCT_TC_CASE(bn, amn, bmn, st_)                                                                   \
-    if (BN == bn && a_mn == amn && b_mn == bmn) return launch_cfg<bn, amn, bmn, st_>(ta, tb, M, N, K, split_k, epi, st);
+    if (BN == bn && a_mn == amn && b_mn == bmn && ST == st_) return launch_cfg<bn, amn, bmn, st_>(ta, tb, M, N, K, split_k, epi, st);
+    GCT_TC_CASE(16, false, false, 4)
+    GCT_TC_CASE(16, false, false, 8)
     GCT_TC_CASE(32, false, false, 4)
+    GCT_TC_CASE(32, false, false, 8)
     GCT_TC_CASE(64, false, false, 4)
+    GCT_TC_CASE(64, false, false, 8)
     GCT_TC_CASE(128, false, false, 3)
+    GCT_TC_CASE(128, false, false, 6)
     GCT_TC_CASE(256, false, false, 4)
     GCT_TC_CASE(64, false, true, 4)
     GCT_TC_CASE(128, false, true, 3)
+    GCT_TC_CASE(128, false, true, 6)
     GCT_TC_CASE(256, false, true, 4)
     GCT_TC_CASE(64, true, true, 4)
     GCT_TC_CASE(128, true, true, 3)
+    GCT_TC_CASE(128, true, true, 6)
     GCT_TC_CASE(256, true, true, 4)
     GCT_TC_CASE(32, true, false, 4)
     GCT_TC_CASE(64, true, false, 4)
     GCT_TC_CASE(128, true, false, 3)
     GCT_TC_CASE(256, true, false, 4)
 #undef GCT_TC_CASE
-    GCT_FAIL(GCT_ERR_UNSUPPORTED, "no tcgen05 GEMM instantiation for BN=%d a_mn=%d b_mn=%d", BN, (int)a_mn, (int)b_mn);
+    GCT_FAIL(GCT_ERR_UNSUPPORTED, "no tcgen05 GEMM instantiation for BN=%d stages=%d a_mn=%d b_mn=%d", BN, ST, (int)a_mn, (int)b_mn);
 }
 
 }  // namespace tc
