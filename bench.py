@@ -156,21 +156,25 @@ def time_decode_attention(sampler, dev, steps, Sm):
     qkv = torch.randn(B, 3 * d, device=dev).bfloat16()
     out = torch.empty(B, d, device=dev, dtype=torch.bfloat16)
     valid = torch.ones(B, Lmax, device=dev, dtype=torch.uint8)
-    st = L.stream_ptr()
-
     def launch(l, t):
         L.check(lib.gct_decode_attention(L.ptr(qkv), 3 * d, qkv[:, d:].data_ptr(), qkv[:, 2 * d:].data_ptr(), 3 * d,
                                          kc[l].data_ptr(), vc[l].data_ptr(), Lmax * d, d, t, L.ptr(valid), Lmax, L.ptr(out), d, B, H,
-                                         L.DTYPE_BF16, st))
+                                         L.DTYPE_BF16, L.stream_ptr()))
     for t in (10, 50, 90):
         for l in range(N):
             launch(l, t)
     torch.cuda.synchronize()
+    # replayed from a CUDA graph so that the python/ctypes launch cost does not pace the GPU
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for t in range(steps):
+            for l in range(N):
+                launch(l, t)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(steps):
-        for l in range(N):
-            launch(l, t)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -395,11 +399,14 @@ def main():
     ap.add_argument("--steps", type=int, default=59)       # 59 x 512 = 30 208 latent draws (cfg 2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=512, help="latent draws per sample_smiles call")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-batch", type=int, default=512)
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    global BATCH
+    BATCH = args.batch
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

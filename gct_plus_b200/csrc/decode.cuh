@@ -4,6 +4,7 @@
 // HBM-bound: each (batch, head) streams its K/V rows once with 16-byte loads.
 #pragma once
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 struct DecAttnParams {
     const void* q; int ldq;                  // [B, ldq], head h at column h*64
@@ -16,70 +17,172 @@ struct DecAttnParams {
     int H; float scale;
 };
 
-// one warp per (b, h); lane = (g = lane/8 : key slot, sub = lane%8 : 8-dim slice)
+// One CTA per batch row: a producer warp streams that row's K and V cache slabs (contiguous [keys][H*64]) through a
+// DA_NS-stage shared-memory ring with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx), so the bytes in
+// flight are set by the ring depth, not by registers or warp count; H consumer warps (one per head) run an online
+// softmax over the chunks.  lane = (g = lane/8 : key slot inside the chunk, sub = lane%8 : 8-dim slice of the head).
+// Keys after the row's last attendable key are never fetched (cross-attention latents are padded per batch).
+constexpr int DEC_MAX_KEYS = 256;
+constexpr int DA_CHUNK = 16;       // keys per chunk
+constexpr int DA_NS = 3;           // ring stages (each holds a K chunk and a V chunk)
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(288)
 decode_attn_kernel(DecAttnParams p) {
+    extern __shared__ __align__(128) uint8_t da_smem[];
+    __shared__ uint8_t valid_s[DEC_MAX_KEYS];
+    __shared__ __align__(8) uint64_t bars[2 * DA_NS];
+    __shared__ int nrow_s;
     const int b = blockIdx.x;
-    const int h = threadIdx.x >> 5;
-    if (h >= p.H) return;
-    const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
-    const int col = h * 64 + sub * 8;
-    const f8 q = ld8(reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + col);
-    T* kc = reinterpret_cast<T*>(p.kcache) + (size_t)b * p.cache_bstride + col;
-    T* vc = reinterpret_cast<T*>(p.vcache) + (size_t)b * p.cache_bstride + col;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = p.H, rowlen = H * 64;
+    const uint32_t rowbytes = rowlen * sizeof(T);
+    const uint32_t chunk_bytes = DA_CHUNK * rowbytes;
+    const uint32_t ring = tc::smem_u32(da_smem);
+    const uint32_t bar0 = tc::smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DA_NS; ++s) { tc::mbar_init(bar0 + 8 * s, 1); tc::mbar_init(bar0 + 8 * (DA_NS + s), H); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        nrow_s = 0;
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_launch_dependents();
+    const int nc = p.n_cached;
+    const int nall = nc + (p.knew ? 1 : 0);
     const uint8_t* valid = p.key_valid + (size_t)b * p.kv_stride;
-    int nkeys = p.n_cached;
+    for (int j = threadIdx.x; j < nall; j += blockDim.x) {
+        const uint8_t v = valid[j];
+        valid_s[j] = v;
+        if (v && j < nc) atomicMax(&nrow_s, j + 1);
+    }
+    __syncthreads();
+    // cached keys that must be fetched; if none is attendable every score is -1e9 and the softmax is uniform over
+    // all of them (the reference's masked_fill behaviour), so fetch them all in that corner case
+    const int nrow = (nrow_s == 0 && !(p.knew && valid_s[nc])) ? nc : nrow_s;
+    const int nchunks = (nrow + DA_CHUNK - 1) / DA_CHUNK;
+    const T* kslab = reinterpret_cast<const T*>(p.kcache) + (size_t)b * p.cache_bstride;
+    const T* vslab = reinterpret_cast<const T*>(p.vcache) + (size_t)b * p.cache_bstride;
+
+    if (warp == H) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % DA_NS;
+                tc::mbar_wait(bar0 + 8 * (DA_NS + s), ((c / DA_NS) & 1) ^ 1);
+                const int nk = min(DA_CHUNK, nrow - c * DA_CHUNK);
+                const uint32_t bytes = nk * rowbytes;
+                const uint32_t dst = ring + s * 2 * chunk_bytes;
+                tc::mbar_expect_tx(bar0 + 8 * s, 2 * bytes);
+                bulk_g2s(dst, kslab + (size_t)c * DA_CHUNK * p.pitch, bytes, bar0 + 8 * s);
+                bulk_g2s(dst + chunk_bytes, vslab + (size_t)c * DA_CHUNK * p.pitch, bytes, bar0 + 8 * s);
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: warp = head ----------------
+    const int h = warp, g = lane >> 3, sub = lane & 7;
+    const int col = h * 64 + sub * 8;
+    const unsigned gmask = 0xFFu << (g * 8);
+    const f8 q = ld8(reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + col);
     f8 kn, vn;
     if (p.knew) {
         kn = ld8(reinterpret_cast<const T*>(p.knew) + (size_t)b * p.ldnew + col);
         vn = ld8(reinterpret_cast<const T*>(p.vnew) + (size_t)b * p.ldnew + col);
         if (g == 0) {       // append this step's K/V row to the cache
-            st8(kc + (size_t)p.n_cached * p.pitch, kn);
-            st8(vc + (size_t)p.n_cached * p.pitch, vn);
+            st8(const_cast<T*>(kslab) + (size_t)nc * p.pitch + col, kn);
+            st8(const_cast<T*>(vslab) + (size_t)nc * p.pitch + col, vn);
         }
-        nkeys += 1;
     }
     float m = -INFINITY, l = 0.f;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    const unsigned gmask = 0xFFu << (g * 8);      // the 8 lanes that share one key
-#pragma unroll 2
-    for (int j0 = 0; j0 < nkeys; j0 += 4) {
-        const int j = j0 + g;
-        if (j < nkeys) {     // uniform within each 8-lane group
-            f8 kk, vv;
-            if (p.knew && j == p.n_cached) { kk = kn; vv = vn; }
-            else { kk = ld8(kc + (size_t)j * p.pitch); vv = ld8(vc + (size_t)j * p.pitch); }
-            float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % DA_NS;
+        tc::mbar_wait(bar0 + 8 * s, (c / DA_NS) & 1);
+        const T* Ks = reinterpret_cast<const T*>(da_smem + (size_t)s * 2 * chunk_bytes);
+        const T* Vs = reinterpret_cast<const T*>(da_smem + (size_t)s * 2 * chunk_bytes + chunk_bytes);
+        const int nk = min(DA_CHUNK, nrow - c * DA_CHUNK);
+        float sc[4];
+        float cm = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s = fmaf(q.v[e], kk.v[e], s);
-            s += __shfl_xor_sync(gmask, s, 1);
-            s += __shfl_xor_sync(gmask, s, 2);
-            s += __shfl_xor_sync(gmask, s, 4);
-            s = valid[j] ? s * p.scale : -1e9f;
-            const float mn = fmaxf(m, s);
-            const float corr = __expf(m - mn), pj = __expf(s - mn);
-            l = l * corr + pj;
+        for (int i = 0; i < 4; ++i) {
+            const int jj = g + 4 * i;
+            sc[i] = -INFINITY;
+            if (jj < nk) {      // uniform within the 8-lane group
+                const f8 kf = ld8(Ks + (size_t)jj * rowlen + col);
+                float d = 0.f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vv.v[e], acc[e] * corr);
-            m = mn;
+                for (int e = 0; e < 8; ++e) d = fmaf(q.v[e], kf.v[e], d);
+                d += __shfl_xor_sync(gmask, d, 1);
+                d += __shfl_xor_sync(gmask, d, 2);
+                d += __shfl_xor_sync(gmask, d, 4);
+                sc[i] = valid_s[c * DA_CHUNK + jj] ? d * p.scale : -1e9f;
+            }
+            cm = fmaxf(cm, sc[i]);
         }
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+        const float mn = fmaxf(m, cm);
+        const float corr = __expf(m - mn);
+        l *= corr;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int jj = g + 4 * i;
+            if (jj < nk) {
+                const float pj = __expf(sc[i] - mn);
+                const f8 vf = ld8(Vs + (size_t)jj * rowlen + col);
+                l += pj;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf.v[e], acc[e]);
+            }
+        }
+        m = mn;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (DA_NS + s));
     }
-    __syncwarp();
-    // merge the four key slots
-    float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
-    const float f = (m == -INFINITY) ? 0.f : __expf(m - M);
-    l *= f;
+    if (p.knew) {
+        // this step's own key: every lane computes the same score (cheap), slot 0 adds the value
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(q.v[e], kn.v[e], d);
+        d += __shfl_xor_sync(gmask, d, 1);
+        d += __shfl_xor_sync(gmask, d, 2);
+        d += __shfl_xor_sync(gmask, d, 4);
+        const float sn = valid_s[nc] ? d * p.scale : -1e9f;
+        const float mn = fmaxf(m, sn);
+        const float corr = __expf(m - mn);
+        l *= corr;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= corr;
+        if (g == 0) {
+            const float pj = __expf(sn - mn);
+            l += pj;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vn.v[e], acc[e]);
+        }
+        m = mn;
+    }
+    // l counted each key once per lane of its group: reduce over the four key slots
     l += __shfl_xor_sync(0xffffffffu, l, 8);
     l += __shfl_xor_sync(0xffffffffu, l, 16);
     const float inv = 1.f / l;
     f8 o;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        float a = acc[e] * f;
+        float a = acc[e];
         a += __shfl_xor_sync(0xffffffffu, a, 8);
         a += __shfl_xor_sync(0xffffffffu, a, 16);
         o.v[e] = a * inv;
@@ -87,11 +190,28 @@ decode_attn_kernel(DecAttnParams p) {
     if (g == 0) st8(reinterpret_cast<T*>(p.out) + (size_t)b * p.ldo + col, o);
 }
 
+template <typename T>
+static int launch_decode_attn(const DecAttnParams& p, int B, cudaStream_t st) {
+    GCT_REQUIRE(p.H >= 1 && p.H <= 8, "decode attention: H=%d outside [1,8]", p.H);
+    GCT_REQUIRE(p.n_cached + 1 <= DEC_MAX_KEYS, "decode attention: %d keys > %d", p.n_cached + 1, DEC_MAX_KEYS);
+    GCT_REQUIRE(p.pitch == p.H * 64, "decode attention: cache rows must be contiguous (pitch %d != %d)", p.pitch, p.H * 64);
+    const size_t smem = (size_t)DA_NS * 2 * DA_CHUNK * p.H * 64 * sizeof(T);
+    static size_t cur = 0;
+    if (smem > cur) {
+        GCT_CUDA(cudaFuncSetAttribute(decode_attn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    GCT_CUDA(launch_k(decode_attn_kernel<T>, dim3(B), dim3((p.H + 1) * 32), smem, st, true, p));
+    return GCT_OK;
+}
+
 // x[b,:] = table[ys[b,pos]]*sqrt(d) + pe[pos + pe_off]; key_valid[b,pos] = tok != pad
 __global__ void decode_embed_kernel(const int64_t* __restrict__ ys, int ys_stride, int pos, const float* __restrict__ table,
                                     int vocab, const float* __restrict__ pe, int pe_off, int d, float scale, int pad_id,
                                     float* __restrict__ x, uint8_t* __restrict__ key_valid, int kv_stride) {
     const int b = blockIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
     long long t = ys[(size_t)b * ys_stride + pos];
     if (threadIdx.x == 0) key_valid[(size_t)b * kv_stride + pos] = (t != pad_id);
     if (t < 0 || t >= vocab) t = 0;
@@ -122,6 +242,8 @@ struct SampleParams {
 __global__ void decode_sample_kernel(SampleParams p) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
     if (b >= p.B) return;
     const float* lr = p.logits + (size_t)b * p.ld;
     float v[4];

@@ -45,27 +45,30 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ tok, int Ltok, const
     }
 }
 
-// backward of the above: scatter-free reduction.  dx is the gradient w.r.t. `out`.
-// One block per (vocab id | cond slot) column-chunk; loops over all rows and accumulates rows whose
-// token matches.  The tables are tiny (<= 64 ids), rows are ~40k: every block streams the token
-// array (8 B/row) and reads only the matching dx rows.
+// backward of the above.  The table is tiny (<= 128 ids) and the rows are many (~40k): each block reduces a
+// chunk of rows into a [vocab][128-column] tile in shared memory (thread = column, so no intra-block
+// conflicts), then flushes the tile with one atomic per (id, column).  dx is the gradient w.r.t. `out`.
+constexpr int EMB_BWD_ROWS = 256;
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, int B, int Ltok, int nc, const float* __restrict__ dx,
                                  int d, float scale, DropCtx drop, float* __restrict__ dtable, int vocab) {
-    const int v = blockIdx.x;              // vocab id
+    extern __shared__ float acc[];           // [vocab][128]
+    const int c = blockIdx.y * 128 + threadIdx.x;
+    for (int i = threadIdx.x; i < vocab * 128; i += 128) acc[i] = 0.f;
+    __syncthreads();
     const int L = nc + Ltok;
-    const int c0 = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c0 >= d) return;
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const int64_t* tr = tok + (size_t)b * Ltok;
-        for (int l = 0; l < Ltok; ++l) {
-            if (tr[l] == v) {
-                const size_t row = (size_t)b * L + nc + l;
-                acc += drop_apply(drop, (uint64_t)row * d + c0, dx[row * d + c0]);
-            }
+    const long long p0 = (long long)blockIdx.x * EMB_BWD_ROWS, p1 = min((long long)B * Ltok, p0 + EMB_BWD_ROWS);
+    if (c < d) {
+        for (long long p = p0; p < p1; ++p) {
+            long long v = tok[p];
+            if (v < 0 || v >= vocab) v = 0;
+            const size_t row = (size_t)(p / Ltok) * L + nc + (size_t)(p % Ltok);
+            acc[v * 128 + threadIdx.x] += drop_apply(drop, (uint64_t)row * d + c, dx[row * d + c]);
+        }
+        for (int v = 0; v < vocab; ++v) {
+            const float a = acc[v * 128 + threadIdx.x];
+            if (a != 0.f) atomicAdd(dtable + (size_t)v * d + c, a * scale);
         }
     }
-    dtable[(size_t)v * d + c0] += acc * scale;
 }
 
 // cond-token linear backward: dW[l*d+c, k] += scale * sum_b dx[b,l,c]*conds[b,k]; dB[l*d+c] += scale*sum_b dx
@@ -114,6 +117,8 @@ __global__ void norm_fwd_kernel(const float* __restrict__ x, const float* __rest
     const int d = NV * 128;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_launch_dependents();
     if (row >= rows) return;
     const float* xr = x + (size_t)row * d;
     float4 v[NV];
@@ -429,14 +434,24 @@ __global__ void cast_drop_colsum_kernel(const float* __restrict__ in, T* __restr
     }
 }
 
-// colsum[c] += sum_r in[r, c]  (in has leading dimension ld)
+// colsum[c] += sum_r in[r, c]  (in has leading dimension ld; cols % 8 == 0, ld % 8 == 0): 8 columns per thread
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ colsum) {
-    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
     if (c >= cols) return;
-    float acc = 0.f;
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) acc += to_f(in[(size_t)r * ld + c]);
-    atomicAdd(colsum + c, acc);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c + 8 <= cols && (ld & 7) == 0) {
+#pragma unroll 4
+        for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+            f8 v = ld8(in + (size_t)r * ld + c);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
+        }
+    } else {
+        for (int r = blockIdx.x; r < rows; r += gridDim.x)
+            for (int e = 0; e < 8 && c + e < cols; ++e) acc[e] += to_f(in[(size_t)r * ld + c + e]);
+    }
+    for (int e = 0; e < 8 && c + e < cols; ++e) atomicAdd(colsum + c + e, acc[e]);
 }
 
 // Fused Adam over the flat parameter buffer (torch.optim.Adam semantics, train1.py:116-119),

@@ -6,6 +6,7 @@
 
 thread_local char g_gct_err[512] = {0};
 int g_gct_simt_only = 0;
+int g_gct_pdl = 1;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -22,6 +23,7 @@ int gct_sm(void) {
 }
 int gct_num_slots(int n_layers) { return GCT_NUM_GLOBAL_SLOTS + n_layers * (GCT_ENC_LAYER_SLOTS + GCT_DEC_LAYER_SLOTS); }
 int gct_set_gemm_backend(int simt_only) { g_gct_simt_only = simt_only; return GCT_OK; }
+int gct_set_pdl(int enabled) { g_gct_pdl = enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
                  void* stream) {
@@ -281,6 +283,7 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
                                        : decode_steps_impl<bf16>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream);
 }
 int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
+int gct_decode_begin_launches(const gct_config_t* cfg) { return 3 + 2 * cfg->n_layers + (cfg->nconds > 0 ? 1 : 0); }
 
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,
                          int64_t cache_bstride, int pitch, int n_cached, const uint8_t* key_valid, int kv_stride, void* out,
@@ -290,10 +293,7 @@ int gct_decode_attention(const void* q, int ldq, const void* knew, const void* v
     p.q = q; p.ldq = ldq; p.knew = knew; p.vnew = vnew; p.ldnew = ldnew; p.kcache = kcache; p.vcache = vcache;
     p.cache_bstride = cache_bstride; p.pitch = pitch; p.n_cached = n_cached; p.key_valid = key_valid; p.kv_stride = kv_stride;
     p.out = out; p.ldo = ldo; p.H = H; p.scale = 0.125f;
-    if (dtype == GCT_DTYPE_F32) decode_attn_kernel<float><<<B, H * 32, 0, ST(stream)>>>(p);
-    else decode_attn_kernel<bf16><<<B, H * 32, 0, ST(stream)>>>(p);
-    GCT_LAUNCH_CHECK();
-    return GCT_OK;
+    return dtype == GCT_DTYPE_F32 ? launch_decode_attn<float>(p, B, ST(stream)) : launch_decode_attn<bf16>(p, B, ST(stream));
 }
 
 int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream) {

@@ -52,6 +52,7 @@ gemm_simt_kernel(const TA* __restrict__ A, long long sam, long long sak, const T
         __syncthreads();
     }
     const bool atomic = gridDim.z > 1;
+    if (blockIdx.z != 0) epi.bias = nullptr;      // split-K: the bias is added once
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = m0 + ty * 4 + i;

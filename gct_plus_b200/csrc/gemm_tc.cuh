@@ -102,6 +102,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // 8 consecutive columns of one row through the fused epilogue, vectorised when aligned
 template <typename T>
 __device__ __forceinline__ void epilogue_vec8(const Epilogue& e, int row, int col, const float* acc, int N, bool atomic) {
@@ -204,6 +215,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    // everything above touched only kernel parameters and on-chip state: under programmatic dependent launch it
+    // overlaps the previous kernel's tail.  Operands / residuals written by that kernel are read only after this wait.
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -256,15 +271,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tcgen05_fence_after();
             const int row = m0 + q * 32 + lane;
             const bool atomic = gridDim.z > 1;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                float acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
+            if (blockIdx.z != 0) epi.bias = nullptr;      // split-K: the bias is added once
+            if constexpr (BN == 16) {
+                float acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16), acc);
                 if (row < M) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = n0 + c * 32 + j * 8;
+                    for (int j = 0; j < 2; ++j) {
+                        const int col = n0 + j * 8;
                         if (col < N) epilogue_vec8<bf16>(epi, row, col, acc + j * 8, N, atomic);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    float acc[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
+                    if (row < M) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = n0 + c * 32 + j * 8;
+                            if (col < N) epilogue_vec8<bf16>(epi, row, col, acc + j * 8, N, atomic);
+                        }
                     }
                 }
             }
@@ -351,8 +379,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
     int kps = (num_kb + split_k - 1) / split_k;
     split_k = (num_kb + kps - 1) / kps;
     dim3 grid(cdiv(N, BN), cdiv(M, BM), split_k);
-    kern<<<grid, 192, L::TOTAL, st>>>(ta, tb, M, N, K, kps, epi);
-    GCT_LAUNCH_CHECK();
+    GCT_CUDA(launch_k(kern, grid, dim3(192), (size_t)L::TOTAL, st, true, ta, tb, M, N, K, kps, epi));
     return GCT_OK;
 }
 
@@ -365,9 +392,18 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
     if (split_k > 1 && !(epi.flags & EPI_ACCUM)) GCT_FAIL(GCT_ERR_ARG, "split-K needs an accumulating epilogue");
     // bn_hint = BN + 1000*STAGES (either part may be 0 = choose here)
     int BN = bn_hint % 1000, ST = bn_hint / 1000;
-    if (BN == 0) BN = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
+    if (BN == 0) {
+        // largest tile that still fills the 148 SMs; small-M (decode) problems fall through to narrow tiles
+        const long long mt = (M + BM - 1) / BM;
+        if (N <= 32) BN = 32;
+        else if (N <= 64) BN = 64;
+        else if (mt * ((N + 127) / 128) >= 148) BN = 128;
+        else if (mt * ((N + 63) / 64) >= 148) BN = 64;
+        else if (mt * ((N + 31) / 32) >= 100 || a_mn || b_mn) BN = 32;
+        else BN = 16;
+    }
     if (b_mn && BN < 64) BN = 64;
-    if (ST == 0) ST = (BN == 128) ? 3 : 4;
+    if (ST == 0) ST = (BN == 128) ? 3 : (BN == 16 ? 8 : 4);
     CUtensorMap ta, tb;
     if (!a_mn) GCT_TRY(get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, &ta));
     else GCT_TRY(get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, &ta));

@@ -63,7 +63,7 @@ struct Model {
         GCT_REQUIRE(dff % 64 == 0 && lat % 32 == 0, "d_ff %% 64 and latent %% 32 must be 0");
         GCT_REQUIRE(nc >= 0 && nc <= 8, "nconds=%d outside [0,8]", nc);
         GCT_REQUIRE(N >= 1 && N <= 16, "n_layers=%d outside [1,16]", N);
-        GCT_REQUIRE(c.trg_vocab <= 128 && c.src_vocab >= 1, "trg_vocab=%d must be <= 128", c.trg_vocab);
+        GCT_REQUIRE(c.trg_vocab <= 96 && c.src_vocab >= 1 && c.src_vocab <= 96, "vocabularies must be <= 96 ids (got %d / %d)", c.src_vocab, c.trg_vocab);
         GCT_REQUIRE(w.params_f32 && w.slot_offsets_host, "weights missing");
         if (sizeof(T) == 2) GCT_REQUIRE(w.params_bf16, "bf16 shadow parameters missing");
         drop0.seed = seed; drop0.scale = 1.f; drop0.thresh = 0;
@@ -111,8 +111,8 @@ struct Model {
         Epilogue e = epi(nullptr, Kin); e.out32 = G(wslot); e.flags = EPI_ACCUM;
         GCT_TRY(gemm(dY, true, ldy, X, true, ldx, Nout, Kin, R, e, wgrad_split(Nout, Kin, R)));
         if (do_bias) {
-            dim3 grid(min(cdiv(R, 32), 512), cdiv(Nout, 128));
-            colsum_kernel<T><<<grid, 128, 0, st>>>(dY, R, Nout, ldy, G(bslot));
+            dim3 grid(min(cdiv(R, 16), 1184), cdiv(Nout, 8 * 64));
+            colsum_kernel<T><<<grid, 64, 0, st>>>(dY, R, Nout, ldy, G(bslot));
             GCT_LAUNCH_CHECK();
         }
         return GCT_OK;
@@ -120,7 +120,7 @@ struct Model {
     int norm_fwd(const float* x, int aslot, int bslot, T* y, float* y32, int rows) {
         const int nv = d / 128;
         dim3 grid(cdiv(rows, 8));
-#define GCT_NORM_CASE(NV) case NV: norm_fwd_kernel<T, NV><<<grid, 256, 0, st>>>(x, P(aslot), P(bslot), y, y32, rows, 1e-6f); break;
+#define GCT_NORM_CASE(NV) case NV: GCT_CUDA(launch_k(norm_fwd_kernel<T, NV>, grid, dim3(256), 0, st, true, x, P(aslot), P(bslot), y, y32, rows, 1e-6f)); break;
         switch (nv) { GCT_NORM_CASE(1) GCT_NORM_CASE(2) GCT_NORM_CASE(3) GCT_NORM_CASE(4) GCT_NORM_CASE(5) GCT_NORM_CASE(6)
                       GCT_NORM_CASE(7) GCT_NORM_CASE(8) default: GCT_FAIL(GCT_ERR_UNSUPPORTED, "norm width %d", d); }
 #undef GCT_NORM_CASE
@@ -529,8 +529,8 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         }
         // decoder embedding (+ cond2dec tokens)
         {
-            dim3 grid(m.c.trg_vocab, cdiv(d, 128));
-            embed_bwd_kernel<<<grid, 128, 0, st>>>(io.trg, B, A.Tt, c2d ? nc : 0, dy, d, sqd, m.site(S_DEC_PE),
+            dim3 grid(cdiv((long long)B * A.Tt, EMB_BWD_ROWS), cdiv(d, 128));
+            embed_bwd_kernel<<<grid, 128, (size_t)m.c.trg_vocab * 128 * sizeof(float), st>>>(io.trg, B, A.Tt, c2d ? nc : 0, dy, d, sqd, m.site(S_DEC_PE),
                                                    m.G(GCT_SLOT_DEC_EMB), m.c.trg_vocab);
             GCT_LAUNCH_CHECK();
             if (c2d) {
@@ -603,8 +603,8 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         GCT_TRY(m.norm_bwd(xin, m.enc_slot(l, E_N1A), m.enc_slot(l, E_N1B), other, nullptr, dx, Me));
     }
     {
-        dim3 grid(m.c.src_vocab, cdiv(d, 128));
-        embed_bwd_kernel<<<grid, 128, 0, st>>>(io.src, B, A.S, nc, dx, d, sqd, m.site(S_ENC_PE), m.G(GCT_SLOT_ENC_EMB), m.c.src_vocab);
+        dim3 grid(cdiv((long long)B * A.S, EMB_BWD_ROWS), cdiv(d, 128));
+        embed_bwd_kernel<<<grid, 128, (size_t)m.c.src_vocab * 128 * sizeof(float), st>>>(io.src, B, A.S, nc, dx, d, sqd, m.site(S_ENC_PE), m.G(GCT_SLOT_ENC_EMB), m.c.src_vocab);
         GCT_LAUNCH_CHECK();
         if (nc > 0) {
             dim3 g2(nc, cdiv(d, 128));
@@ -622,7 +622,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
 template <typename T>
 struct DecodeWs {
     int B, Lz, Sm, Lmax;
-    T* zpad; T* mem; T* kvx;        // kvx: [N][B*Sm][2d]
+    T* zpad; T* mem; T* kx; T* vx;  // cross-attention keys / values: [N][B*Sm][d] each
     T* kc; T* vc;                   // [N][B][Lmax][d]
     float* x; T* xn; T* qkv; T* att; T* q2; T* hbuf; float* logits;
     uint8_t* key_valid; uint8_t* cross_mask; uint8_t* done;
@@ -634,7 +634,8 @@ struct DecodeWs {
         Sm = Lz + ((c.use_cond2lat && nc > 0 && !(c.use_cond2dec)) ? nc : 0);
         zpad = bp.arr<T>((size_t)B * Sm * c.latent_dim);
         mem = bp.arr<T>((size_t)B * Sm * d);
-        kvx = bp.arr<T>((size_t)N * B * Sm * 2 * d);
+        kx = bp.arr<T>((size_t)N * B * Sm * d);
+        vx = bp.arr<T>((size_t)N * B * Sm * d);
         kc = bp.arr<T>((size_t)N * B * Lmax * d);
         vc = bp.arr<T>((size_t)N * B * Lmax * d);
         x = bp.arr<float>((size_t)B * d); xn = bp.arr<T>((size_t)B * d); qkv = bp.arr<T>((size_t)B * 3 * d);
@@ -653,7 +654,7 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
     GCT_REQUIRE(!(m.c.use_cond2dec && nc > 0), "KV-cached decode does not cover use_cond2dec (host falls back to re-decode)");
     GCT_REQUIRE(D.zs && D.src_mask && D.ys && D.status, "decode: zs / src_mask / ys / status missing");
     GCT_REQUIRE(D.prefix_len >= 1 && D.prefix_len <= D.max_len, "decode: bad prefix length");
-    GCT_REQUIRE(D.max_len <= 200 && Sm <= 256, "decode: max_len %d > 200 or memory length %d > 256", D.max_len, Sm);
+    GCT_REQUIRE(D.max_len <= 200 && Sm <= DEC_MAX_KEYS, "decode: max_len %d > 200 or memory length %d > %d", D.max_len, Sm, DEC_MAX_KEYS);
     zpad_kernel<T><<<cdiv((size_t)B * Sm * lat, 256), 256, 0, st>>>(D.zs, B, Lz, Sm, lat, W.zpad);
     GCT_LAUNCH_CHECK();
     cross_mask_kernel<<<cdiv(B * Sm, 256), 256, 0, st>>>(D.src_mask, B, Lz, Sm, W.cross_mask);
@@ -664,9 +665,14 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
         cond_tokens_kernel<T><<<B * nc, 128, 0, st>>>(D.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, W.mem, Sm);
         GCT_LAUNCH_CHECK();
     }
-    for (int l = 0; l < N; ++l)
-        GCT_TRY(m.linear_T(W.mem, B * Sm, d, m.dec_slot(l, D_KV2_W), m.dec_slot(l, D_KV2_B), 2 * d,
-                           W.kvx + (size_t)l * B * Sm * 2 * d));
+    for (int l = 0; l < N; ++l) {
+        // K and V of the memory as two contiguous [B*Sm, d] slabs (rows [0,d) / [d,2d) of the fused k;v weight)
+        const int ws = m.dec_slot(l, D_KV2_W), bs = m.dec_slot(l, D_KV2_B);
+        Epilogue ek = Model<T>::epi(m.P(bs), d); ek.outT = W.kx + (size_t)l * B * Sm * d;
+        GCT_TRY(m.gemm(W.mem, false, d, m.WT(ws), false, d, B * Sm, d, d, ek));
+        Epilogue ev = Model<T>::epi(m.P(bs) + d, d); ev.outT = W.vx + (size_t)l * B * Sm * d;
+        GCT_TRY(m.gemm(W.mem, false, d, m.WT(ws) + (size_t)d * d, false, d, B * Sm, d, d, ev));
+    }
     GCT_CUDA(cudaMemsetAsync(W.done, 0, B, st));
     GCT_CUDA(cudaMemsetAsync(D.status, 0, 2 * sizeof(int), st));
     GCT_CUDA(cudaMemsetAsync(W.key_valid, 0, (size_t)B * W.Lmax, st));
@@ -678,9 +684,8 @@ template <typename T>
 static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int pos, int step, bool sample) {
     const int d = m.d, dff = m.dff, N = m.N, B = W.B, Sm = W.Sm, Lmax = W.Lmax;
     cudaStream_t st = m.st;
-    decode_embed_kernel<<<B, 128, 0, st>>>(D.ys, D.max_len, pos, m.P(GCT_SLOT_DEC_EMB), m.c.trg_vocab, m.P(GCT_SLOT_DEC_PE), 0, d,
-                                           sqrtf((float)d), m.c.pad_id, W.x, W.key_valid, Lmax);
-    GCT_LAUNCH_CHECK();
+    GCT_CUDA(launch_k(decode_embed_kernel, dim3(B), dim3(128), 0, st, true, (const int64_t*)D.ys, D.max_len, pos, m.P(GCT_SLOT_DEC_EMB),
+                      m.c.trg_vocab, m.P(GCT_SLOT_DEC_PE), 0, d, sqrtf((float)d), m.c.pad_id, W.x, W.key_valid, Lmax));
     for (int l = 0; l < N; ++l) {
         GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), W.xn, nullptr, B));
         GCT_TRY(m.linear_T(W.xn, B, d, m.dec_slot(l, D_QKV_W), m.dec_slot(l, D_QKV_B), 3 * d, W.qkv));
@@ -690,8 +695,7 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             p.kcache = W.kc + (size_t)l * B * Lmax * d; p.vcache = W.vc + (size_t)l * B * Lmax * d;
             p.cache_bstride = (long long)Lmax * d; p.pitch = d; p.n_cached = pos; p.key_valid = W.key_valid; p.kv_stride = Lmax;
             p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
-            decode_attn_kernel<T><<<B, m.H * 32, 0, st>>>(p);
-            GCT_LAUNCH_CHECK();
+            GCT_TRY(launch_decode_attn<T>(p, B, st));
         }
         {
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O1_B)), d); e.res32 = W.x; e.out32 = W.x;
@@ -700,13 +704,12 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
         GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), W.xn, nullptr, B));
         GCT_TRY(m.linear_T(W.xn, B, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), d, W.q2));
         {
-            T* kv = W.kvx + (size_t)l * B * Sm * 2 * d;
             DecAttnParams p;
             p.q = W.q2; p.ldq = d; p.knew = nullptr; p.vnew = nullptr; p.ldnew = 0;
-            p.kcache = kv; p.vcache = kv + d; p.cache_bstride = (long long)Sm * 2 * d; p.pitch = 2 * d; p.n_cached = Sm;
+            p.kcache = W.kx + (size_t)l * B * Sm * d; p.vcache = W.vx + (size_t)l * B * Sm * d;
+            p.cache_bstride = (long long)Sm * d; p.pitch = d; p.n_cached = Sm;
             p.key_valid = W.cross_mask; p.kv_stride = Sm; p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
-            decode_attn_kernel<T><<<B, m.H * 32, 0, st>>>(p);
-            GCT_LAUNCH_CHECK();
+            GCT_TRY(launch_decode_attn<T>(p, B, st));
         }
         {
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O2_B)), d); e.res32 = W.x; e.out32 = W.x;
@@ -717,9 +720,9 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff); e.flags = EPI_GELU; e.outT = W.hbuf;
             GCT_TRY(m.gemm(W.xn, false, d, m.WT(m.dec_slot(l, D_F1_W)), false, d, B, dff, d, e));
         }
-        {
-            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F2_B)), d); e.res32 = W.x; e.out32 = W.x;
-            GCT_TRY(m.gemm(W.hbuf, false, dff, m.WT(m.dec_slot(l, D_F2_W)), false, dff, B, d, dff, e));
+        {   // x += hbuf W2^T + b2 : in-place accumulate lets the long-K GEMM use split-K (bias from split 0 only)
+            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F2_B)), d); e.out32 = W.x; e.flags = EPI_ACCUM;
+            GCT_TRY(m.gemm(W.hbuf, false, dff, m.WT(m.dec_slot(l, D_F2_W)), false, dff, B, d, dff, e, B <= 1024 ? 2 : 1));
         }
     }
     if (!sample) return GCT_OK;      // prefix position: only the caches were needed
@@ -734,7 +737,6 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
     sp.uniforms = D.uniforms ? D.uniforms + (size_t)step * B : nullptr;
     sp.seed = D.seed; sp.step = step; sp.greedy = D.greedy; sp.eos_id = D.eos_id; sp.done = W.done; sp.n_done = D.status;
     sp.first_all_done = D.status + 1; sp.B = B; sp.probs_out = nullptr;
-    decode_sample_kernel<<<cdiv(B, 4), 128, 0, st>>>(sp);
-    GCT_LAUNCH_CHECK();
+    GCT_CUDA(launch_k(decode_sample_kernel, dim3(cdiv(B, 4)), dim3(128), 0, st, true, sp));
     return GCT_OK;
 }

@@ -82,6 +82,7 @@ int gct_version(void);
 int gct_sm(void);                                   /* compiled SM target: must be 100 */
 int gct_num_slots(int n_layers);
 int gct_set_gemm_backend(int simt_only);            /* test hook: 1 routes bf16 GEMMs through the SIMT kernel */
+int gct_set_pdl(int enabled);                       /* programmatic dependent launch on the decode path (default on) */
 
 /* ---- operator level (used by the unit tests and by the Python autograd wrappers) -------- */
 /* Norm: Model/modules.py:80-95.  y (dtype T) [, y32] = alpha*(x-mean)/(std+eps)+bias ; x fp32 [rows,d] */

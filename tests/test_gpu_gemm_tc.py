@@ -25,10 +25,12 @@ def _close(out, ref, tol=2e-3):
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 0), (256, 128, 128, 0), (512, 1536, 512, 0), (296, 96, 200, 64),
-                                      (512, 512, 2048, 32), (1024, 256, 512, 256), (384, 64, 320, 64)])
+                                      (512, 512, 2048, 32), (1024, 256, 512, 256), (384, 64, 320, 64), (512, 512, 512, 16), (128, 48, 64, 16)])
 def test_majorness(a_mn, b_mn, M, N, K, bn):
-    if b_mn and bn == 32:
+    if b_mn and bn in (16, 32):
         bn = 64
+    if a_mn and bn == 16:
+        bn = 32
     As, Bs, ref = _ops(M, N, K, a_mn, b_mn)
     out, _, _ = gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, bn=bn)
     _close(out, ref)
