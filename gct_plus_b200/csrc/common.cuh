@@ -117,8 +117,8 @@ __device__ __forceinline__ float block_sum(float v, float* smem32) {
 }
 
 // exact-erf GELU (Model/sublayers.py:86 uses F.gelu default) and its derivative
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
+__device__ __noinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __noinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
     const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
     return cdf + x * pdf;

@@ -18,6 +18,8 @@
 #include <unordered_map>
 #include "epilogue.cuh"
 
+extern int g_gct_persist;
+
 namespace tc {
 
 constexpr int BM = 128;
@@ -167,6 +169,78 @@ __device__ __forceinline__ void epilogue_vec8(const Epilogue& e, int row, int co
     if (e.outT) st8(reinterpret_cast<T*>(e.outT) + idx, v);
 }
 
+// 32 consecutive columns of one row: the global operands of the epilogue (bias, residual, dGELU pre-activation)
+// are requested first, as independent 16/32-byte loads, and only then is the accumulator pulled out of TMEM, so
+// their latency overlaps the tcgen05.ld instead of serialising behind it.
+struct EpiOperands { f8 b[4], r[4], h[4]; };
+
+template <typename T>
+__device__ __forceinline__ bool epi_fast(const Epilogue& e, int col, int N) {
+    return (col + 32 <= N) && ((e.ldc & 7) == 0) && !(e.flags & EPI_BIAS_ROW);
+}
+template <typename T>
+__device__ __forceinline__ void epi_prefetch(const Epilogue& e, int row, int col, EpiOperands& o) {
+    const size_t idx = (size_t)row * e.ldc + col;
+    if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.b[j] = ld8(e.bias + col + 8 * j);
+    }
+    if (e.res32) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.r[j] = ld8(e.res32 + idx + 8 * j);
+    }
+    if (e.flags & EPI_DGELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o.h[j] = ld8(reinterpret_cast<const T*>(e.aux_in) + idx + 8 * j);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, const float* acc, const EpiOperands& o,
+                                           bool atomic) {
+    const size_t idx = (size_t)row * e.ldc + col;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f8 v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.v[k] = acc[8 * j + k] * e.alpha;
+        if (e.bias) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] += o.b[j].v[k];
+        }
+        if (e.flags & EPI_GELU) {
+            if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] = gelu_erf(v.v[k]);
+        }
+        if (e.drop.thresh) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] = drop_apply(e.drop, idx + 8 * j + k, v.v[k]);
+        }
+        if (e.flags & EPI_DGELU) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] *= gelu_erf_grad(o.h[j].v[k]);
+        }
+        if (e.res32) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] += o.r[j].v[k];
+        }
+        if (e.flags & EPI_ACCUM) {
+            if (atomic) {
+                atomicAdd(reinterpret_cast<float4*>(e.out32 + idx + 8 * j), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+                atomicAdd(reinterpret_cast<float4*>(e.out32 + idx + 8 * j + 4), make_float4(v.v[4], v.v[5], v.v[6], v.v[7]));
+            } else {
+                f8 c = ld8(e.out32 + idx + 8 * j);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c.v[k] += v.v[k];
+                st8(e.out32 + idx + 8 * j, c);
+            }
+            continue;
+        }
+        if (e.out32) st8(e.out32 + idx + 8 * j, v);
+        if (e.outT) st8(reinterpret_cast<T*>(e.outT) + idx + 8 * j, v);
+    }
+}
+
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
@@ -285,12 +359,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
+                    const int col0 = n0 + c * 32;
+                    const bool fast = row < M && epi_fast<bf16>(epi, col0, N);
+                    EpiOperands ops;
+                    if (fast) epi_prefetch<bf16>(epi, row, col0, ops);
                     float acc[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), acc);
-                    if (row < M) {
+                    if (fast) {
+                        epi_finish<bf16>(epi, row, col0, acc, ops, atomic);
+                    } else if (row < M) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int col = n0 + c * 32 + j * 8;
+                            const int col = col0 + j * 8;
                             if (col < N) epilogue_vec8<bf16>(epi, row, col, acc + j * 8, N, atomic);
                         }
                     }
@@ -303,6 +383,170 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"((uint32_t)(BN < 32 ? 32 : BN))
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent variant for problems with more tiles than SMs: one CTA per SM walks the tile list.
+// The TMA producer runs ahead across tile boundaries (no pipeline refill bubble per tile), the
+// accumulator is double-buffered in TMEM (2 x BN columns) so the eight epilogue warps drain tile i
+// while the MMA warp already accumulates tile i+1.
+// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (TMEM lane quarter =
+// warp % 4, column half = (warp - 2) / 4); warp 2 owns the TMEM allocation.
+// ------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct PersistSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
+    static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
+};
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(320, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                       int kb_per_split, int num_splits, Epilogue epi) {
+    using L = PersistSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + L::BAR_OFF;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+    uint32_t* tmem_slot_gen = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (K + BK - 1) / BK;
+    const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    const int total = m_tiles * n_tiles * num_splits;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)L::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BM, z = tile / (n_tiles * m_tiles);
+                const int kb_begin = z * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(empty_bar(s), phase ^ 1u);
+                    mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
+                    const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+                    if constexpr (!A_MN) {
+                        tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, kb * BK, full_bar(s));
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(s));
+                    }
+                    if (++s == STAGES) { s = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+            int s = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int z = tile / (n_tiles * m_tiles);
+                const int kb_begin = z * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    mbar_wait(full_bar(s), phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+                        umma_bf16(tacc, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (++s == STAGES) { s = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        const int q = warp & 3, ch = (warp - 2) >> 2;
+        constexpr int CHUNKS = BN / 32;                       // 32-column chunks per tile
+        constexpr int PER = (CHUNKS + 1) / 2;                 // chunks per column half
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool atomic = num_splits > 1;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BM, z = tile / (n_tiles * m_tiles);
+            Epilogue e = epi;
+            if (z != 0) e.bias = nullptr;
+            const int row = m0 + q * 32 + lane;
+            bool waited = false;
+#pragma unroll 1
+            for (int c = ch * PER; c < min(CHUNKS, (ch + 1) * PER); ++c) {
+                const int col0 = n0 + c * 32;
+                const bool fast = row < M && epi_fast<bf16>(e, col0, N);
+                EpiOperands ops;
+                if (fast) epi_prefetch<bf16>(e, row, col0, ops);
+                if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); waited = true; }
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                if (fast) {
+                    epi_finish<bf16>(e, row, col0, v, ops, atomic);
+                } else if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = col0 + j * 8;
+                        if (col < N) epilogue_vec8<bf16>(e, row, col, v + j * 8, N, atomic);
+                    }
+                }
+            }
+            if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(acc)) : "memory");
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
                      : "memory");
     }
 }
@@ -383,6 +627,36 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
     return GCT_OK;
 }
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int split_k, const Epilogue& epi,
+                          cudaStream_t st) {
+    using L = PersistSmem<BN, STAGES>;
+    auto kern = gemm_tc_persist_kernel<BN, A_MN, B_MN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    const int num_kb = (K + BK - 1) / BK;
+    int kps = (num_kb + split_k - 1) / split_k;
+    split_k = (num_kb + kps - 1) / kps;
+    const long long total = (long long)cdiv(M, BM) * cdiv(N, BN) * split_k;
+    dim3 grid((unsigned)(total < sm_count() ? total : sm_count()));
+    GCT_CUDA(launch_k(kern, grid, dim3(320), (size_t)L::TOTAL, st, true, ta, tb, M, N, K, kps, split_k, epi));
+    return GCT_OK;
+}
+
 // A: K-major -> storage [M rows, K cols] with pitch lda; MN-major -> storage [K rows, M cols] with pitch lda.
 // B: K-major -> storage [N rows, K cols] with pitch ldb; MN-major -> storage [K rows, N cols] with pitch ldb.
 static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B, bool b_mn, long long ldb, int M, int N,
@@ -393,13 +667,15 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
     // bn_hint = BN + 1000*STAGES (either part may be 0 = choose here)
     int BN = bn_hint % 1000, ST = bn_hint / 1000;
     if (BN == 0) {
-        // largest tile that still fills the 148 SMs; small-M (decode) problems fall through to narrow tiles
-        const long long mt = (M + BM - 1) / BM;
+        // largest tile that still fills the SMs (wide tiles have the best smem-read : MMA ratio);
+        // small-M (decode) problems fall through to narrow tiles
+        const long long mt = (M + BM - 1) / BM, sp = split_k, sms = sm_count();
         if (N <= 32) BN = 32;
         else if (N <= 64) BN = 64;
-        else if (mt * ((N + 127) / 128) >= 148) BN = 128;
-        else if (mt * ((N + 63) / 64) >= 148) BN = 64;
-        else if (mt * ((N + 31) / 32) >= 100 || a_mn || b_mn) BN = 32;
+        else if (N % 256 == 0 && mt * (N / 256) * sp >= sms) BN = 256;
+        else if (mt * ((N + 127) / 128) * sp >= sms) BN = 128;
+        else if (mt * ((N + 63) / 64) * sp >= sms) BN = 64;
+        else if (mt * ((N + 31) / 32) * sp >= 100 || a_mn || b_mn) BN = 32;
         else BN = 16;
     }
     if (b_mn && BN < 64) BN = 64;
@@ -410,6 +686,21 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
     if (!b_mn) GCT_TRY(get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)BN, &tb));
     else GCT_TRY(get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, &tb));
 
+    if (g_gct_persist && (bn_hint / 1000) == 0 && (BN == 128 || BN == 256 || BN == 64) &&
+        (long long)cdiv(M, BM) * cdiv(N, BN) * split_k > sm_count()) {
+#define GCT_TCP_CASE(bn, amn, bmn, st_) \
+        if (BN == bn && a_mn == amn && b_mn == bmn) return launch_persist<bn, amn, bmn, st_>(ta, tb, M, N, K, split_k, epi, st);
+        GCT_TCP_CASE(64, false, false, 8)
+        GCT_TCP_CASE(128, false, false, 6)
+        GCT_TCP_CASE(256, false, false, 4)
+        GCT_TCP_CASE(64, false, true, 8)
+        GCT_TCP_CASE(128, false, true, 6)
+        GCT_TCP_CASE(256, false, true, 4)
+        GCT_TCP_CASE(64, true, true, 8)
+        GCT_TCP_CASE(128, true, true, 6)
+        GCT_TCP_CASE(256, true, true, 4)
+#undef GCT_TCP_CASE
+    }
 #define GCT_TC_CASE(bn, amn, bmn, st_)                                                                   \
     if (BN == bn && a_mn == amn && b_mn == bmn && ST == st_) return launch_cfg<bn, amn, bmn, st_>(ta, tb, M, N, K, split_k, epi, st);
     GCT_TC_CASE(16, false, false, 4)

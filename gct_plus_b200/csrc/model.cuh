@@ -100,7 +100,7 @@ struct Model {
     }
     // split-K factor for weight gradients: enough CTAs to fill the machine
     int wgrad_split(int Mout, int Nout, int R) const {
-        const int tiles = cdiv(Mout, 128) * cdiv(Nout, 128);
+        const int tiles = cdiv(Mout, 128) * cdiv(Nout, 256);
         int s = (2 * 148 + tiles - 1) / tiles;
         const int kb = cdiv(R, 64);
         if (s > kb / 2) s = kb / 2;

@@ -47,6 +47,18 @@ def run(M, N, K, bn, stages, split, a_mn=False, b_mn=False, iters=50, nbuf=1, ac
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "decode"
+    if mode == "train2":
+        M = 41472
+        for (N, K) in [(1536, 512), (512, 512), (2048, 512), (512, 2048)]:
+            for bn in (0, 128, 256, 64):
+                run(M, N, K, bn, 0, 1, nbuf=3, iters=10)
+        for (N, K) in [(1536, 512), (512, 512), (2048, 512), (512, 2048)]:
+            for bn in (0, 128, 256):
+                run(4096, N, K, bn, 0, 1, nbuf=1, iters=20)
+        for bn in (0, 128, 256):
+            run(M, 512, 1536, bn, 0, 1, b_mn=True, nbuf=3, iters=10)
+            run(1536, 512, M, bn, 0, 9, a_mn=True, b_mn=True, nbuf=3, iters=10, accum=True)
+        sys.exit(0)
     if mode == "decode":
         for (N, K) in [(1536, 512), (512, 512), (2048, 512), (512, 2048)]:
             for bn, stv in [(128, 3), (128, 6), (64, 4), (64, 8), (32, 4), (32, 8), (16, 8)]:

@@ -11,13 +11,15 @@ import bench  # noqa: E402
 import gct_plus_b200._lib as L  # noqa: E402
 
 dev = torch.device("cuda:0")
+bench.BATCH = int(os.environ.get("GCT_PROFILE_B", "512"))
 s = bench.build_sampler(dev)
 s.use_cuda_graph = False
 inputs = bench.sample_inputs(s, 2, seed=5, pinned=False)
 toklen, zs = inputs[0]
+NB = zs.size(0)
 Lz = zs.size(1)
-mask = (torch.arange(Lz).expand(512, 1, Lz) < torch.LongTensor(toklen).view(512, 1, 1)).to(dev)
-ys0 = torch.full((512, 1), 2, dtype=torch.long, device=dev)
+mask = (torch.arange(Lz).expand(NB, 1, Lz) < torch.LongTensor(toklen).view(NB, 1, 1)).to(dev)
+ys0 = torch.full((NB, 1), 2, dtype=torch.long, device=dev)
 s.decode(zs=zs.to(dev), ys=ys0, src_mask=mask)          # warm-up (all attributes set, descriptors cached)
 torch.cuda.synchronize()
 # second batch: run steps manually so that only a window is profiled
@@ -26,7 +28,7 @@ cfg = model._cfg()
 st = next(iter(s._static.values()))
 ws = model._ws.get('decode', 0, dev)
 w = model._weights()
-dec = L.GctDecode(B=512, Lz=st['zs'].size(1), max_len=st['ys'].size(1), prefix_len=1, greedy=0, eos_id=3, seed=0,
+dec = L.GctDecode(B=NB, Lz=st['zs'].size(1), max_len=st['ys'].size(1), prefix_len=1, greedy=0, eos_id=3, seed=0,
                   zs=st['zs'].data_ptr(), src_mask=st['mask'].data_ptr(), dconds=None, uniforms=st['uni'].data_ptr(),
                   ys=st['ys'].data_ptr(), status=st['status'].data_ptr())
 L.check(lib.gct_decode_begin(C.byref(cfg), C.byref(w), C.byref(dec), L.ptr(ws), ws.numel(), L.stream_ptr()))
