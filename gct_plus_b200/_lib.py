@@ -51,6 +51,7 @@ _PROTOS = {
     "gct_num_slots": (C.c_int, [C.c_int]),
     "gct_set_gemm_backend": (C.c_int, [C.c_int]),
     "gct_set_pdl": (C.c_int, [C.c_int]),
+    "gct_set_attention_backend": (C.c_int, [C.c_int]),
     "gct_set_persistent_gemm": (C.c_int, [C.c_int]),
     "gct_norm_fwd": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "gct_norm_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
@@ -107,6 +108,8 @@ def lib():
             raise GctError(f"libgct_b200.so was built for sm_{L.gct_sm()}, expected sm_100a")
         if os.environ.get("GCT_B200_PERSIST") == "0":
             L.gct_set_persistent_gemm(0)
+        if os.environ.get("GCT_B200_SIMT_ATTN") == "1":
+            L.gct_set_attention_backend(1)
         if os.environ.get("GCT_B200_PDL") == "0":
             L.gct_set_pdl(0)
         if os.environ.get("GCT_B200_SIMT_GEMM") == "1":      # test hook: bf16 GEMMs through the SIMT kernel

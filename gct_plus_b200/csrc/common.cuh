@@ -124,6 +124,24 @@ __device__ __noinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// bf16 tier: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution), fully inlined
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float r = 1.f - p * t * __expf(-ax * ax);
+    return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+    const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752f));
+    return fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf);
+}
+
 // ------------------------------------------------------------------------------------------
 // counter-based dropout RNG: keep(seed, site, idx) is a pure function, so backward regenerates
 // the same mask without storing it.  (Parity with torch's Philox stream is statistical only.)
@@ -141,10 +159,21 @@ __host__ __device__ __forceinline__ DropCtx drop_site(DropCtx c, uint32_t site) 
     c.seed = mix32(c.seed ^ (0x9e3779b9U * (site + 1)));
     return c;
 }
+// one 32-bit hash serves the element pair (idx, idx^1): 16 bits each against thresh>>16
 __device__ __forceinline__ float drop_apply(const DropCtx& c, uint64_t idx, float v) {
     if (c.thresh == 0) return v;
-    uint32_t h = mix32(c.seed ^ mix32((uint32_t)idx) ^ (uint32_t)(idx >> 32) * 0x85ebca6bU);
-    return (h < c.thresh) ? 0.f : v * c.scale;
+    const uint64_t pair = idx >> 1;
+    const uint32_t h = mix32(c.seed + (uint32_t)pair * 0x9e3779b9U + (uint32_t)(pair >> 32) * 0x85ebca6bU);
+    const uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xffffU);
+    return (bits < (c.thresh >> 16)) ? 0.f : v * c.scale;
+}
+
+// both elements of the pair (2*pair_idx, 2*pair_idx+1) from one hash; identical to drop_apply for indices < 2^33
+__device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t pair_idx, float& a, float& b) {
+    const uint32_t h = mix32(c.seed + pair_idx * 0x9e3779b9U);
+    const uint32_t t16 = c.thresh >> 16;
+    a = ((h & 0xffffU) < t16) ? 0.f : a * c.scale;
+    b = ((h >> 16) < t16) ? 0.f : b * c.scale;
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

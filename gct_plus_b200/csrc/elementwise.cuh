@@ -404,54 +404,73 @@ __global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, siz
     }
 }
 
-// out[r,c] = T(dropmask(site, r*ld_idx + c) * in[r,c]); optionally accumulates column sums (bias grad)
+// out[r,c] = T(dropmask(site, r*cols + c) * in[r,c]); optionally accumulates column sums (bias grad).
+// Block = 64 column-threads (4 columns each -> 256 columns) x 4 row groups; the row groups are reduced through
+// shared memory so each block issues one atomic per column.
 template <typename T>
-__global__ void cast_drop_colsum_kernel(const float* __restrict__ in, T* __restrict__ out, int rows, int cols,
-                                        DropCtx drop, float* __restrict__ colsum) {
-    // block: 128 threads -> 128*4 columns chunk? generic: each thread owns 4 consecutive columns
-    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-    if (c >= cols) return;
+__global__ void __launch_bounds__(256)
+cast_drop_colsum_kernel(const float* __restrict__ in, T* __restrict__ out, int rows, int cols, DropCtx drop,
+                        float* __restrict__ colsum) {
+    __shared__ float red[4][256];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int c = (blockIdx.y * 64 + tx) * 4;
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-        const size_t off = (size_t)r * cols + c;
-        float4 v = *reinterpret_cast<const float4*>(in + off);
-        v.x = drop_apply(drop, off + 0, v.x); v.y = drop_apply(drop, off + 1, v.y);
-        v.z = drop_apply(drop, off + 2, v.z); v.w = drop_apply(drop, off + 3, v.w);
-        if constexpr (sizeof(T) == 4) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = v;
-        } else {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-            uint2 u;
-            u.x = *reinterpret_cast<uint32_t*>(&p0);
-            u.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + off) = u;
+    if (c < cols) {
+#pragma unroll 2
+        for (int r = blockIdx.x * 4 + ty; r < rows; r += gridDim.x * 4) {
+            const size_t off = (size_t)r * cols + c;
+            float4 v = *reinterpret_cast<const float4*>(in + off);
+            v.x = drop_apply(drop, off + 0, v.x); v.y = drop_apply(drop, off + 1, v.y);
+            v.z = drop_apply(drop, off + 2, v.z); v.w = drop_apply(drop, off + 3, v.w);
+            if constexpr (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + off) = v;
+            } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&p0);
+                u.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + off) = u;
+            }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    if (colsum) {
-        atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
-        atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
-    }
+    if (!colsum) return;
+    red[ty][tx * 4 + 0] = acc.x; red[ty][tx * 4 + 1] = acc.y; red[ty][tx * 4 + 2] = acc.z; red[ty][tx * 4 + 3] = acc.w;
+    __syncthreads();
+    const int cc = blockIdx.y * 256 + threadIdx.x;
+    if (cc < cols) atomicAdd(colsum + cc, red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
-// colsum[c] += sum_r in[r, c]  (in has leading dimension ld; cols % 8 == 0, ld % 8 == 0): 8 columns per thread
+// colsum[c] += sum_r in[r, c]  (leading dimension ld).  Block = 32 column-threads (8 columns each -> 256 columns)
+// x 8 row groups, reduced through shared memory: one atomic per column per block.
 template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ colsum) {
-    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
-    if (c >= cols) return;
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ colsum) {
+    __shared__ float red[8][256];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = (blockIdx.y * 32 + tx) * 8;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c + 8 <= cols && (ld & 7) == 0) {
 #pragma unroll 4
-        for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        for (int r = blockIdx.x * 8 + ty; r < rows; r += gridDim.x * 8) {
             f8 v = ld8(in + (size_t)r * ld + c);
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] += v.v[e];
         }
-    } else {
-        for (int r = blockIdx.x; r < rows; r += gridDim.x)
+    } else if (c < cols) {
+        for (int r = blockIdx.x * 8 + ty; r < rows; r += gridDim.x * 8)
             for (int e = 0; e < 8 && c + e < cols; ++e) acc[e] += to_f(in[(size_t)r * ld + c + e]);
     }
-    for (int e = 0; e < 8 && c + e < cols; ++e) atomicAdd(colsum + c + e, acc[e]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[ty][tx * 8 + e] = acc[e];
+    __syncthreads();
+    const int cc = blockIdx.y * 256 + threadIdx.x;
+    if (cc < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += red[g][threadIdx.x];
+        atomicAdd(colsum + cc, s);
+    }
 }
 
 // Fused Adam over the flat parameter buffer (torch.optim.Adam semantics, train1.py:116-119),

@@ -7,6 +7,7 @@
 thread_local char g_gct_err[512] = {0};
 int g_gct_simt_only = 0;
 int g_gct_pdl = 1;
+int g_gct_simt_attn = 0;
 int g_gct_persist = 1;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -25,6 +26,7 @@ int gct_sm(void) {
 int gct_num_slots(int n_layers) { return GCT_NUM_GLOBAL_SLOTS + n_layers * (GCT_ENC_LAYER_SLOTS + GCT_DEC_LAYER_SLOTS); }
 int gct_set_gemm_backend(int simt_only) { g_gct_simt_only = simt_only; return GCT_OK; }
 int gct_set_pdl(int enabled) { g_gct_pdl = enabled; return GCT_OK; }
+int gct_set_attention_backend(int simt_only) { g_gct_simt_attn = simt_only; return GCT_OK; }
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
@@ -89,7 +91,7 @@ int gct_attention_fwd(const void* q, int ldq, const void* k, int ldk, const void
                       int64_t mask_bstride, int mask_rstride, void* out, int ldo, float* lse, float* probs, int B, int H,
                       int Lq, int Lk, int dtype, void* stream) {
     AttnParams p = make_attn(q, ldq, k, ldk, v, ldv, mask, mask_bstride, mask_rstride, out, ldo, lse, probs, B, H, Lq, Lk);
-    return dtype == GCT_DTYPE_F32 ? launch_attn_fwd<float>(p, ST(stream)) : launch_attn_fwd<bf16>(p, ST(stream));
+    return dtype == GCT_DTYPE_F32 ? attn_fwd_dispatch<float>(p, ST(stream)) : attn_fwd_dispatch<bf16>(p, ST(stream));
 }
 
 int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
@@ -99,7 +101,7 @@ int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void
     bp.f = make_attn(q, ldq, k, ldk, v, ldv, mask, mask_bstride, mask_rstride, nullptr, 0, const_cast<float*>(lse), nullptr, B, H,
                      Lq, Lk);
     bp.dO = dout; bp.lddo = lddo; bp.dQ = dq; bp.dK = dk; bp.dV = dv; bp.lddq = lddq; bp.lddk = lddk; bp.lddv = lddv;
-    return dtype == GCT_DTYPE_F32 ? launch_attn_bwd<float>(bp, ST(stream)) : launch_attn_bwd<bf16>(bp, ST(stream));
+    return dtype == GCT_DTYPE_F32 ? attn_bwd_dispatch<float>(bp, ST(stream)) : attn_bwd_dispatch<bf16>(bp, ST(stream));
 }
 
 int gct_src_mask(const int64_t* tok, int B, int L, int nc, int pad, uint8_t* out, void* stream) {

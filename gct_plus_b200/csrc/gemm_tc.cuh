@@ -210,15 +210,16 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, 
         if (e.flags & EPI_GELU) {
             if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] = gelu_erf(v.v[k]);
+            for (int k = 0; k < 8; ++k) v.v[k] = gelu_fast(v.v[k]);
         }
         if (e.drop.thresh) {
+            const uint32_t pair0 = (uint32_t)((idx + 8 * j) >> 1);      // idx is even; tensors stay below 2^33 elements
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] = drop_apply(e.drop, idx + 8 * j + k, v.v[k]);
+            for (int k = 0; k < 4; ++k) drop_pair(e.drop, pair0 + k, v.v[2 * k], v.v[2 * k + 1]);
         }
         if (e.flags & EPI_DGELU) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] *= gelu_erf_grad(o.h[j].v[k]);
+            for (int k = 0; k < 8; ++k) v.v[k] *= gelu_fast_grad(o.h[j].v[k]);
         }
         if (e.res32) {
 #pragma unroll

@@ -4,12 +4,29 @@
 #pragma once
 #include "../../include/gct_b200.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "decode.cuh"
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 
 extern int g_gct_simt_only;
+extern int g_gct_simt_attn;
+
+template <typename T>
+static int attn_fwd_dispatch(const AttnParams& p, cudaStream_t st) {
+    if constexpr (sizeof(T) == 2) {
+        if (!g_gct_simt_attn && atc::supported(p)) return atc::launch_fwd(p, st);
+    }
+    return launch_attn_fwd<T>(p, st);
+}
+template <typename T>
+static int attn_bwd_dispatch(const AttnBwdParams& bp, cudaStream_t st) {
+    if constexpr (sizeof(T) == 2) {
+        if (!g_gct_simt_attn && atc::supported(bp.f)) return atc::launch_bwd(bp, st);
+    }
+    return launch_attn_bwd<T>(bp, st);
+}
 
 // ------------------------------------------------------------------------------------------
 // bump allocator over the caller's workspace (dry run with base == nullptr measures the size)
@@ -111,8 +128,9 @@ struct Model {
         Epilogue e = epi(nullptr, Kin); e.out32 = G(wslot); e.flags = EPI_ACCUM;
         GCT_TRY(gemm(dY, true, ldy, X, true, ldx, Nout, Kin, R, e, wgrad_split(Nout, Kin, R)));
         if (do_bias) {
-            dim3 grid(min(cdiv(R, 16), 1184), cdiv(Nout, 8 * 64));
-            colsum_kernel<T><<<grid, 64, 0, st>>>(dY, R, Nout, ldy, G(bslot));
+            const int gy = cdiv(Nout, 256);
+            dim3 grid(max(1, min(cdiv(R, 64), 592 / gy)), gy);
+            colsum_kernel<T><<<grid, 256, 0, st>>>(dY, R, Nout, ldy, G(bslot));
             GCT_LAUNCH_CHECK();
         }
         return GCT_OK;
@@ -140,8 +158,9 @@ struct Model {
     }
     // out(T)[r,c] = dropmask(site)*in ; optional bias grad
     int cast_drop(const float* in, T* out, int rows, int cols, DropCtx dc, float* colsum) {
-        dim3 grid(min(rows, 592), cdiv(cols, 512));
-        cast_drop_colsum_kernel<T><<<grid, 128, 0, st>>>(in, out, rows, cols, dc, colsum);
+        const int gy = cdiv(cols, 256);
+        dim3 grid(max(1, min(cdiv(rows, 32), 592 / gy)), gy);
+        cast_drop_colsum_kernel<T><<<grid, 256, 0, st>>>(in, out, rows, cols, dc, colsum);
         GCT_LAUNCH_CHECK();
         return GCT_OK;
     }
@@ -151,7 +170,7 @@ struct Model {
         p.Q = q; p.K = k; p.V = v; p.ldq = ldq; p.ldk = ldkv; p.ldv = ldkv; p.mask = mask; p.mask_bstride = mb;
         p.mask_rstride = mr; p.O = out; p.ldo = d; p.lse = lse; p.probs = probs; p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
         p.scale = 0.125f; p.drop = dc;
-        return launch_attn_fwd<T>(p, st);
+        return attn_fwd_dispatch<T>(p, st);
     }
     int attention_bwd(const T* q, int ldq, const T* k, const T* v, int ldkv, const uint8_t* mask, long long mb, int mr,
                       const float* lse, const T* dO, T* dq, int lddq, T* dk, T* dv, int lddkv, int B, int Lq, int Lk,
@@ -162,7 +181,7 @@ struct Model {
         p.mask_rstride = mr; p.O = nullptr; p.ldo = d; p.lse = const_cast<float*>(lse); p.probs = nullptr; p.B = B; p.H = H;
         p.Lq = Lq; p.Lk = Lk; p.scale = 0.125f; p.drop = dc;
         bp.dO = dO; bp.lddo = d; bp.dQ = dq; bp.dK = dk; bp.dV = dv; bp.lddq = lddq; bp.lddk = lddkv; bp.lddv = lddkv;
-        return launch_attn_bwd<T>(bp, st);
+        return attn_bwd_dispatch<T>(bp, st);
     }
 };
 
