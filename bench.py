@@ -4,7 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
-  * sampling: one 512-draw batch decoded to max_strlen=100 (99 KV-cached multinomial steps), vaetf;
+  * sampling: one sample_smiles call = one batch of --batch latent draws (default 4096; the reference driver's
+    -batch_size flag, whose default is 512, is also measured and reported under "batch512") decoded to
+    max_strlen=100 (99 KV-cached multinomial steps), vaetf; 8 steps x 4096 = 32 768 draws (cfg 2: "30k draws");
   * training (reported under "train"): one optimiser step (fwd + loss + bwd [+ allreduce] + Adam),
     pvaetf B=512 S=78 T=79 at N=1 (cfg 3), pscavaetf B=512/GPU S=98 T=99 data-parallel at N>1 (cfg 4).
 `value` is timed with inputs resident in HBM; `e2e` goes through the public API
@@ -233,10 +235,11 @@ def run_sampling(args, rank, world, dev):
     d2h = BATCH * MAX_STRLEN * 8
     cfg = sampler.model._cfg()
     per_step = L.lib().gct_decode_launches_per_step(cfg)
-    launches = K * (9 + n_steps_run // max(K, 1) * per_step)
+    launches = K * (3 + 2 * 6 + (n_steps_run // max(K, 1)) * per_step)
     Sm_mean = float(np.mean([z.size(1) for _, z in inputs[W:]]))
+    Sm_true = float(np.mean([np.mean(tl) for tl, _ in inputs[W:]]))       # keys actually attended (rows differ in length)
     return dict(value=value, ms_per_step=ms / K, e2e_value=world * K * BATCH / (t_e2e / 1e3), h2d=h2d, d2h=d2h, clocks=ck,
-                launches=launches, sampler=sampler, Sm_mean=Sm_mean, decode_steps=n_steps_run / K)
+                launches=launches, sampler=sampler, Sm_mean=Sm_mean, Sm_true=Sm_true, decode_steps=n_steps_run / K)
 
 
 def make_train_batch(B, S, nc, scaffold, seed, dev=None, pinned=False):
@@ -396,14 +399,15 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=59)       # 59 x 512 = 30 208 latent draws (cfg 2)
+    ap.add_argument("--steps", type=int, default=8)        # 8 x 4096 = 32 768 latent draws (cfg 2: "30k draws")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=512, help="latent draws per sample_smiles call")
+    ap.add_argument("--batch", type=int, default=4096, help="latent draws per sample_smiles call")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-batch", type=int, default=512)
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-batch512", action="store_true")
     args = ap.parse_args()
     global BATCH
     BATCH = args.batch
@@ -423,10 +427,20 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     hbm_peak, tf_peak, peak_src = peaks()
     s = run_sampling(args, rank, world, dev)
+    b512 = None
+    if BATCH != 512 and not args.no_batch512:
+        big = BATCH
+        BATCH = 512
+        a2 = argparse.Namespace(**vars(args))
+        a2.steps, a2.warmup = 12, 3
+        r = run_sampling(a2, rank, world, dev)
+        b512 = {"batch": 512, "value": r["value"], "unit": "SMILES/s", "ms_per_step": r["ms_per_step"], "steps": 12,
+                "e2e": r["e2e_value"], "note": "the reference driver's default -batch_size (uc_sampling.py:16-23)"}
+        BATCH = big
     steps = MAX_STRLEN - 1
     alg_per_launch, ms_per_launch, nl = time_decode_attention(s["sampler"], dev, steps, s["Sm_mean"])
     achieved = alg_per_launch / (ms_per_launch / 1e3) / 1e9
-    total_alg = decode_alg_bytes(6, BATCH, s["Sm_mean"], steps, 2)
+    total_alg = decode_alg_bytes(6, BATCH, s["Sm_true"], steps, 2)
     train = None
     if not args.no_train:
         s.pop("sampler")
@@ -437,10 +451,11 @@ def main():
         line = {"metric": "sampled_smiles_per_sec", "value": s["value"], "unit": "SMILES/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "cfg2 vaetf unconditioned sampling: 512-draw batches, KV-cached multinomial decode, max_strlen 100 "
-                                       "(99 steps/batch), latent lengths round(N(35,7^2)) in [13,55], random-init weights (no <eos> early stop)",
+                "config": {"workload": f"cfg2 vaetf unconditioned sampling: {BATCH}-draw batches (one sample_smiles call each), KV-cached "
+                                       "multinomial decode, max_strlen 100 (99 steps/batch), latent lengths round(N(35,7^2)) in [13,55], "
+                                       "random-init weights (no <eos> early stop)",
                            "batch": BATCH, "d_model": 512, "layers": "6+6", "heads": 8, "latent": 128, "vocab": VOCAB,
-                           "l2": "working set (KV cache 0.9 GB per batch) larger than L2, no flush needed",
+                           "l2": f"working set (KV cache {0.9 * BATCH / 512:.1f} GB per batch) larger than L2, no flush needed",
                            "sharding": f"{world} independent rank(s), no data-path collective"},
                 "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"]},
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
@@ -450,7 +465,7 @@ def main():
                              "whole_decode": {"algorithmic_bytes_per_batch": total_alg,
                                               "achieved_GBps": total_alg / (s["ms_per_step"] / 1e3) / 1e9,
                                               "frac": total_alg / (s["ms_per_step"] / 1e3) / 1e9 / hbm_peak}},
-                "cpu_baseline": cpu, "train": train}
+                "cpu_baseline": cpu, "batch512": b512, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

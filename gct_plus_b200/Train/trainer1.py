@@ -15,6 +15,7 @@ import torch.distributed as dist
 from .. import _lib as L
 from ..Model.forward_propagation1 import forward_propagation
 from ..Model.modules import get_src_mask, get_trg_mask
+from .dp import allreduce_sum_, world_info
 
 
 def KLAnnealer(epoch, KLA_ini_beta, KLA_inc_beta, KLA_beg_epoch):
@@ -179,7 +180,7 @@ class FusedTrainer:
         self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
         self.use_cond2dec = use_cond2dec
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = world_info(process_group)[1]
         flat = model._flat
         self.grads = torch.zeros_like(flat)
         self.exp_avg = torch.zeros_like(flat)
@@ -247,13 +248,12 @@ class FusedTrainer:
         L.check(lib.gct_backward(C.byref(cfg), C.byref(w), C.byref(io), L.ptr(bf['dlogits']), L.ptr(bf['dmu']), L.ptr(bf['dlv']),
                                  None, L.ptr(bf['ws']), bf['ws'].numel(), L.ptr(bf['scratch']), bf['scratch'].numel(), st),
                 "gct_backward")
-        if self.world > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        gscale = allreduce_sum_(self.grads, self.pg)       # DDP semantics: mean over ranks of the per-rank sum-loss gradient
         self.step_count += 1
         shadow = m._shadow if m.compute_dtype == "bf16" else None
         L.check(lib.gct_adam_step(L.ptr(m._flat), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
                                   L.ptr(shadow), m._flat.numel(), self.step_count, float(self.lr), self.betas[0], self.betas[1],
-                                  self.eps, 1.0 / self.world, st), "gct_adam_step")
+                                  self.eps, gscale, st), "gct_adam_step")
         if shadow is not None:
             m._shadow_version = m._versions()
         self.lr = noam_lr(self.step_count, cfg.d_model, self.warmup)       # takes effect on the next step

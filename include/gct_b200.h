@@ -180,6 +180,7 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
                      int step_end, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
 int gct_decode_launches_per_step(const gct_config_t* cfg);
+int gct_decode_begin_launches(const gct_config_t* cfg);
 /* the step's attention kernel on its own (unit tests, roofline timing): one query per (batch, head) over
  * n_cached cached keys (+ this step's knew/vnew row, which is appended to the cache when non-NULL) */
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,

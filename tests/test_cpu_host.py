@@ -1,0 +1,106 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, the module tree
+reproduces the reference's state_dict / init, host-side helpers follow the reference."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "gct_plus_b200", "libgct_b200.so")
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    import gct_plus_b200._lib as L
+    return L
+
+
+def test_library_exports_every_header_symbol(built):
+    L = built
+    lib = L.lib()
+    hdr = open(os.path.join(ROOT, "include", "gct_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|double|const char\*)\s+(gct_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gct_b200.h but not exported"
+    assert set(L.EXPORTED_SYMBOLS) <= declared
+    assert lib.gct_sm() == 100 and lib.gct_version() >= 100
+    assert lib.gct_num_slots(6) == 22 + 6 * 32
+    assert abs(lib.gct_noam_lr(10, 512, 8000) - O.noam_lr(10, 512, 8000)) < 1e-15
+
+
+def test_cpu_tensors_are_rejected_loudly(built):
+    from gct_plus_b200.Model.modules import get_src_mask
+    with pytest.raises(built.GctError):
+        get_src_mask(torch.zeros(2, 3, dtype=torch.long), 1)
+
+
+ARCH_FULL = dict(N=6, d_model=512, dff=2048, h=8, latent_dim=128)
+ARCH_SMALL = dict(N=2, d_model=128, dff=256, h=2, latent_dim=32)
+CASES = {"vaetf_full": ("vaetf", ARCH_FULL, 0, False, False), "pvaetf_full": ("pvaetf", ARCH_FULL, 3, False, True),
+         "scavaetf_small": ("scavaetf", ARCH_SMALL, 0, False, False), "pscavaetf_small": ("pscavaetf", ARCH_SMALL, 3, False, True),
+         "pvaetf_c2d_small": ("pvaetf", ARCH_SMALL, 3, True, False), "pvaetf_plain_small": ("pvaetf", ARCH_SMALL, 3, False, False)}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_init_matches_reference(name):
+    """Same seed -> same state_dict keys, order, shapes and values as the reference's constructors."""
+    from gct_plus_b200.Model import Cvaetf, Vaetf
+    init = load_golden("init_parity")
+    mt, arch, nc, c2d, c2l = CASES[name]
+    torch.manual_seed(0)
+    m = (Vaetf if mt == "vaetf" else Cvaetf)(32, 32, dropout=0.1, nconds=nc, use_cond2dec=c2d, use_cond2lat=c2l, **arch)
+    sd, gold = m.state_dict(), init[name]
+    assert list(sd.keys()) == list(gold.keys())
+    for k, v in sd.items():
+        g = gold[k]
+        assert v.numel() == g["numel"], k
+        assert torch.equal(v.flatten()[:8].float(), g["head"]), k
+        assert abs(float(v.double().sum()) - g["sum"]) <= 1e-6 * max(1.0, abs(g["sum"])), k
+    assert sum(p.numel() for p in m.parameters()) == init[name + "/nparams"]
+    # parameters are views of one flat buffer in kernel layout; q|k|v rows are adjacent
+    a = m.encoder.layers[0].attn
+    assert a.k_linear.weight.data_ptr() == a.q_linear.weight.data_ptr() + a.q_linear.weight.numel() * 4
+    assert a.v_linear.weight.data_ptr() == a.k_linear.weight.data_ptr() + a.k_linear.weight.numel() * 4
+
+
+def test_state_dict_roundtrip_and_module_prefix(tmp_path):
+    from gct_plus_b200.Model import Cvaetf
+    from gct_plus_b200.Model.build_model import load_state
+    torch.manual_seed(1)
+    a = Cvaetf(32, 32, nconds=3, use_cond2lat=True, dropout=0.1, **ARCH_SMALL)
+    torch.manual_seed(2)
+    b = Cvaetf(32, 32, nconds=3, use_cond2lat=True, dropout=0.1, **ARCH_SMALL)
+    path = str(tmp_path / "model_1.pt")
+    torch.save({"model_state_dict": {"module." + k: v for k, v in a.state_dict().items()}}, path)
+    load_state(b, path, 0)
+    for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(x, y), k
+    # still one flat buffer after load_state_dict (copy_ keeps the aliasing)
+    assert b.encoder.layers[0].attn.q_linear.weight.data_ptr() == b._flat.data_ptr() + 4 * int(b._offsets[22 + 2])
+
+
+def test_toklen_sampler_and_pe_table_are_bit_identical():
+    from gct_plus_b200.Inference.toklen_sampling import tokenlen_gen_from_data_distribution
+    from gct_plus_b200.Model.modules import positional_table
+    m = load_golden("misc")
+    np.random.seed(11)
+    d = m["toklen_data"]
+    out = tokenlen_gen_from_data_distribution(data=d, size=64, nBins=int(d.max() - d.min()))
+    assert np.array_equal(out, m["toklen_out"])
+    pe = positional_table(512)[0]
+    assert torch.equal(pe[[0, 1, 2, 57, 199]], m["pe512_rows"])
+    assert torch.equal(positional_table(128)[0][[0, 1, 99]], m["pe128_rows"])
+
+
+def test_kl_annealer():
+    from gct_plus_b200.Train.trainer1 import KLAnnealer
+    m = load_golden("misc")
+    assert [KLAnnealer(e, 0.02, 0.02, 1) for e in range(1, 6)] == m["kla"]
