@@ -9,6 +9,7 @@ enum : int {
     EPI_DGELU = 2,       // v = v * gelu'(aux_in)
     EPI_ACCUM = 4,       // out32 += v (atomic when split_k > 1)
     EPI_BIAS_ROW = 8,    // bias indexed by row instead of column (unused by the model; kept for tests)
+    EPI_NOSTORE = 16,    // measurement hook: run the epilogue math but skip the global stores
 };
 
 struct Epilogue {

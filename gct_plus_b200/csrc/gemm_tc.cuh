@@ -172,34 +172,35 @@ __device__ __forceinline__ void epilogue_vec8(const Epilogue& e, int row, int co
 // 32 consecutive columns of one row: the global operands of the epilogue (bias, residual, dGELU pre-activation)
 // are requested first, as independent 16/32-byte loads, and only then is the accumulator pulled out of TMEM, so
 // their latency overlaps the tcgen05.ld instead of serialising behind it.
-struct EpiOperands { f8 b[4], r[4], h[4]; };
+template <int NJ> struct EpiOperandsT { f8 b[NJ], r[NJ], h[NJ]; };
+using EpiOperands = EpiOperandsT<4>;
 
-template <typename T>
+template <typename T, int NJ = 4>
 __device__ __forceinline__ bool epi_fast(const Epilogue& e, int col, int N) {
-    return (col + 32 <= N) && ((e.ldc & 7) == 0) && !(e.flags & EPI_BIAS_ROW);
+    return (col + 8 * NJ <= N) && ((e.ldc & 7) == 0) && !(e.flags & EPI_BIAS_ROW);
 }
-template <typename T>
-__device__ __forceinline__ void epi_prefetch(const Epilogue& e, int row, int col, EpiOperands& o) {
+template <typename T, int NJ = 4>
+__device__ __forceinline__ void epi_prefetch(const Epilogue& e, int row, int col, EpiOperandsT<NJ>& o) {
     const size_t idx = (size_t)row * e.ldc + col;
     if (e.bias) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o.b[j] = ld8(e.bias + col + 8 * j);
+        for (int j = 0; j < NJ; ++j) o.b[j] = ld8(e.bias + col + 8 * j);
     }
     if (e.res32) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o.r[j] = ld8(e.res32 + idx + 8 * j);
+        for (int j = 0; j < NJ; ++j) o.r[j] = ld8(e.res32 + idx + 8 * j);
     }
     if (e.flags & EPI_DGELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o.h[j] = ld8(reinterpret_cast<const T*>(e.aux_in) + idx + 8 * j);
+        for (int j = 0; j < NJ; ++j) o.h[j] = ld8(reinterpret_cast<const T*>(e.aux_in) + idx + 8 * j);
     }
 }
-template <typename T>
-__device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, const float* acc, const EpiOperands& o,
+template <typename T, int NJ = 4>
+__device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, const float* acc, const EpiOperandsT<NJ>& o,
                                            bool atomic) {
     const size_t idx = (size_t)row * e.ldc + col;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
         f8 v;
 #pragma unroll
         for (int k = 0; k < 8; ++k) v.v[k] = acc[8 * j + k] * e.alpha;
@@ -237,10 +238,136 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, 
             }
             continue;
         }
+        if (e.flags & EPI_NOSTORE) { if (v.v[0] == 1.2345e30f) st8(e.out32 + idx, v); continue; }
         if (e.out32) st8(e.out32 + idx + 8 * j, v);
         if (e.outT) st8(reinterpret_cast<T*>(e.outT) + idx + 8 * j, v);
     }
 }
+
+// Compile-time specialised epilogue for one 16-column chunk of one row (the persistent kernel's hot path):
+// no per-element branches, no 64-bit index arithmetic (the caller passes element offsets), operands requested
+// before the TMEM load.  ACT: 0 none, 1 GELU (pre-activation saved to aux_out), 2 dGELU (pre-activation from aux_in).
+template <bool HAS_BIAS, int ACT, bool HAS_RES, bool OUT_F32>
+__device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __restrict__ bias, uint32_t taddr, size_t off, int col) {
+    float4 b4[4], r4[4];
+    uint4 h2[2];
+    if constexpr (HAS_BIAS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
+    }
+    if constexpr (HAS_RES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r4[i] = *(reinterpret_cast<const float4*>(e.res32 + off) + i);
+    }
+    if constexpr (ACT == 2) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) h2[i] = *(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.aux_in) + off) + i);
+    }
+    float v[16];
+    tmem_ld16(taddr, v);
+    if constexpr (HAS_BIAS) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[4 * i] += b4[i].x; v[4 * i + 1] += b4[i].y; v[4 * i + 2] += b4[i].z; v[4 * i + 3] += b4[i].w; }
+    }
+    if constexpr (ACT == 1) {
+        if (e.aux_out) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint4 u;
+                __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(v[8 * g + 2 * i], v[8 * g + 2 * i + 1]);
+                *(reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.aux_out) + off) + g) = u;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+    }
+    if (e.drop.thresh) {
+        const uint32_t pair0 = (uint32_t)(off >> 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) drop_pair(e.drop, pair0 + i, v[2 * i], v[2 * i + 1]);
+    }
+    if constexpr (ACT == 2) {
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(h2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 hf = __bfloat1622float2(hp[i]);
+            v[2 * i] *= gelu_fast_grad(hf.x);
+            v[2 * i + 1] *= gelu_fast_grad(hf.y);
+        }
+    }
+    if constexpr (HAS_RES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[4 * i] += r4[i].x; v[4 * i + 1] += r4[i].y; v[4 * i + 2] += r4[i].z; v[4 * i + 3] += r4[i].w; }
+    }
+    if constexpr (OUT_F32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *(reinterpret_cast<float4*>(e.out32 + off) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(v[8 * g + 2 * i], v[8 * g + 2 * i + 1]);
+            *(reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.outT) + off) + g) = u;
+        }
+    }
+}
+
+// epilogue "mode": which specialisation serves this launch (0 = generic runtime-flag path)
+__host__ __device__ inline int epi_mode(const Epilogue& e) {
+    if ((e.flags & (EPI_ACCUM | EPI_BIAS_ROW | EPI_NOSTORE | 32)) || e.alpha != 1.f || (e.ldc & 7)) return 0;
+    const bool b = e.bias != nullptr, r = e.res32 != nullptr, f = e.out32 != nullptr, t = e.outT != nullptr;
+    if (f == t) return 0;                                    // exactly one output
+    if (e.flags & EPI_GELU) return (b && !r && t) ? 3 : 0;
+    if (e.flags & EPI_DGELU) return (!b && !r && t) ? 6 : 0;
+    if (t) return r ? 0 : (b ? 1 : 5);
+    return b ? (r ? 2 : 7) : (r ? 8 : 4);
+}
+
+// Same arithmetic as epi_finish for NJ 8-column groups, but the final values are handed back (vals[8*NJ]) so that
+// the caller can stage them in shared memory and write whole 128-byte row segments.  Not used for EPI_ACCUM.
+template <typename T, int NJ>
+__device__ __forceinline__ void epi_compute(const Epilogue& e, int row, int col, const float* acc, const EpiOperandsT<NJ>& o,
+                                            float* vals) {
+    const size_t idx = (size_t)row * e.ldc + col;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        f8 v;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.v[k] = acc[8 * j + k] * e.alpha;
+        if (e.bias) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] += o.b[j].v[k];
+        }
+        if (e.flags & EPI_GELU) {
+            if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] = gelu_fast(v.v[k]);
+        }
+        if (e.drop.thresh) {
+            const uint32_t pair0 = (uint32_t)((idx + 8 * j) >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) drop_pair(e.drop, pair0 + k, v.v[2 * k], v.v[2 * k + 1]);
+        }
+        if (e.flags & EPI_DGELU) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] *= gelu_fast_grad(o.h[j].v[k]);
+        }
+        if (e.res32) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] += o.r[j].v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vals[8 * j + k] = v.v[k];
+    }
+}
+
+// Warp-private staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7).
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk16) { return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4)); }
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 struct SmemLayout {
@@ -393,8 +520,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // The TMA producer runs ahead across tile boundaries (no pipeline refill bubble per tile), the
 // accumulator is double-buffered in TMEM (2 x BN columns) so the eight epilogue warps drain tile i
 // while the MMA warp already accumulates tile i+1.
-// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (TMEM lane quarter =
-// warp % 4, column half = (warp - 2) / 4); warp 2 owns the TMEM allocation.
+// Warp roles (576 threads): 0 = TMA producer, 1 = MMA issuer, 2..17 = epilogue (TMEM lane quarter =
+// warp % 4, column slice = (warp - 2) / 4); warp 2 owns the TMEM allocation.
 // ------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 struct PersistSmem {
@@ -407,7 +534,7 @@ struct PersistSmem {
 };
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                        int kb_per_split, int num_splits, Epilogue epi) {
     using L = PersistSmem<BN, STAGES>;
@@ -432,7 +559,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -504,34 +631,65 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        const int q = warp & 3, ch = (warp - 2) >> 2;
-        constexpr int CHUNKS = BN / 32;                       // 32-column chunks per tile
-        constexpr int PER = (CHUNKS + 1) / 2;                 // chunks per column half
+        // 16 epilogue warps: TMEM lane quarter q = warp % 4, column slice cs = (warp - 2) / 4 owns BN/4 columns,
+        // walked in 16-column chunks (small register footprint -> 576 threads fit the register file)
+        const int q = warp & 3, cs = (warp - 2) >> 2;
+        constexpr int SLICE = BN / 4;
+        constexpr int NCH = (SLICE + 15) / 16;
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool atomic = num_splits > 1;
+        const int mode = epi_mode(epi);
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BM, z = tile / (n_tiles * m_tiles);
             Epilogue e = epi;
             if (z != 0) e.bias = nullptr;
-            const int row = m0 + q * 32 + lane;
+            const int row = ((e.flags & 32) ? 0 : m0) + q * 32 + lane;      // flag 32: measurement hook, every tile writes rows [0,128)
             bool waited = false;
+            const uint32_t tslice = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cs * SLICE);
+            if (mode != 0 && n0 + BN <= N && m0 + BM <= M) {
+                // hot path: full tile (keeps tcgen05.ld warp-uniform), compile-time specialised epilogue
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tcgen05_fence_after();
+                waited = true;
+                {
+                    const int colb = n0 + cs * SLICE;
+                    const size_t off0 = (size_t)row * e.ldc + colb;
+                    const float* bias = (z != 0) ? nullptr : e.bias;
+#define GCT_EPI_RUN(HB, ACT_, HR, F32)                                                                    \
+    _Pragma("unroll 1") for (int c = 0; c < NCH; ++c)                                                     \
+        epi_chunk16<HB, ACT_, HR, F32>(e, bias, tslice + c * 16, off0 + c * 16, colb + c * 16);
+                    switch (mode) {
+                        case 1: GCT_EPI_RUN(true, 0, false, false) break;
+                        case 2: GCT_EPI_RUN(true, 0, true, true) break;
+                        case 3: GCT_EPI_RUN(true, 1, false, false) break;
+                        case 4: GCT_EPI_RUN(false, 0, false, true) break;
+                        case 5: GCT_EPI_RUN(false, 0, false, false) break;
+                        case 6: GCT_EPI_RUN(false, 2, false, false) break;
+                        case 7: GCT_EPI_RUN(true, 0, false, true) break;
+                        default: GCT_EPI_RUN(false, 0, true, true) break;
+                    }
+#undef GCT_EPI_RUN
+                }
+            } else {
 #pragma unroll 1
-            for (int c = ch * PER; c < min(CHUNKS, (ch + 1) * PER); ++c) {
-                const int col0 = n0 + c * 32;
-                const bool fast = row < M && epi_fast<bf16>(e, col0, N);
-                EpiOperands ops;
-                if (fast) epi_prefetch<bf16>(e, row, col0, ops);
-                if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); waited = true; }
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                if (fast) {
-                    epi_finish<bf16>(e, row, col0, v, ops, atomic);
-                } else if (row < M) {
+                for (int c = 0; c < NCH; ++c) {
+                    const int coff = cs * SLICE + c * 16;
+                    const int col0 = n0 + coff;
+                    const bool fast = row < M && epi_fast<bf16, 2>(e, col0, N);
+                    EpiOperandsT<2> ops;
+                    if (fast) epi_prefetch<bf16, 2>(e, row, col0, ops);
+                    if (!waited) { mbar_wait(tfull_bar(acc), acc_phase); tcgen05_fence_after(); waited = true; }
+                    float v[16];
+                    tmem_ld16(tslice + c * 16, v);
+                    if (fast) {
+                        epi_finish<bf16, 2>(e, row, col0, v, ops, atomic);
+                    } else if (row < M) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = col0 + j * 8;
-                        if (col < N) epilogue_vec8<bf16>(e, row, col, v + j * 8, N, atomic);
+                        for (int j = 0; j < 2; ++j) {
+                            const int col = col0 + j * 8;
+                            if (col < N) epilogue_vec8<bf16>(e, row, col, v + j * 8, N, atomic);
+                        }
                     }
                 }
             }
@@ -654,7 +812,7 @@ static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     split_k = (num_kb + kps - 1) / kps;
     const long long total = (long long)cdiv(M, BM) * cdiv(N, BN) * split_k;
     dim3 grid((unsigned)(total < sm_count() ? total : sm_count()));
-    GCT_CUDA(launch_k(kern, grid, dim3(320), (size_t)L::TOTAL, st, true, ta, tb, M, N, K, kps, split_k, epi));
+    GCT_CUDA(launch_k(kern, grid, dim3(576), (size_t)L::TOTAL, st, true, ta, tb, M, N, K, kps, split_k, epi));
     return GCT_OK;
 }
 

@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 lib = L.lib()
 
 
-def run(M, N, K, bn, stages, split, a_mn=False, b_mn=False, iters=50, nbuf=1, accum=False):
+def run(M, N, K, bn, stages, split, a_mn=False, b_mn=False, iters=50, nbuf=1, accum=False, flags=0):
     As = [torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16() for _ in range(nbuf)]
     Bs = [torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16() for _ in range(nbuf)]
     outT = None if accum else torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -24,7 +24,7 @@ def run(M, N, K, bn, stages, split, a_mn=False, b_mn=False, iters=50, nbuf=1, ac
     def call(i):
         A, B = As[i % nbuf], Bs[i % nbuf]
         L.check(lib.gct_gemm(L.ptr(A), int(a_mn), A.stride(0), L.ptr(B), int(b_mn), B.stride(0), M, N, K, L.ptr(bias), None, None,
-                             None, L.ptr(out32), L.ptr(outT), N, 4 if accum else 0, split, hint, 1, L.stream_ptr()))
+                             None, L.ptr(out32), L.ptr(outT), N, (4 if accum else 0) | flags, split, hint, 1, L.stream_ptr()))
     for i in range(3):
         call(i)
     torch.cuda.synchronize()
@@ -47,6 +47,13 @@ def run(M, N, K, bn, stages, split, a_mn=False, b_mn=False, iters=50, nbuf=1, ac
 
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "decode"
+    if mode == "nostore":
+        M = 41472
+        for (N, K) in [(1536, 512), (512, 512), (2048, 512), (512, 2048)]:
+            run(M, N, K, 0, 0, 1, nbuf=3, iters=10)
+            run(M, N, K, 0, 0, 1, nbuf=3, iters=10, flags=16)
+            run(M, N, K, 0, 0, 1, nbuf=3, iters=10, flags=32)
+        sys.exit(0)
     if mode == "train2":
         M = 41472
         for (N, K) in [(1536, 512), (512, 512), (2048, 512), (512, 2048)]:
