@@ -316,6 +316,13 @@ def run_training(args, rank, world, dev):
             "peak_source": src, "dtype": "bf16", "loss_finite": bool(np.isfinite(loss))}
 
 
+def base_config(batch, world, note):
+    return {"workload": "cfg2 vaetf unconditioned sampling: multinomial decode to max_strlen 100 (99 steps per batch), latent lengths "
+                        "round(N(35,7^2)) in [13,55], random-init weights (no <eos> early stop)",
+            "batch": batch, "d_model": 512, "layers": "6+6", "heads": 8, "latent": 128, "vocab": VOCAB, "l2": note,
+            "sharding": f"{world} independent rank(s), no data-path collective"}
+
+
 def barrier(world):
     if world > 1:
         torch.distributed.barrier()
@@ -390,8 +397,7 @@ def run_reference(args, rank):
     print(json.dumps({"impl": "reference", "metric": "sampled_smiles_per_sec", "value": v, "unit": "SMILES/s", "n_gpus": args.gpus,
                       "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "cfg2 vaetf unconditioned sampling, multinomial, max_strlen 100 (CPU, bounded sample)",
-                                 "batch": n},
+                      "config": base_config(n, 1, f"CPU oracle port; each step decodes {n} draw(s) instead of {BATCH}"),
                       "cpu_baseline": {"value": v, "unit": "SMILES/s", "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": "SMILES/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
@@ -451,12 +457,7 @@ def main():
         line = {"metric": "sampled_smiles_per_sec", "value": s["value"], "unit": "SMILES/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"cfg2 vaetf unconditioned sampling: {BATCH}-draw batches (one sample_smiles call each), KV-cached "
-                                       "multinomial decode, max_strlen 100 (99 steps/batch), latent lengths round(N(35,7^2)) in [13,55], "
-                                       "random-init weights (no <eos> early stop)",
-                           "batch": BATCH, "d_model": 512, "layers": "6+6", "heads": 8, "latent": 128, "vocab": VOCAB,
-                           "l2": f"working set (KV cache {0.9 * BATCH / 512:.1f} GB per batch) larger than L2, no flush needed",
-                           "sharding": f"{world} independent rank(s), no data-path collective"},
+                "config": base_config(BATCH, world, f"working set (KV cache {0.9 * BATCH / 512:.1f} GB per batch) larger than L2, no flush needed"),
                 "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"]},
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",

@@ -23,8 +23,6 @@ struct DecAttnParams {
 // softmax over the chunks.  lane = (g = lane/8 : key slot inside the chunk, sub = lane%8 : 8-dim slice of the head).
 // Keys after the row's last attendable key are never fetched (cross-attention latents are padded per batch).
 constexpr int DEC_MAX_KEYS = 256;
-constexpr int DA_CHUNK = 16;       // keys per chunk
-constexpr int DA_NS = 3;           // ring stages (each holds a K chunk and a V chunk)
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -35,14 +33,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <typename T>
+// DA_CHUNK keys per ring stage (each stage holds a K chunk and a V chunk), DA_NS stages, DA_ROWS batch rows per CTA
+// (the copy ring keeps streaming across them).
+template <typename T, int DA_CHUNK, int DA_NS, int DA_ROWS>
 __global__ void __launch_bounds__(288)
-decode_attn_kernel(DecAttnParams p) {
+decode_attn_kernel(DecAttnParams p, int B) {
     extern __shared__ __align__(128) uint8_t da_smem[];
-    __shared__ uint8_t valid_s[DEC_MAX_KEYS];
+    __shared__ uint8_t valid_s[DA_ROWS][DEC_MAX_KEYS];
     __shared__ __align__(8) uint64_t bars[2 * DA_NS];
-    __shared__ int nrow_s;
-    const int b = blockIdx.x;
+    __shared__ int nrow_s[DA_ROWS];
+    const int b0 = blockIdx.x * DA_ROWS;
+    const int nrows_cta = min(DA_ROWS, B - b0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.H, rowlen = H * 64;
     const uint32_t rowbytes = rowlen * sizeof(T);
@@ -52,142 +53,173 @@ decode_attn_kernel(DecAttnParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < DA_NS; ++s) { tc::mbar_init(bar0 + 8 * s, 1); tc::mbar_init(bar0 + 8 * (DA_NS + s), H); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        nrow_s = 0;
     }
+    if (threadIdx.x < DA_ROWS) nrow_s[threadIdx.x] = 0;
     __syncthreads();
     pdl_wait();
     pdl_launch_dependents();
     const int nc = p.n_cached;
     const int nall = nc + (p.knew ? 1 : 0);
-    const uint8_t* valid = p.key_valid + (size_t)b * p.kv_stride;
-    for (int j = threadIdx.x; j < nall; j += blockDim.x) {
-        const uint8_t v = valid[j];
-        valid_s[j] = v;
-        if (v && j < nc) atomicMax(&nrow_s, j + 1);
+    for (int r = 0; r < nrows_cta; ++r) {
+        const uint8_t* valid = p.key_valid + (size_t)(b0 + r) * p.kv_stride;
+        for (int j = threadIdx.x; j < nall; j += blockDim.x) {
+            const uint8_t v = valid[j];
+            valid_s[r][j] = v;
+            if (v && j < nc) atomicMax(&nrow_s[r], j + 1);
+        }
     }
     __syncthreads();
-    // cached keys that must be fetched; if none is attendable every score is -1e9 and the softmax is uniform over
-    // all of them (the reference's masked_fill behaviour), so fetch them all in that corner case
-    const int nrow = (nrow_s == 0 && !(p.knew && valid_s[nc])) ? nc : nrow_s;
-    const int nchunks = (nrow + DA_CHUNK - 1) / DA_CHUNK;
-    const T* kslab = reinterpret_cast<const T*>(p.kcache) + (size_t)b * p.cache_bstride;
-    const T* vslab = reinterpret_cast<const T*>(p.vcache) + (size_t)b * p.cache_bstride;
+    // cached keys that must be fetched per row; if none is attendable every score is -1e9 and the softmax is uniform
+    // over all of them (the reference's masked_fill behaviour), so fetch them all in that corner case
+    auto row_keys = [&](int r) { return (nrow_s[r] == 0 && !(p.knew && valid_s[r][nc])) ? nc : nrow_s[r]; };
 
     if (warp == H) {
-        // ---------------- producer ----------------
+        // ---------------- producer: one continuous stream of chunks over the CTA's rows ----------------
         if (lane == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % DA_NS;
-                tc::mbar_wait(bar0 + 8 * (DA_NS + s), ((c / DA_NS) & 1) ^ 1);
-                const int nk = min(DA_CHUNK, nrow - c * DA_CHUNK);
-                const uint32_t bytes = nk * rowbytes;
-                const uint32_t dst = ring + s * 2 * chunk_bytes;
-                tc::mbar_expect_tx(bar0 + 8 * s, 2 * bytes);
-                bulk_g2s(dst, kslab + (size_t)c * DA_CHUNK * p.pitch, bytes, bar0 + 8 * s);
-                bulk_g2s(dst + chunk_bytes, vslab + (size_t)c * DA_CHUNK * p.pitch, bytes, bar0 + 8 * s);
+            int g = 0;
+            for (int r = 0; r < nrows_cta; ++r) {
+                const int nrow = row_keys(r);
+                const T* kslab = reinterpret_cast<const T*>(p.kcache) + (size_t)(b0 + r) * p.cache_bstride;
+                const T* vslab = reinterpret_cast<const T*>(p.vcache) + (size_t)(b0 + r) * p.cache_bstride;
+                for (int c = 0; c * DA_CHUNK < nrow; ++c, ++g) {
+                    const int s = g % DA_NS;
+                    tc::mbar_wait(bar0 + 8 * (DA_NS + s), ((g / DA_NS) & 1) ^ 1);
+                    const int nk = min(DA_CHUNK, nrow - c * DA_CHUNK);
+                    const uint32_t bytes = nk * rowbytes;
+                    const uint32_t dst = ring + s * 2 * chunk_bytes;
+                    tc::mbar_expect_tx(bar0 + 8 * s, 2 * bytes);
+                    bulk_g2s(dst, kslab + (size_t)c * DA_CHUNK * p.pitch, bytes, bar0 + 8 * s);
+                    bulk_g2s(dst + chunk_bytes, vslab + (size_t)c * DA_CHUNK * p.pitch, bytes, bar0 + 8 * s);
+                }
             }
         }
         return;
     }
     // ---------------- consumers: warp = head ----------------
-    const int h = warp, g = lane >> 3, sub = lane & 7;
+    const int h = warp, gq = lane >> 3, sub = lane & 7;
     const int col = h * 64 + sub * 8;
-    const unsigned gmask = 0xFFu << (g * 8);
-    const f8 q = ld8(reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + col);
-    f8 kn, vn;
-    if (p.knew) {
-        kn = ld8(reinterpret_cast<const T*>(p.knew) + (size_t)b * p.ldnew + col);
-        vn = ld8(reinterpret_cast<const T*>(p.vnew) + (size_t)b * p.ldnew + col);
-        if (g == 0) {       // append this step's K/V row to the cache
-            st8(const_cast<T*>(kslab) + (size_t)nc * p.pitch + col, kn);
-            st8(const_cast<T*>(vslab) + (size_t)nc * p.pitch + col, vn);
-        }
-    }
-    float m = -INFINITY, l = 0.f;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % DA_NS;
-        tc::mbar_wait(bar0 + 8 * s, (c / DA_NS) & 1);
-        const T* Ks = reinterpret_cast<const T*>(da_smem + (size_t)s * 2 * chunk_bytes);
-        const T* Vs = reinterpret_cast<const T*>(da_smem + (size_t)s * 2 * chunk_bytes + chunk_bytes);
-        const int nk = min(DA_CHUNK, nrow - c * DA_CHUNK);
-        float sc[4];
-        float cm = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int jj = g + 4 * i;
-            sc[i] = -INFINITY;
-            if (jj < nk) {      // uniform within the 8-lane group
-                const f8 kf = ld8(Ks + (size_t)jj * rowlen + col);
-                float d = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) d = fmaf(q.v[e], kf.v[e], d);
-                d += __shfl_xor_sync(gmask, d, 1);
-                d += __shfl_xor_sync(gmask, d, 2);
-                d += __shfl_xor_sync(gmask, d, 4);
-                sc[i] = valid_s[c * DA_CHUNK + jj] ? d * p.scale : -1e9f;
+    const unsigned gmask = 0xFFu << (gq * 8);
+    int g = 0;
+    for (int r = 0; r < nrows_cta; ++r) {
+        const int b = b0 + r;
+        const int nrow = row_keys(r);
+        const int nchunks = (nrow + DA_CHUNK - 1) / DA_CHUNK;
+        const uint8_t* vld = valid_s[r];
+        T* kslab = reinterpret_cast<T*>(p.kcache) + (size_t)b * p.cache_bstride;
+        T* vslab = reinterpret_cast<T*>(p.vcache) + (size_t)b * p.cache_bstride;
+        const f8 q = ld8(reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + col);
+        f8 kn, vn;
+        if (p.knew) {
+            kn = ld8(reinterpret_cast<const T*>(p.knew) + (size_t)b * p.ldnew + col);
+            vn = ld8(reinterpret_cast<const T*>(p.vnew) + (size_t)b * p.ldnew + col);
+            if (gq == 0) {       // append this step's K/V row to the cache
+                st8(kslab + (size_t)nc * p.pitch + col, kn);
+                st8(vslab + (size_t)nc * p.pitch + col, vn);
             }
-            cm = fmaxf(cm, sc[i]);
         }
-        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
-        cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
-        const float mn = fmaxf(m, cm);
-        const float corr = __expf(m - mn);
-        l *= corr;
+        float m = -INFINITY, l = 0.f;
+        float acc[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] *= corr;
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+            const int s = g % DA_NS;
+            tc::mbar_wait(bar0 + 8 * s, (g / DA_NS) & 1);
+            const T* Ks = reinterpret_cast<const T*>(da_smem + (size_t)s * 2 * chunk_bytes);
+            const T* Vs = reinterpret_cast<const T*>(da_smem + (size_t)s * 2 * chunk_bytes + chunk_bytes);
+            const int nk = min(DA_CHUNK, nrow - c * DA_CHUNK);
+            constexpr int KPG = DA_CHUNK / 4;        // keys per 8-lane group per chunk
+            float sc[KPG];
+            float cm = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int jj = g + 4 * i;
-            if (jj < nk) {
-                const float pj = __expf(sc[i] - mn);
-                const f8 vf = ld8(Vs + (size_t)jj * rowlen + col);
+            for (int i = 0; i < KPG; ++i) {
+                const int jj = gq + 4 * i;
+                sc[i] = -INFINITY;
+                if (jj < nk) {      // uniform within the 8-lane group
+                    const f8 kf = ld8(Ks + (size_t)jj * rowlen + col);
+                    float d = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d = fmaf(q.v[e], kf.v[e], d);
+                    d += __shfl_xor_sync(gmask, d, 1);
+                    d += __shfl_xor_sync(gmask, d, 2);
+                    d += __shfl_xor_sync(gmask, d, 4);
+                    sc[i] = vld[c * DA_CHUNK + jj] ? d * p.scale : -1e9f;
+                }
+                cm = fmaxf(cm, sc[i]);
+            }
+            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+            cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+            const float mn = fmaxf(m, cm);
+            const float corr = __expf(m - mn);
+            l *= corr;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+            for (int i = 0; i < KPG; ++i) {
+                const int jj = gq + 4 * i;
+                if (jj < nk) {
+                    const float pj = __expf(sc[i] - mn);
+                    const f8 vf = ld8(Vs + (size_t)jj * rowlen + col);
+                    l += pj;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf.v[e], acc[e]);
+                }
+            }
+            m = mn;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (DA_NS + s));
+        }
+        if (p.knew) {
+            // this step's own key: every lane computes the same score (cheap), slot 0 adds the value
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d = fmaf(q.v[e], kn.v[e], d);
+            d += __shfl_xor_sync(gmask, d, 1);
+            d += __shfl_xor_sync(gmask, d, 2);
+            d += __shfl_xor_sync(gmask, d, 4);
+            const float sn = vld[nc] ? d * p.scale : -1e9f;
+            const float mn = fmaxf(m, sn);
+            const float corr = __expf(m - mn);
+            l *= corr;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] *= corr;
+            if (gq == 0) {
+                const float pj = __expf(sn - mn);
                 l += pj;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf.v[e], acc[e]);
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vn.v[e], acc[e]);
             }
+            m = mn;
         }
-        m = mn;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8 * (DA_NS + s));
-    }
-    if (p.knew) {
-        // this step's own key: every lane computes the same score (cheap), slot 0 adds the value
-        float d = 0.f;
+        // l counted each key once per lane of its group: reduce over the four key slots
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        const float inv = 1.f / l;
+        f8 o;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d = fmaf(q.v[e], kn.v[e], d);
-        d += __shfl_xor_sync(gmask, d, 1);
-        d += __shfl_xor_sync(gmask, d, 2);
-        d += __shfl_xor_sync(gmask, d, 4);
-        const float sn = valid_s[nc] ? d * p.scale : -1e9f;
-        const float mn = fmaxf(m, sn);
-        const float corr = __expf(m - mn);
-        l *= corr;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] *= corr;
-        if (g == 0) {
-            const float pj = __expf(sn - mn);
-            l += pj;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vn.v[e], acc[e]);
+        for (int e = 0; e < 8; ++e) {
+            float a = acc[e];
+            a += __shfl_xor_sync(0xffffffffu, a, 8);
+            a += __shfl_xor_sync(0xffffffffu, a, 16);
+            o.v[e] = a * inv;
         }
-        m = mn;
+        if (gq == 0) st8(reinterpret_cast<T*>(p.out) + (size_t)b * p.ldo + col, o);
     }
-    // l counted each key once per lane of its group: reduce over the four key slots
-    l += __shfl_xor_sync(0xffffffffu, l, 8);
-    l += __shfl_xor_sync(0xffffffffu, l, 16);
-    const float inv = 1.f / l;
-    f8 o;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        float a = acc[e];
-        a += __shfl_xor_sync(0xffffffffu, a, 8);
-        a += __shfl_xor_sync(0xffffffffu, a, 16);
-        o.v[e] = a * inv;
+}
+
+extern int g_da_cfg;      // tuning knob: chunk*100 + stages*10 + rows (0 = default)
+
+template <typename T, int CH, int NS, int ROWS>
+static int launch_decode_attn_cfg(const DecAttnParams& p, int B, cudaStream_t st) {
+    const size_t smem = (size_t)NS * 2 * CH * p.H * 64 * sizeof(T);
+    if (smem > 227 * 1024) GCT_FAIL(GCT_ERR_UNSUPPORTED, "decode attention config needs %zu B of shared memory", smem);
+    static size_t cur = 0;
+    auto kern = decode_attn_kernel<T, CH, NS, ROWS>;
+    if (smem > cur) {
+        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
     }
-    if (g == 0) st8(reinterpret_cast<T*>(p.out) + (size_t)b * p.ldo + col, o);
+    GCT_CUDA(launch_k(kern, dim3((B + ROWS - 1) / ROWS), dim3((p.H + 1) * 32), smem, st, true, p, B));
+    return GCT_OK;
 }
 
 template <typename T>
@@ -195,14 +227,31 @@ static int launch_decode_attn(const DecAttnParams& p, int B, cudaStream_t st) {
     GCT_REQUIRE(p.H >= 1 && p.H <= 8, "decode attention: H=%d outside [1,8]", p.H);
     GCT_REQUIRE(p.n_cached + 1 <= DEC_MAX_KEYS, "decode attention: %d keys > %d", p.n_cached + 1, DEC_MAX_KEYS);
     GCT_REQUIRE(p.pitch == p.H * 64, "decode attention: cache rows must be contiguous (pitch %d != %d)", p.pitch, p.H * 64);
-    const size_t smem = (size_t)DA_NS * 2 * DA_CHUNK * p.H * 64 * sizeof(T);
-    static size_t cur = 0;
-    if (smem > cur) {
-        GCT_CUDA(cudaFuncSetAttribute(decode_attn_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
+    if constexpr (sizeof(T) == 4) {
+        return launch_decode_attn_cfg<T, 8, 3, 1>(p, B, st);
+    } else {
+        switch (g_da_cfg) {
+            case 1631: return launch_decode_attn_cfg<T, 16, 3, 1>(p, B, st);
+            case 1632: return launch_decode_attn_cfg<T, 16, 3, 2>(p, B, st);
+            case 1634: return launch_decode_attn_cfg<T, 16, 3, 4>(p, B, st);
+            case 861: return launch_decode_attn_cfg<T, 8, 6, 1>(p, B, st);
+            case 862: return launch_decode_attn_cfg<T, 8, 6, 2>(p, B, st);
+            case 1661: return launch_decode_attn_cfg<T, 16, 6, 1>(p, B, st);
+            case 1662: return launch_decode_attn_cfg<T, 16, 6, 2>(p, B, st);
+            case 3231: return launch_decode_attn_cfg<T, 32, 3, 1>(p, B, st);
+            case 3232: return launch_decode_attn_cfg<T, 32, 3, 2>(p, B, st);
+            case 1641: return launch_decode_attn_cfg<T, 16, 4, 1>(p, B, st);
+            case 831: return launch_decode_attn_cfg<T, 8, 3, 1>(p, B, st);
+            case 832: return launch_decode_attn_cfg<T, 8, 3, 2>(p, B, st);
+            case 841: return launch_decode_attn_cfg<T, 8, 4, 1>(p, B, st);
+            case 821: return launch_decode_attn_cfg<T, 8, 2, 1>(p, B, st);
+            case 1621: return launch_decode_attn_cfg<T, 16, 2, 1>(p, B, st);
+            case 1622: return launch_decode_attn_cfg<T, 16, 2, 2>(p, B, st);
+            case 431: return launch_decode_attn_cfg<T, 4, 3, 1>(p, B, st);
+            case 441: return launch_decode_attn_cfg<T, 4, 4, 1>(p, B, st);
+            default: return launch_decode_attn_cfg<T, 8, 3, 1>(p, B, st);     // 48 KB ring -> 4 CTAs/SM: best of the sweep
+        }
     }
-    GCT_CUDA(launch_k(decode_attn_kernel<T>, dim3(B), dim3((p.H + 1) * 32), smem, st, true, p));
-    return GCT_OK;
 }
 
 // x[b,:] = table[ys[b,pos]]*sqrt(d) + pe[pos + pe_off]; key_valid[b,pos] = tok != pad

@@ -7,6 +7,7 @@
 thread_local char g_gct_err[512] = {0};
 int g_gct_simt_only = 0;
 int g_gct_pdl = 1;
+int g_da_cfg = 0;
 int g_gct_simt_attn = 0;
 int g_gct_persist = 1;
 
@@ -26,6 +27,7 @@ int gct_sm(void) {
 int gct_num_slots(int n_layers) { return GCT_NUM_GLOBAL_SLOTS + n_layers * (GCT_ENC_LAYER_SLOTS + GCT_DEC_LAYER_SLOTS); }
 int gct_set_gemm_backend(int simt_only) { g_gct_simt_only = simt_only; return GCT_OK; }
 int gct_set_pdl(int enabled) { g_gct_pdl = enabled; return GCT_OK; }
+int gct_set_decode_attn_config(int cfg) { g_da_cfg = cfg; return GCT_OK; }
 int gct_set_attention_backend(int simt_only) { g_gct_simt_attn = simt_only; return GCT_OK; }
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
 
