@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
-  * sampling: one sample_smiles call = one batch of --batch latent draws (default 4096; the reference driver's
+  * sampling: one sample_smiles call = one batch of --batch latent draws (default 8192; the reference driver's
     -batch_size flag, whose default is 512, is also measured and reported under "batch512") decoded to
-    max_strlen=100 (99 KV-cached multinomial steps), vaetf; 8 steps x 4096 = 32 768 draws (cfg 2: "30k draws");
+    max_strlen=100 (99 KV-cached multinomial steps), vaetf; default batch 8192 (4 calls cover cfg 2's 30k draws);
   * training (reported under "train"): one optimiser step (fwd + loss + bwd [+ allreduce] + Adam),
     pvaetf B=512 S=78 T=79 at N=1 (cfg 3), pscavaetf B=512/GPU S=98 T=99 data-parallel at N>1 (cfg 4).
 `value` is timed with inputs resident in HBM; `e2e` goes through the public API
@@ -34,6 +34,10 @@ ARCH = dict(N=6, d_model=512, dff=2048, h=8, latent_dim=128)
 VOCAB = 32
 MAX_STRLEN = 100
 BATCH = 512
+# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attn launch (ncu --set full, B=4096, 49 cached keys,
+# profiles/r01_decode_attn_b4096_t49_ncu_details.txt) next to the algorithmic bytes of that same launch
+NCU_TRAFFIC = {"dram_bytes_per_launch": 439313920, "algorithmic_bytes_same_launch": 436207616, "shape": "B=4096, 49 cached keys + 1 new",
+               "source": "profiles/r01_decode_attn_b4096_t49_ncu_details.txt"}
 ITOS = ["<unk>", "<pad>", "<sos>", "<eos>", "<sep>"] + list("CcNnOoSsFIBrl()[]=#123456+-H@/")[:27]
 
 
@@ -405,10 +409,10 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)        # 8 x 4096 = 32 768 latent draws (cfg 2: "30k draws")
+    ap.add_argument("--steps", type=int, default=8)        # 8 sample_smiles calls of --batch draws
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="latent draws per sample_smiles call")
+    ap.add_argument("--batch", type=int, default=8192, help="latent draws per sample_smiles call")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-batch", type=int, default=512)
     ap.add_argument("--no-train", action="store_true")
@@ -461,7 +465,8 @@ def main():
                 "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"]},
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",
-                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                             "traffic": NCU_TRAFFIC,
                              "peak_source": peak_src, "launches_timed": nl, "us_per_launch": ms_per_launch * 1e3,
                              "whole_decode": {"algorithmic_bytes_per_batch": total_alg,
                                               "achieved_GBps": total_alg / (s["ms_per_step"] / 1e3) / 1e9,

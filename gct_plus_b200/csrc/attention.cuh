@@ -88,6 +88,7 @@ attn_fwd_kernel(AttnParams p) {
         const float inv = 1.f / sum;
         if (p.lse && lane == 0) p.lse[((size_t)b * p.H + h) * Lq + i] = mx + logf(sum);
         const size_t prow = (((size_t)b * p.H + h) * Lq + i) * Lk;
+        const size_t drow = (((size_t)b * p.H + h) * Lq + i) * ((Lk + 1) & ~1);   // dropout index base (even stride)
 #pragma unroll
         for (int jj = 0; jj < ATT_MAXJ; ++jj)
             if (jj < nj) {
@@ -95,7 +96,7 @@ attn_fwd_kernel(AttnParams p) {
                 s[jj] *= inv;
                 if (j < Lk) {
                     if (p.probs) p.probs[prow + j] = s[jj];
-                    s[jj] = drop_apply(p.drop, prow + j, s[jj]);
+                    s[jj] = drop_apply(p.drop, drow + j, s[jj]);
                 }
             }
         float o0 = 0.f, o1 = 0.f;
@@ -179,6 +180,7 @@ attn_bwd_kernel(AttnBwdParams bp) {
         const uint8_t* mrow = p.mask ? p.mask + (size_t)b * p.mask_bstride + (size_t)i * p.mask_rstride : nullptr;
         const float lse = p.lse[((size_t)b * p.H + h) * Lq + i];
         const size_t prow = (((size_t)b * p.H + h) * Lq + i) * Lk;
+        const size_t drow = (((size_t)b * p.H + h) * Lq + i) * ((Lk + 1) & ~1);   // dropout index base (even stride)
         float Dsum = 0.f;
         float pd[ATT_MAXJ];
 #pragma unroll
@@ -191,8 +193,8 @@ attn_bwd_kernel(AttnBwdParams bp) {
                     float sc = s[jj] * p.scale;
                     if (mrow && mrow[j] == 0) sc = -1e9f;
                     pr = expf(sc - lse);
-                    pd[jj] = drop_apply(p.drop, prow + j, pr);          // dropped probability used in PV
-                    dp[jj] = drop_apply(p.drop, prow + j, dp[jj]);      // gradient through the same mask
+                    pd[jj] = drop_apply(p.drop, drow + j, pr);          // dropped probability used in PV
+                    dp[jj] = drop_apply(p.drop, drow + j, dp[jj]);      // gradient through the same mask
                     Dsum += pr * dp[jj];
                 }
                 s[jj] = pr;

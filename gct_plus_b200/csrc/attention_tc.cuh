@@ -141,6 +141,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mx = fmaxf(red[row], red[128 + row]);
     float sum = 0.f;
     const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
+    const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
         const int c = c0 + cc;
@@ -171,8 +172,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     if (c * 32 + jj < Lk) p.probs[prow + c * 32 + jj] = v[cc * 32 + jj] * inv;
             }
             if (p.drop.thresh) {
+                const uint32_t pair0 = (drow32 + (uint32_t)(c * 32)) >> 1;      // drow32 is even
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) v[cc * 32 + jj] = drop_apply(p.drop, prow + c * 32 + jj, v[cc * 32 + jj]);
+                for (int jj = 0; jj < 16; ++jj) drop_pair(p.drop, pair0 + jj, v[cc * 32 + 2 * jj], v[cc * 32 + 2 * jj + 1]);
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) st_row8(sm + FwdSmem::P, row, c * 32 + g * 8, v + cc * 32 + g * 8);
@@ -288,7 +290,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint8_t* mrow = p.mask ? (mask_l + (dense ? min(row, Lq - 1) * Lk : 0)) : nullptr;
     const float lse = qok ? p.lse[((size_t)b * p.H + h) * Lq + row] : 0.f;
     const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
-    float s[32], g[32];
+    float s[32], g[32], pd_keep[32];
+    const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
     float D = 0.f;
     if (live) {
         tmem_ld32(trow + c * 32, s);
@@ -302,12 +305,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const bool masked = mrow && mrow[j] == 0;
                 if (masked) sc = -1e9f;
                 pr = __expf(sc - lse);
-                gd = drop_apply(p.drop, prow + j, g[jj]);
-                D += pr * gd;
-                if (masked) gd = CUDART_INF_F;        // marks "no gradient through a masked score" (pr is 0 there anyway)
+                gd = masked ? CUDART_INF_F : g[jj];   // INF marks "no gradient through a masked score" (pr is 0 there anyway)
             }
             s[jj] = pr;
             g[jj] = gd;
+        }
+        // dropout: one hash per element pair, the same mask for the probability (Pd) and for its gradient
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) pd_keep[jj] = s[jj];
+        if (p.drop.thresh) {
+            const uint32_t pair0 = (drow32 + (uint32_t)(c * 32)) >> 1;
+            const uint32_t t16 = p.drop.thresh >> 16;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const uint32_t hsh = mix32(p.drop.seed + (pair0 + jj) * 0x9e3779b9U);
+                const float k0 = ((hsh & 0xffffU) < t16) ? 0.f : p.drop.scale, k1 = ((hsh >> 16) < t16) ? 0.f : p.drop.scale;
+                pd_keep[2 * jj] *= k0; pd_keep[2 * jj + 1] *= k1;
+                if (g[2 * jj] != CUDART_INF_F) g[2 * jj] *= k0;
+                if (g[2 * jj + 1] != CUDART_INF_F) g[2 * jj + 1] *= k1;
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+            if (g[jj] != CUDART_INF_F) D += s[jj] * g[jj];
         }
     }
     red[c * 128 + row] = D;
@@ -321,7 +341,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float pr = s[jj];
             float ds = 0.f, pd = 0.f;
             if (qok && j < Lk) {
-                pd = drop_apply(p.drop, prow + j, pr);
+                pd = pd_keep[jj];
                 ds = (g[jj] == CUDART_INF_F) ? 0.f : pr * (g[jj] - D) * p.scale;   // 1/sqrt(dk) of dQ / dK folded in
             }
             s[jj] = pd;
