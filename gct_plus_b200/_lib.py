@@ -51,6 +51,7 @@ _PROTOS = {
     "gct_num_slots": (C.c_int, [C.c_int]),
     "gct_set_gemm_backend": (C.c_int, [C.c_int]),
     "gct_set_pdl": (C.c_int, [C.c_int]),
+    "gct_set_tma_store": (C.c_int, [C.c_int]),
     "gct_set_decode_attn_config": (C.c_int, [C.c_int]),
     "gct_set_attention_backend": (C.c_int, [C.c_int]),
     "gct_set_persistent_gemm": (C.c_int, [C.c_int]),
@@ -113,6 +114,8 @@ def lib():
             L.gct_set_attention_backend(1)
         if os.environ.get("GCT_B200_DA_CFG"):
             L.gct_set_decode_attn_config(int(os.environ["GCT_B200_DA_CFG"]))
+        if os.environ.get("GCT_B200_TMA_STORE") == "0":
+            L.gct_set_tma_store(0)
         if os.environ.get("GCT_B200_PDL") == "0":
             L.gct_set_pdl(0)
         if os.environ.get("GCT_B200_SIMT_GEMM") == "1":      # test hook: bf16 GEMMs through the SIMT kernel

@@ -10,6 +10,7 @@ int g_gct_pdl = 1;
 int g_da_cfg = 0;
 int g_gct_simt_attn = 0;
 int g_gct_persist = 1;
+int g_gct_tma_store = 1;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -30,6 +31,7 @@ int gct_set_pdl(int enabled) { g_gct_pdl = enabled; return GCT_OK; }
 int gct_set_decode_attn_config(int cfg) { g_da_cfg = cfg; return GCT_OK; }
 int gct_set_attention_backend(int simt_only) { g_gct_simt_attn = simt_only; return GCT_OK; }
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
+int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
                  void* stream) {

@@ -85,6 +85,7 @@ int gct_set_gemm_backend(int simt_only);            /* test hook: 1 routes bf16 
 int gct_set_persistent_gemm(int enabled);          /* persistent, TMEM double-buffered GEMM for > 148 tiles (default on) */
 int gct_set_attention_backend(int simt_only);       /* test hook: 1 keeps bf16 attention on the SIMT kernel */
 int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring stages*10 + rows per CTA (0 = default) */
+int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue (default on) */
 int gct_set_pdl(int enabled);                       /* programmatic dependent launch on the decode path (default on) */
 
 /* ---- operator level (used by the unit tests and by the Python autograd wrappers) -------- */

@@ -53,6 +53,7 @@ if __name__ == "__main__":
             run(M, N, K, 0, 0, 1, nbuf=3, iters=10)
             run(M, N, K, 0, 0, 1, nbuf=3, iters=10, flags=16)
             run(M, N, K, 0, 0, 1, nbuf=3, iters=10, flags=32)
+            run(M, N, K, 0, 0, 1, nbuf=3, iters=10, flags=64)
         sys.exit(0)
     if mode == "train2":
         M = 41472

@@ -61,3 +61,36 @@ def test_split_k_accumulate():
     acc = torch.ones((M, N), device=DEV)
     gemm(As, Bs, M, N, K, a_mn=True, b_mn=True, flags=4, split_k=8, out32=acc)
     _close(acc, ref + 1.0)
+
+
+@pytest.mark.parametrize("N,K", [(512, 512), (1536, 512), (256, 512), (2048, 128), (384, 192)])
+@pytest.mark.parametrize("mode", ["bias_T", "bias_res_F32", "gelu", "plain_F32", "plain_T", "bias_F32", "res_F32"])
+def test_persistent_kernel_epilogue_modes(N, K, mode):
+    """More tiles than SMs -> persistent kernel with the specialised, smem-staged epilogue; every mode the model uses."""
+    M = 19 * 1024 + 128          # 153 full row tiles (+ a partial-tile run below)
+    for Mx in (M, M - 40):
+        As, Bs, ref = _ops(Mx, N, K, False, False, seed=7)
+        bias = torch.randn(N, device=DEV)
+        res = torch.randn(Mx, N, device=DEV)
+        if mode == "bias_T":
+            _, outT, _ = gemm(As, Bs, Mx, N, K, bias=bias, want_T=True)
+            _close(outT, ref + bias, 1e-2)
+        elif mode == "bias_res_F32":
+            out, _, _ = gemm(As, Bs, Mx, N, K, bias=bias, res=res)
+            _close(out, ref + bias + res)
+        elif mode == "gelu":
+            _, outT, aux = gemm(As, Bs, Mx, N, K, bias=bias, flags=1, want_T=True)
+            _close(aux, ref + bias, 1e-2)
+            _close(outT, torch.nn.functional.gelu(ref + bias), 1e-2)
+        elif mode == "plain_F32":
+            out, _, _ = gemm(As, Bs, Mx, N, K)
+            _close(out, ref)
+        elif mode == "plain_T":
+            _, outT, _ = gemm(As, Bs, Mx, N, K, want_T=True)
+            _close(outT, ref, 1e-2)
+        elif mode == "bias_F32":
+            out, _, _ = gemm(As, Bs, Mx, N, K, bias=bias)
+            _close(out, ref + bias)
+        else:
+            out, _, _ = gemm(As, Bs, Mx, N, K, res=res)
+            _close(out, ref + res)
