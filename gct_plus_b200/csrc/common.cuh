@@ -124,22 +124,72 @@ __device__ __noinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
-// bf16 tier: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution), fully inlined
-__device__ __forceinline__ float erf_fast(float x) {
-    const float ax = fabsf(x);
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float r = 1.f - p * t * __expf(-ax * ax);
-    return copysignf(r, x);
+// bf16 tier: Phi(x) = 0.5 erfc(-x/sqrt2) by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution) with
+// the 1/sqrt2 and the 0.5 folded into the constants:  t = 1/(1 + p'|x|), e = exp(-x^2/2), Phi(-|x|) = poly(t) t e.
+// The same two MUFU results (t, e) give both gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x e / sqrt(2 pi).
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#define GCT_AS_P  0.23164189f           /* 0.3275911 / sqrt(2) */
+#define GCT_AS_A1 0.127414796f          /* 0.5 * 0.254829592 */
+#define GCT_AS_A2 (-0.142248368f)
+#define GCT_AS_A3 0.7107068705f
+#define GCT_AS_A4 (-0.7265760135f)
+#define GCT_AS_A5 0.5307027145f
+#define GCT_NEG_HALF_LOG2E (-0.72134752044f)
+#define GCT_INV_SQRT_2PI 0.39894228040143268f
+__device__ __forceinline__ void gelu_phi_e(float x, float& phi, float& e) {
+    const float t = rcp_approx(fmaf(GCT_AS_P, fabsf(x), 1.f));
+    e = ex2_approx(x * x * GCT_NEG_HALF_LOG2E);
+    float p = fmaf(GCT_AS_A5, t, GCT_AS_A4);
+    p = fmaf(p, t, GCT_AS_A3);
+    p = fmaf(p, t, GCT_AS_A2);
+    p = fmaf(p, t, GCT_AS_A1);
+    const float h = p * (t * e);                      // Phi(-|x|)
+    phi = 0.5f + copysignf(0.5f - h, x);
 }
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_fast(float x) { float phi, e; gelu_phi_e(x, phi, e); return x * phi; }
 __device__ __forceinline__ float gelu_fast_grad(float x) {
-    const float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752f));
-    return fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf);
+    float phi, e; gelu_phi_e(x, phi, e);
+    return fmaf(x * e, GCT_INV_SQRT_2PI, phi);
+}
+// Packed (fp32x2: FFMA2 / FMUL2 / FADD2 issue one instruction per element PAIR on sm_100) evaluation for two
+// pre-activations at once.  m = per-element multipliers applied to both results (dropout keep * 1/(1-p), or 1):
+//   g = m * gelu(x),  dg = m * gelu'(x)
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void gelu_pair(float2 x, float2 m, float2& g, float2& dg) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 den = __ffma2_rn(ax, f2(GCT_AS_P), f2(1.f));
+    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+    const float2 ea = __fmul2_rn(__fmul2_rn(x, x), f2(GCT_NEG_HALF_LOG2E));
+    const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
+    float2 p = __ffma2_rn(t, f2(GCT_AS_A5), f2(GCT_AS_A4));
+    p = __ffma2_rn(p, t, f2(GCT_AS_A3));
+    p = __ffma2_rn(p, t, f2(GCT_AS_A2));
+    p = __ffma2_rn(p, t, f2(GCT_AS_A1));
+    const float2 h = __fmul2_rn(p, __fmul2_rn(t, e));
+    float2 u = __ffma2_rn(h, f2(-1.f), f2(0.5f));
+    u.x = copysignf(u.x, x.x); u.y = copysignf(u.y, x.y);
+    const float2 phi = __fadd2_rn(u, f2(0.5f));
+    const float2 xm = __fmul2_rn(x, m);
+    g = __fmul2_rn(xm, phi);
+    dg = __ffma2_rn(__fmul2_rn(xm, e), f2(GCT_INV_SQRT_2PI), __fmul2_rn(phi, m));
+}
+// gelu only (no saved gradient)
+__device__ __forceinline__ float2 gelu_pair_fwd(float2 x, float2 m) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 den = __ffma2_rn(ax, f2(GCT_AS_P), f2(1.f));
+    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+    const float2 ea = __fmul2_rn(__fmul2_rn(x, x), f2(GCT_NEG_HALF_LOG2E));
+    const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
+    float2 p = __ffma2_rn(t, f2(GCT_AS_A5), f2(GCT_AS_A4));
+    p = __ffma2_rn(p, t, f2(GCT_AS_A3));
+    p = __ffma2_rn(p, t, f2(GCT_AS_A2));
+    p = __ffma2_rn(p, t, f2(GCT_AS_A1));
+    const float2 h = __fmul2_rn(p, __fmul2_rn(t, e));
+    float2 u = __ffma2_rn(h, f2(-1.f), f2(0.5f));
+    u.x = copysignf(u.x, x.x); u.y = copysignf(u.y, x.y);
+    const float2 phi = __fadd2_rn(u, f2(0.5f));
+    return __fmul2_rn(__fmul2_rn(x, m), phi);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -174,6 +224,21 @@ __device__ __forceinline__ void drop_pair(const DropCtx& c, uint32_t pair_idx, f
     const uint32_t t16 = c.thresh >> 16;
     a = ((h & 0xffffU) < t16) ? 0.f : a * c.scale;
     b = ((h >> 16) < t16) ? 0.f : b * c.scale;
+}
+// the same decisions as multipliers {0, 1/(1-p)} (1 when dropout is off): lets the caller fold the mask into packed math
+template <bool BRANCH = true>
+__device__ __forceinline__ float2 drop_mult_pair(const DropCtx& c, uint32_t pair_idx) {
+    if (BRANCH && c.thresh == 0) return make_float2(1.f, 1.f);      // without the branch: thresh 0 keeps everything, scale is 1
+    const uint32_t h = mix32(c.seed + pair_idx * 0x9e3779b9U);
+    const uint32_t thi = c.thresh & 0xffff0000U;          // (h >> 16) < t16  <=>  h < (t16 << 16)
+    return make_float2(((h << 16) < thi) ? 0.f : c.scale, (h < thi) ? 0.f : c.scale);
+}
+__device__ __forceinline__ float drop_mult(const DropCtx& c, uint64_t idx) {
+    if (c.thresh == 0) return 1.f;
+    const uint64_t pair = idx >> 1;
+    const uint32_t h = mix32(c.seed + (uint32_t)pair * 0x9e3779b9U + (uint32_t)(pair >> 32) * 0x85ebca6bU);
+    const uint32_t bits = (idx & 1) ? (h >> 16) : (h & 0xffffU);
+    return (bits < (c.thresh >> 16)) ? 0.f : c.scale;
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

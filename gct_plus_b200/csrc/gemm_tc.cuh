@@ -136,18 +136,23 @@ __device__ __forceinline__ void epilogue_vec8(const Epilogue& e, int row, int co
         for (int j = 0; j < 8; ++j) v.v[j] += b.v[j];
     }
     if (e.flags & EPI_GELU) {
-        if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx, v);
+        if (e.flags & EPI_GELU_GRAD) {
+            f8 dg;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v.v[j] = gelu_erf(v.v[j]);
+            for (int j = 0; j < 8; ++j) dg.v[j] = drop_mult(e.drop, idx + j) * gelu_fast_grad(v.v[j]);
+            st8(reinterpret_cast<T*>(e.aux_out) + idx, dg);
+        } else if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = gelu_fast(v.v[j]);
     }
     if (e.drop.thresh) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v.v[j] = drop_apply(e.drop, idx + j, v.v[j]);
     }
-    if (e.flags & EPI_DGELU) {
+    if (e.flags & (EPI_DGELU | EPI_MUL_AUX)) {
         f8 h = ld8(reinterpret_cast<const T*>(e.aux_in) + idx);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v.v[j] *= gelu_erf_grad(h.v[j]);
+        for (int j = 0; j < 8; ++j) v.v[j] *= (e.flags & EPI_DGELU) ? gelu_fast_grad(h.v[j]) : h.v[j];
     }
     if (e.res32) {
         f8 r = ld8(e.res32 + idx);
@@ -191,7 +196,7 @@ __device__ __forceinline__ void epi_prefetch(const Epilogue& e, int row, int col
 #pragma unroll
         for (int j = 0; j < NJ; ++j) o.r[j] = ld8(e.res32 + idx + 8 * j);
     }
-    if (e.flags & EPI_DGELU) {
+    if (e.flags & (EPI_DGELU | EPI_MUL_AUX)) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) o.h[j] = ld8(reinterpret_cast<const T*>(e.aux_in) + idx + 8 * j);
     }
@@ -210,7 +215,12 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, 
             for (int k = 0; k < 8; ++k) v.v[k] += o.b[j].v[k];
         }
         if (e.flags & EPI_GELU) {
-            if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
+            if (e.flags & EPI_GELU_GRAD) {
+                f8 dg;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dg.v[k] = drop_mult(e.drop, idx + 8 * j + k) * gelu_fast_grad(v.v[k]);
+                st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, dg);
+            } else if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v.v[k] = gelu_fast(v.v[k]);
         }
@@ -222,6 +232,10 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, 
         if (e.flags & EPI_DGELU) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) v.v[k] *= gelu_fast_grad(o.h[j].v[k]);
+        }
+        if (e.flags & EPI_MUL_AUX) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] *= o.h[j].v[k];
         }
         if (e.res32) {
 #pragma unroll
@@ -266,7 +280,7 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
 #pragma unroll
         for (int i = 0; i < 4; ++i) r4[i] = *(reinterpret_cast<const float4*>(e.res32 + off) + i);
     }
-    if constexpr (ACT == 2) {
+    if constexpr (ACT == 2 || ACT == 4) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) h2[i] = *(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.aux_in) + off) + i);
     }
@@ -289,13 +303,25 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
             }
         }
         if constexpr (WHICH == 1) return;        // aux-only pass: the pre-activation is all that was wanted
+        const uint32_t pair0 = (uint32_t)(off >> 1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
-    }
-    if (e.drop.thresh) {
+        for (int i = 0; i < 8; ++i) {            // packed fp32x2 GELU with the dropout multiplier folded in
+            const float2 g = gelu_pair_fwd(make_float2(v[2 * i], v[2 * i + 1]), drop_mult_pair(e.drop, pair0 + i));
+            v[2 * i] = g.x; v[2 * i + 1] = g.y;
+        }
+    } else if (e.drop.thresh) {
         const uint32_t pair0 = (uint32_t)(off >> 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) drop_pair(e.drop, pair0 + i, v[2 * i], v[2 * i + 1]);
+    }
+    if constexpr (ACT == 4) {
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(h2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 hf = make_float2(__uint_as_float(hw[i] << 16), __uint_as_float(hw[i] & 0xffff0000u));
+            const float2 r = __fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), hf);
+            v[2 * i] = r.x; v[2 * i + 1] = r.y;
+        }
     }
     if constexpr (ACT == 2) {
         const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(h2);
@@ -336,6 +362,28 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
     }
 }
 
+// GELU forward that also saves the gradient factor, 16 columns of one row in ONE pass over the accumulator:
+//   gp[8] = bf16x2 pairs of keep*gelu(acc + bias),  dp[8] = bf16x2 pairs of keep*gelu'(acc + bias)
+__device__ __forceinline__ void epi_gelu16(const Epilogue& e, const float* __restrict__ bias, uint32_t taddr, size_t off, int col,
+                                           uint32_t* gp, uint32_t* dp) {
+    float4 b4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b4[i] = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
+    float v[16];
+    tmem_ld16(taddr, v);
+    const uint32_t pair0 = (uint32_t)(off >> 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 bb = (i & 1) ? make_float2(b4[i >> 1].z, b4[i >> 1].w) : make_float2(b4[i >> 1].x, b4[i >> 1].y);
+        const float2 x = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), bb);
+        float2 g, dg;
+        gelu_pair(x, drop_mult_pair<false>(e.drop, pair0 + i), g, dg);
+        __nv_bfloat162 gh = __floats2bfloat162_rn(g.x, g.y), dh = __floats2bfloat162_rn(dg.x, dg.y);
+        gp[i] = *reinterpret_cast<uint32_t*>(&gh);
+        dp[i] = *reinterpret_cast<uint32_t*>(&dh);
+    }
+}
+
 // One elected lane hands the warp's staged 32-row x 128-byte tile to the TMA engine (tensor store, SWIZZLE_128B box);
 // rows / columns outside the tensor are clipped by the hardware.  Returns once the tile may be overwritten.
 __device__ __forceinline__ void stage_tma_store(const CUtensorMap* map, uint32_t stg_smem, int col, int row, int lane) {
@@ -372,8 +420,12 @@ __host__ __device__ inline int epi_mode(const Epilogue& e) {
     if ((e.flags & (EPI_ACCUM | EPI_BIAS_ROW | EPI_NOSTORE)) || e.alpha != 1.f || (e.ldc & 7)) return 0;
     const bool b = e.bias != nullptr, r = e.res32 != nullptr, f = e.out32 != nullptr, t = e.outT != nullptr;
     if (f == t) return 0;                                    // exactly one output
-    if (e.flags & EPI_GELU) return (b && !r && t) ? 3 : 0;
+    if (e.flags & EPI_GELU) {
+        if (e.flags & EPI_GELU_GRAD) return (b && !r && t && e.aux_out) ? 9 : 0;
+        return (b && !r && t) ? 3 : 0;
+    }
     if (e.flags & EPI_DGELU) return (!b && !r && t) ? 6 : 0;
+    if (e.flags & EPI_MUL_AUX) return (!b && !r && t) ? 10 : 0;
     if (t) return r ? 0 : (b ? 1 : 5);
     return b ? (r ? 2 : 7) : (r ? 8 : 4);
 }
@@ -394,7 +446,12 @@ __device__ __forceinline__ void epi_compute(const Epilogue& e, int row, int col,
             for (int k = 0; k < 8; ++k) v.v[k] += o.b[j].v[k];
         }
         if (e.flags & EPI_GELU) {
-            if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
+            if (e.flags & EPI_GELU_GRAD) {
+                f8 dg;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) dg.v[k] = drop_mult(e.drop, idx + 8 * j + k) * gelu_fast_grad(v.v[k]);
+                st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, dg);
+            } else if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
 #pragma unroll
             for (int k = 0; k < 8; ++k) v.v[k] = gelu_fast(v.v[k]);
         }
@@ -406,6 +463,10 @@ __device__ __forceinline__ void epi_compute(const Epilogue& e, int row, int col,
         if (e.flags & EPI_DGELU) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) v.v[k] *= gelu_fast_grad(o.h[j].v[k]);
+        }
+        if (e.flags & EPI_MUL_AUX) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v.v[k] *= o.h[j].v[k];
         }
         if (e.res32) {
 #pragma unroll
@@ -755,7 +816,47 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         case 5: GCT_EPI_RUN(false, 0, false, false) break;
                         case 6: GCT_EPI_RUN(false, 2, false, false) break;
                         case 7: GCT_EPI_RUN(true, 0, false, true) break;
-                        default: GCT_EPI_RUN(false, 0, true, true) break;
+                        case 8: GCT_EPI_RUN(false, 0, true, true) break;
+                        case 10: GCT_EPI_RUN(false, 4, false, false) break;
+                        default: {       // 9: GELU + saved gradient factor, one pass over TMEM, two bf16 outputs
+                            constexpr int SEG_COLS = 64 < SLICE ? 64 : SLICE;
+                            constexpr int CPS = SEG_COLS / 16;
+                            const uint32_t stg_s = smem_u32(stg);
+                            const bool tma = use_tma_store && SEG_COLS * 2 == 128;
+#pragma unroll 1
+                            for (int c0 = 0; c0 < NCH; c0 += CPS) {
+                                const int seg0 = c0 * 16;
+                                uint32_t dgp[CPS][8];
+#pragma unroll
+                                for (int ci = 0; ci < CPS; ++ci) {
+                                    uint32_t gp[8];
+                                    epi_gelu16(e, bias, tslice + (c0 + ci) * 16, off0 + (c0 + ci) * 16, colb + (c0 + ci) * 16, gp, dgp[ci]);
+                                    *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2)) = make_uint4(gp[0], gp[1], gp[2], gp[3]);
+                                    *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2 + 1)) = make_uint4(gp[4], gp[5], gp[6], gp[7]);
+                                }
+                                if (tma) {
+                                    stage_tma_store(&tmC, stg_s, colb + seg0, m0 + q * 32, lane);
+                                } else {
+                                    __syncwarp();
+                                    stage_flush(stg, lane, 0, CPS * 2, reinterpret_cast<uint8_t*>(e.outT) + (row0_off + seg0) * 2,
+                                                (size_t)e.ldc * 2, rows_valid);
+                                    __syncwarp();
+                                }
+#pragma unroll
+                                for (int ci = 0; ci < CPS; ++ci) {
+                                    *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2)) = make_uint4(dgp[ci][0], dgp[ci][1], dgp[ci][2], dgp[ci][3]);
+                                    *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2 + 1)) = make_uint4(dgp[ci][4], dgp[ci][5], dgp[ci][6], dgp[ci][7]);
+                                }
+                                if (tma) {
+                                    stage_tma_store(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);
+                                } else {
+                                    __syncwarp();
+                                    stage_flush(stg, lane, 0, CPS * 2, reinterpret_cast<uint8_t*>(e.aux_out) + (row0_off + seg0) * 2,
+                                                (size_t)e.ldc * 2, rows_valid);
+                                    __syncwarp();
+                                }
+                            }
+                        } break;
                     }
 #undef GCT_EPI_RUN
                 }

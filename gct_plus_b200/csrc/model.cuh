@@ -322,7 +322,7 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
             GCT_TRY(m.norm_fwd(a.x1, m.enc_slot(l, E_N2A), m.enc_slot(l, E_N2B), a.a2, a.a2_32, Me));
             {   // g = drop(gelu(a2 W1^T + b1))
                 Epilogue e = Model<T>::epi(m.P(m.enc_slot(l, E_F1_B)), dff);
-                e.flags = EPI_GELU; e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + ES_FF);
+                e.flags = EPI_GELU | EPI_GELU_GRAD; e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + ES_FF);
                 GCT_TRY(m.gemm(a.a2, false, d, m.WT(m.enc_slot(l, E_F1_W)), false, d, Me, dff, d, e));
             }
             {   // xout = a2 + drop(g W2^T + b2)
@@ -402,7 +402,7 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
         GCT_TRY(m.norm_fwd(a.y2, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), a.a3, nullptr, Md));
         {
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff);
-            e.flags = EPI_GELU; e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + DS_FF);
+            e.flags = EPI_GELU | EPI_GELU_GRAD; e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + DS_FF);
             GCT_TRY(m.gemm(a.a3, false, d, m.WT(m.dec_slot(l, D_F1_W)), false, d, Md, dff, d, e));
         }
         {
@@ -447,7 +447,7 @@ struct BwdScratch {
 };
 
 // FFN block backward shared by encoder and decoder layers.
-//   forward:  hpre = a W1^T + b1 ; g = dropF(gelu(hpre)) ; out = res + dropO(g W2^T + b2)
+//   forward:  pre = a W1^T + b1 ; g = dropF(gelu(pre)) ; hpre := keepF*gelu'(pre) ; out = res + dropO(g W2^T + b2)
 //   in: dout (fp32 grad of out).  out: dA (fp32) = dHpre W1 (+ add_to_dA)
 template <typename T>
 static int ffn_backward(Model<T>& m, BwdScratch<T>& S, int M, const float* dout, const T* a, const T* hpre, const T* g,
@@ -456,9 +456,10 @@ static int ffn_backward(Model<T>& m, BwdScratch<T>& S, int M, const float* dout,
     const int d = m.d, dff = m.dff;
     GCT_TRY(m.cast_drop(dout, S.dyT, M, d, drop_out, m.G(f2b)));
     GCT_TRY(m.wgrad(S.dyT, d, g, dff, M, d, dff, f2w, f2b, false));
-    {   // dHpre = dropF'(dY W2) * gelu'(hpre)
+    {   // dHpre = (dY W2) * [keepF * gelu'(pre)]  -- the bracket was saved by the forward epilogue (EPI_GELU_GRAD)
+        (void)drop_ff;
         Epilogue e = Model<T>::epi(nullptr, dff);
-        e.flags = EPI_DGELU; e.aux_in = hpre; e.outT = S.dhT; e.drop = drop_ff;
+        e.flags = EPI_MUL_AUX; e.aux_in = hpre; e.outT = S.dhT;
         GCT_TRY(m.gemm(S.dyT, false, d, m.WT(f2w), true, dff, M, dff, d, e));
     }
     GCT_TRY(m.wgrad(S.dhT, dff, a, d, M, dff, d, f1w, f1b, true));

@@ -96,7 +96,8 @@ int gct_norm_bwd(const float* x, const float* alpha, const float* dy, const floa
                  float* dbias, int rows, int d, void* stream);
 /* Generic GEMM C[M,N] = A(m,k)*B(n,k) (+bias, GELU, residual): nn.Linear of Model/sublayers.py:54-88.
  * a_mn/b_mn: 0 = K-major storage ([M|N rows, K cols]), 1 = MN-major ([K rows, M|N cols]).
- * flags: 1 GELU, 2 dGELU(aux), 4 accumulate into out32.  dtype 1 -> tcgen05, 0 -> SIMT fp32. */
+ * flags: 1 GELU (aux_out <- pre-activation), 2 dGELU(aux_in), 4 accumulate into out32, 128 (with 1) aux_out <-
+ * keep*gelu'(pre) instead of the pre-activation, 256 multiply by aux_in.  dtype 1 -> tcgen05, 0 -> SIMT fp32. */
 int gct_gemm(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
              const float* bias, const float* res32, const void* aux_in, void* aux_out, float* out32, void* outT,
              int ldc, int flags, int split_k, int bn_hint, int dtype, void* stream);

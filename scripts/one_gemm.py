@@ -1,4 +1,5 @@
-"""Runs one tcgen05 GEMM shape a few times (target for `ncu --set full`)."""
+"""Runs one tcgen05 GEMM shape a few times (target for `ncu --set full`).
+usage: one_gemm.py M N K bn [flags [b_mn]]   flags: 1 GELU (+128 saves keep*gelu'), 256 multiply by aux_in"""
 import os
 import sys
 
@@ -9,14 +10,23 @@ sys.path.insert(0, ROOT)
 import gct_plus_b200._lib as L  # noqa: E402
 
 M, N, K, bn = (int(x) for x in sys.argv[1:5])
+flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+b_mn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 dev = torch.device("cuda:0")
 lib = L.lib()
 A = torch.randn(M, K, device=dev).bfloat16()
-B = torch.randn(N, K, device=dev).bfloat16()
+B = (torch.randn(K, N, device=dev) if b_mn else torch.randn(N, K, device=dev)).bfloat16()
 out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-bias = torch.randn(N, device=dev)
-for _ in range(4):
-    L.check(lib.gct_gemm(L.ptr(A), 0, K, L.ptr(B), 0, K, M, N, K, L.ptr(bias), None, None, None, None, L.ptr(out), N, 0, 1, bn, 1,
-                         L.stream_ptr()))
+aux_out = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if flags & 1 else None
+aux_in = torch.randn(M, N, device=dev).bfloat16() if flags & (2 | 256) else None
+bias = torch.randn(N, device=dev) if not (flags & (2 | 256)) else None
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(6):
+    if i == 2:
+        e0.record()
+    L.check(lib.gct_gemm(L.ptr(A), 0, K, L.ptr(B), b_mn, B.stride(0), M, N, K, L.ptr(bias), None, L.ptr(aux_in), L.ptr(aux_out), None,
+                         L.ptr(out), N, flags, 1, bn, 1, L.stream_ptr()))
+e1.record()
 torch.cuda.synchronize()
-print("ok")
+us = e0.elapsed_time(e1) * 1e3 / 4
+print(f"ok M={M} N={N} K={K} flags={flags} b_mn={b_mn}: {us:.1f} us/launch, {2.0 * M * N * K / us / 1e6:.0f} TFLOP/s")

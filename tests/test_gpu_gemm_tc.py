@@ -36,6 +36,26 @@ def test_majorness(a_mn, b_mn, M, N, K, bn):
     _close(out, ref)
 
 
+def _gelu_grad(x):
+    return 0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_gelu_grad_and_mul_aux_small(dtype):
+    """Non-persistent / SIMT tiers of the two epilogue modes the FFN forward / backward use."""
+    M, N, K = 256, 256, 128
+    As, Bs, ref = _ops(M, N, K, False, False, seed=11)
+    bias = torch.randn(N, device=DEV)
+    tol = 1e-2 if dtype == "bf16" else 1e-5
+    A_, B_ = (As, Bs) if dtype == "bf16" else (As.float(), Bs.float())
+    _, outT, aux = gemm(A_, B_, M, N, K, bias=bias, flags=1 | 128, want_T=True, dtype=dtype)
+    _close(outT, torch.nn.functional.gelu(ref + bias), tol)
+    _close(aux, _gelu_grad(ref + bias), tol)
+    aux_in = torch.randn(M, N, device=DEV).to(outT.dtype)
+    _, out2, _ = gemm(A_, B_, M, N, K, flags=256, want_T=True, aux_in=aux_in, dtype=dtype)
+    _close(out2, ref * aux_in.float(), tol)
+
+
 def test_small_vocab_tile():
     As, Bs, ref = _ops(512, 28, 512, False, False, seed=3)      # N = 28 < BN = 32, ldc = 28
     out, _, _ = gemm(As, Bs, 512, 28, 512)
@@ -64,7 +84,7 @@ def test_split_k_accumulate():
 
 
 @pytest.mark.parametrize("N,K", [(512, 512), (1536, 512), (256, 512), (2048, 128), (384, 192)])
-@pytest.mark.parametrize("mode", ["bias_T", "bias_res_F32", "gelu", "plain_F32", "plain_T", "bias_F32", "res_F32"])
+@pytest.mark.parametrize("mode", ["bias_T", "bias_res_F32", "gelu", "gelu_grad", "mul_aux", "plain_F32", "plain_T", "bias_F32", "res_F32"])
 def test_persistent_kernel_epilogue_modes(N, K, mode):
     """More tiles than SMs -> persistent kernel with the specialised, smem-staged epilogue; every mode the model uses."""
     M = 19 * 1024 + 128          # 153 full row tiles (+ a partial-tile run below)
@@ -82,6 +102,14 @@ def test_persistent_kernel_epilogue_modes(N, K, mode):
             _, outT, aux = gemm(As, Bs, Mx, N, K, bias=bias, flags=1, want_T=True)
             _close(aux, ref + bias, 1e-2)
             _close(outT, torch.nn.functional.gelu(ref + bias), 1e-2)
+        elif mode == "gelu_grad":       # EPI_GELU | EPI_GELU_GRAD: aux = gelu'(pre) (dropout off -> keep = 1)
+            _, outT, aux = gemm(As, Bs, Mx, N, K, bias=bias, flags=1 | 128, want_T=True)
+            _close(outT, torch.nn.functional.gelu(ref + bias), 1e-2)
+            _close(aux, _gelu_grad(ref + bias), 1e-2)
+        elif mode == "mul_aux":         # EPI_MUL_AUX: out = acc * aux_in
+            aux_in = torch.randn(Mx, N, device=DEV).bfloat16()
+            _, outT, _ = gemm(As, Bs, Mx, N, K, flags=256, want_T=True, aux_in=aux_in)
+            _close(outT, ref * aux_in.float(), 1e-2)
         elif mode == "plain_F32":
             out, _, _ = gemm(As, Bs, Mx, N, K)
             _close(out, ref)
