@@ -61,7 +61,7 @@ _PROTOS = {
                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "gct_attention_fwd": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, i64, C.c_int, vp, C.c_int, vp, vp,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
-    "gct_attention_bwd": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, i64, C.c_int, vp, vp, C.c_int, vp,
+    "gct_attention_bwd": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, i64, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp,
                                     C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "gct_src_mask": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "gct_trg_mask": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),

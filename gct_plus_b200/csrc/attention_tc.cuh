@@ -1,17 +1,22 @@
 // tcgen05 attention for the training / teacher-forced path: L <= 128, d_k = 64, bf16 operands.
-// One CTA per (batch, head); thread t owns query row t (= TMEM lane t), so the softmax needs no
-// shuffles: each thread reads its whole score row out of TMEM.
+// One CTA per (batch, head), 256 threads: thread (q = warp % 4, half = warp / 4, lane) owns query row q*32+lane
+// (= its TMEM lane) and one half of the score columns, which it reads from TMEM in 16-column pieces -- twice in the
+// forward (row max, then exp / sum / dropout), once in the backward -- so the register footprint stays small and
+// several CTAs are co-resident per SM (4 forward, 2 backward): one CTA's TMA / MMA latency hides behind another's math.
 //
-//   forward :  S = Q K^T          (UMMA 128 x Lk16 x 64, A/B K-major)          -> TMEM cols [0,128)
-//              P = dropout(exp(scale*S - max)) as bf16 into swizzled smem       (row max / sum in registers)
-//              O = P V            (UMMA 128 x 64 x Lk, A = P K-major, B = V MN-major) -> TMEM cols [128,192)
+//   forward :  S = Q K^T          (UMMA 128 x NS x 64, A/B K-major)             -> TMEM cols [0,NS), NS = ceil16(Lk)
+//              P = dropout(exp2(c*S - max)) as bf16 into swizzled smem (over the dead Q/K tiles)
+//              O = P V            (UMMA 128 x 64 x NS, A = P K-major, B = V MN-major) -> TMEM cols [0,64) (S is dead)
 //              out = O / sum, lse = max + log(sum)
-//   backward:  S = Q K^T, dP = dO V^T  -> TMEM;  P = exp(scale*S - lse), D = sum_j P dP',
-//              dS = P (dP' - D), Pd = dropout(P) to smem;  then three UMMAs that reuse the SAME smem tiles under
-//              different descriptors:  dV = Pd^T dO (A = Pd MN-major, B = dO MN-major),
-//              dQ = dS K (A = dS K-major, B = K MN-major),  dK = dS^T Q (A = dS MN-major, B = Q MN-major).
-// Q/K/V/dO tiles arrive by TMA (box 64 x 128 rows, SWIZZLE_128B); rows past this batch element's length
-// belong to the next element (finite) or are zero-filled and are neutralised by zeroing the matching P / dS entries.
+//   backward:  S = Q K^T, dP = dO V^T -> TMEM;  D = rowsum(dO * O) (from the saved forward output, identical to
+//              sum_j P dP' also under dropout);  P = exp(scale*S - lse), dS = P (dP' - D) scale, Pd = dropout(P) to smem;
+//              then three UMMAs that reuse the SAME smem tiles under different descriptors:
+//              dV = Pd^T dO (A = Pd MN-major, B = dO MN-major), dQ = dS K (A = dS K-major, B = K MN-major),
+//              dK = dS^T Q (A = dS MN-major, B = Q MN-major).
+// Q/K/V/dO tiles arrive by TMA (box 64 x ceil16(L) rows, SWIZZLE_128B); rows past this batch element's length belong to
+// the next element (finite) or are zero-filled and are neutralised by zeroing the matching P / dS entries.  UMMA reads
+// of M = 128 rows from a shorter tile run into the neighbouring tile (finite bits, rows never stored).
+// The byte mask [B,(1|Lq),Lk] is packed to one bit per key while the TMA loads are in flight.
 #pragma once
 #include "attention.cuh"
 #include "gemm_tc.cuh"
@@ -20,67 +25,90 @@
 namespace atc {
 using namespace tc;
 
-constexpr int TILE = 16384;          // 128 rows x 128 B
-
-// copies n mask bytes global -> shared with 16-byte loads; returns the shared pointer that mirrors `mg`
-// (offset so that both sides share the same 16-byte misalignment)
-__device__ __forceinline__ const uint8_t* load_mask(const uint8_t* __restrict__ mg, int n, uint8_t* mask_s, int t, int nt) {
-    const int mis = (int)(reinterpret_cast<uintptr_t>(mg) & 15);
-    uint8_t* ms = mask_s + mis;
-    const int head = min(n, (16 - mis) & 15);
-    if (t < head) ms[t] = mg[t];
-    const int nvec = (n - head) >> 4;
-    const uint4* src = reinterpret_cast<const uint4*>(mg + head);
-    uint4* dst = reinterpret_cast<uint4*>(ms + head);
-    for (int i = t; i < nvec; i += nt) dst[i] = src[i];
-    for (int i = head + nvec * 16 + t; i < n; i += nt) ms[i] = mg[i];
-    return ms;
-}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kFill2 = -1.4426950408889634e9f;     // the reference's -1e9 fill, in log2 units
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// byte offset of element (row, col) inside a [2][128][64] bf16 tile pair with the 128B swizzle (col in [0,128))
-__device__ __forceinline__ uint32_t swz_off(int row, int col) {
-    const int blk = col >> 6, c = col & 63;
-    return (uint32_t)(blk * TILE + row * 128 + ((((c >> 3) ^ (row & 7)) << 4) | ((c & 7) << 1)));
-}
-// stores 8 consecutive columns [col, col+8) of row `row` (col % 8 == 0) as bf16
-__device__ __forceinline__ void st_row8(uint8_t* tile, int row, int col, const float* v) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+// byte offset of 16-byte chunk `chunk` (8 bf16 columns) of row `row` inside one [rows][64] bf16 block, 128B swizzle
+__device__ __forceinline__ uint32_t swz16(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// bits[r*4 + w]: bit (j % 32) of word j / 32 is set iff key j is visible to query row r.  nrows = 1 for a broadcast
+// key-padding row.  Loads are issued eight rows at a time so that their latencies overlap.
+__device__ __forceinline__ void build_mask_bits(const uint8_t* __restrict__ mg, int nrows, int Lk, int rstride, uint32_t* bits,
+                                                int warp, int lane, int nwarp) {
+    const int nw = (Lk + 31) >> 5;
+    for (int r0 = warp * 8; r0 < nrows; r0 += nwarp * 8) {
+        for (int w = 0; w < nw; ++w) {
+            const int j = w * 32 + lane;
+            uint8_t m[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(tile + swz_off(row, col)) = u;
+            for (int i = 0; i < 8; ++i) m[i] = (j < Lk && r0 + i < nrows) ? mg[(size_t)(r0 + i) * rstride + j] : (uint8_t)0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t word = __ballot_sync(0xffffffffu, m[i] != 0);
+                if (lane == 0 && r0 + i < nrows) bits[(r0 + i) * 4 + w] = word;
+            }
+        }
+    }
+}
+// the 16 mask bits of 16-column chunk c16
+__device__ __forceinline__ uint32_t mask16(const uint4& mb, int c16) {
+    const uint32_t w = (c16 < 4) ? ((c16 < 2) ? mb.x : mb.y) : ((c16 < 6) ? mb.z : mb.w);
+    return w >> ((c16 & 1) << 4);
+}
+// raw scores -> masked scores in log2 units: visible -> c*s, masked -> fill, past the last key (TAIL chunk only) -> -inf
+template <bool TAIL>
+__device__ __forceinline__ void score16(float* v, uint32_t m16, float cs, int nvalid) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 s = __fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(cs, cs));
+        v[2 * i] = (m16 & (1u << (2 * i))) ? s.x : kFill2;
+        v[2 * i + 1] = (m16 & (2u << (2 * i))) ? s.y : kFill2;
+        if (TAIL) {
+            if (2 * i >= nvalid) v[2 * i] = -CUDART_INF_F;
+            if (2 * i + 1 >= nvalid) v[2 * i + 1] = -CUDART_INF_F;
+        }
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
 }
 
-struct FwdSmem {
-    static constexpr int Q = 0, K = TILE, V = 2 * TILE, P = 3 * TILE, MASK = 5 * TILE, RED = MASK + 16384 + 64,
-                         BARS = RED + 2 * 4 * 128 * 4;
-    static constexpr int TOTAL = BARS + 64 + 1024;
+struct FwdLayout {
+    int q, k, v, bits, red, bars, total;       // byte offsets from the 1 KB-aligned base; P aliases [0, 32768)
+    __host__ __device__ FwdLayout(int RPq, int RPk) {
+        q = 0; k = RPq * 128;
+        int qk = k + RPk * 128;
+        if (qk < 32768) qk = 32768;
+        v = qk; bits = v + RPk * 128; red = bits + 2048; bars = red + 2048; total = bars + 64 + 1024;
+    }
 };
 
-// Forward: 256 threads.  Thread (q = warp % 4, half = warp / 4, lane) owns query row q*32+lane (its TMEM lane) and
-// the score columns [64*half, 64*half+64); row max / sum are combined across the two halves through shared memory.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + FwdSmem::BARS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + FwdSmem::BARS + 32);
-    uint8_t* mask_s = sm + FwdSmem::MASK;
-    float* red = reinterpret_cast<float*>(sm + FwdSmem::RED);      // [2 kinds][2 halves][128 rows]
+    const int Lq = p.Lq, Lk = p.Lk;
+    const int RPq = (Lq + 15) & ~15, NS = (Lk + 15) & ~15;
+    const FwdLayout L(RPq, NS);
+    const uint32_t bars = base + L.bars;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bars + 32);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(sm + L.bits);
+    float* red = reinterpret_cast<float*>(sm + L.red);       // [2 kinds][2 halves][128 rows]
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
-    const int Lq = p.Lq, Lk = p.Lk;
     if (t == 32) {
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -89,50 +117,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (t == 0) {
-        mbar_expect_tx(bars, 3 * TILE);
-        tma_load_2d(base + FwdSmem::Q, &tmQ, h * 64, b * Lq, bars);
-        tma_load_2d(base + FwdSmem::K, &tmK, h * 64, b * Lk, bars);
-        tma_load_2d(base + FwdSmem::V, &tmV, h * 64, b * Lk, bars);
+        mbar_expect_tx(bars, (uint32_t)(RPq + 2 * NS) * 128u);
+        tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
+        tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
+        tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
     }
     const bool dense = p.mask_rstride != 0;
-    const uint8_t* mask_l = mask_s;
-    if (p.mask) mask_l = load_mask(p.mask + (size_t)b * p.mask_bstride, dense ? Lq * Lk : Lk, mask_s, t, 256);
+    if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
     __syncthreads();
     mbar_wait(bars, 0);
-    const int NS = (Lk + 15) & ~15;
     if (t == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(128, NS, false, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem, make_smem_desc(base + FwdSmem::Q + k * 32, 16, 1024), make_smem_desc(base + FwdSmem::K + k * 32, 16, 1024),
-                      idesc, k > 0 ? 1u : 0u);
+            umma_bf16(tmem, make_smem_desc(base + L.q + k * 32, 16, 1024), make_smem_desc(base + L.k + k * 32, 16, 1024), idesc,
+                      k > 0 ? 1u : 0u);
         umma_commit(bars + 8);
     }
+    // this thread's 16-column chunks: [cbeg, cend)
+    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
+    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const bool wactive = q * 32 < Lq;                 // warp-uniform: the warp owns at least one real query row
+    uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (p.mask) mb = *reinterpret_cast<const uint4*>(bits + (dense ? min(row, Lq - 1) : 0) * 4);
+    const float cs = p.scale * kLog2e;
     mbar_wait(bars + 8, 0);
     __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge after the elected-thread branch / spin loop
     tcgen05_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    const int nch = (Lk + 31) >> 5;                  // 32-column chunks that hold keys
-    const int c0 = half * 2;                         // this thread's chunks: c0, c0+1
-    const uint8_t* mrow = p.mask ? (mask_l + (dense ? min(row, Lq - 1) * Lk : 0)) : nullptr;
-    float v[64];
-    float mx = -INFINITY;
+    float mx = -CUDART_INF_F;
+    if (wactive) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        const int c = c0 + cc;
-        if (c < nch) {                               // warp-uniform
-            tmem_ld32(trow + c * 32, v + cc * 32);
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c16 = cbeg + ci;
+            if (c16 < cend) {
+                float v[16];
+                tmem_ld16(trow + c16 * 16, v);
+                const int nvalid = Lk - c16 * 16;
+                if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
+                else score16<true>(v, mask16(mb, c16), cs, nvalid);
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = c * 32 + jj;
-                float s = -INFINITY;
-                if (j < Lk) {
-                    s = v[cc * 32 + jj] * p.scale;
-                    if (mrow && mrow[j] == 0) s = -1e9f;
-                }
-                v[cc * 32 + jj] = s;
-                mx = fmaxf(mx, s);
+                for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
             }
         }
     }
@@ -140,21 +166,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     mx = fmaxf(red[row], red[128 + row]);
     float sum = 0.f;
-    const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
     const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
+    if (wactive) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        const int c = c0 + cc;
-        if (c < nch) {
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c16 = cbeg + ci;
+            if (c16 < cend) {
+                float v[16];
+                tmem_ld16(trow + c16 * 16, v);
+                const int nvalid = Lk - c16 * 16;
+                if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
+                else score16<true>(v, mask16(mb, c16), cs, nvalid);
+                uint32_t pk[8];
+                const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;      // drow32 is even
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = c * 32 + jj;
-                float pj = 0.f;
-                if (j < Lk) {
-                    pj = __expf(v[cc * 32 + jj] - mx);
-                    sum += pj;
+                for (int i = 0; i < 8; ++i) {
+                    const float2 d = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(-mx, -mx));
+                    float2 e = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                    sum += e.x + e.y;
+                    e = __fmul2_rn(e, drop_mult_pair<true>(p.drop, pair0 + i));
+                    pk[i] = pack_bf16(e.x, e.y);
                 }
-                v[cc * 32 + jj] = pj;
+                uint8_t* pt = sm + (c16 >> 2) * 16384;
+                *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
         }
     }
@@ -162,46 +197,43 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     sum = red[256 + row] + red[256 + 128 + row];
     const float inv = 1.f / sum;
+    if (p.probs && wactive) {          // get_attn: normalised pre-dropout probabilities (S is still intact in TMEM)
+        const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
+#pragma unroll 1
+        for (int c16 = cbeg; c16 < cend; ++c16) {
+            float v[16];
+            tmem_ld16(trow + c16 * 16, v);
+            const int nvalid = Lk - c16 * 16;
+            score16<true>(v, mask16(mb, c16), cs, nvalid);
+            if (row < Lq) {
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-        const int c = c0 + cc;
-        if (c < nch) {
-            if (p.probs && row < Lq) {
-#pragma unroll
-                for (int jj = 0; jj < 32; ++jj)
-                    if (c * 32 + jj < Lk) p.probs[prow + c * 32 + jj] = v[cc * 32 + jj] * inv;
+                for (int i = 0; i < 16; ++i)
+                    if (i < nvalid) p.probs[prow + c16 * 16 + i] = ex2_approx(v[i] - mx) * inv;
             }
-            if (p.drop.thresh) {
-                const uint32_t pair0 = (drow32 + (uint32_t)(c * 32)) >> 1;      // drow32 is even
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) drop_pair(p.drop, pair0 + jj, v[cc * 32 + 2 * jj], v[cc * 32 + 2 * jj + 1]);
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) st_row8(sm + FwdSmem::P, row, c * 32 + g * 8, v + cc * 32 + g * 8);
         }
     }
-    if (half == 0 && row < Lq && p.lse) p.lse[((size_t)b * p.H + h) * Lq + row] = mx + __logf(sum);
+    if (half == 0 && row < Lq && p.lse) p.lse[((size_t)b * p.H + h) * Lq + row] = (mx + __log2f(sum)) * kLn2;
     fence_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     if (t == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(128, 64, false, true);
-        const int nk = (Lk + 15) >> 4;
+        const int nk = NS >> 4;
         for (int k = 0; k < nk; ++k)
-            umma_bf16(tmem + 128, make_smem_desc(base + FwdSmem::P + (k >> 2) * TILE + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(base + FwdSmem::V + k * 2048, 8192, 1024), idesc, k > 0 ? 1u : 0u);
+            umma_bf16(tmem, make_smem_desc(base + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(base + L.v + k * 2048, 8192, 1024), idesc, k > 0 ? 1u : 0u);
         umma_commit(bars + 16);
     }
     mbar_wait(bars + 16, 0);
     __syncwarp();
     tcgen05_fence_after();
-    {
+    if (wactive) {
         // O is 64 columns: each half stores 32 of them
         float o32[32];
-        bf16* og = reinterpret_cast<bf16*>(p.O) + ((size_t)b * Lq + row) * p.ldo + h * 64 + half * 32;
-        tmem_ld32(trow + 128 + half * 32, o32);
+        tmem_ld32(trow + half * 32, o32);
         if (row < Lq) {
+            bf16* og = reinterpret_cast<bf16*>(p.O) + ((size_t)b * Lq + row) * p.ldo + h * 64 + half * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 f8 o;
@@ -213,33 +245,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
-struct BwdSmem {
-    static constexpr int Q = 0, K = TILE, V = 2 * TILE, DO = 3 * TILE, PD = 4 * TILE, DS = 6 * TILE, MASK = 8 * TILE,
-                         RED = MASK + 16384 + 64, BARS = RED + 4 * 128 * 4;
-    static constexpr int TOTAL = BARS + 64 + 1024;
+struct BwdLayout {
+    int BS, pd, ds, dO, q, k, v, bits, red, bars, total;      // BS = bytes of one [RPq][64] block
+    __host__ __device__ BwdLayout(int RPq, int RPk) {
+        BS = RPq * 128;
+        pd = 0; ds = 2 * BS; dO = 4 * BS; q = 5 * BS; k = 6 * BS; v = k + RPk * 128; bits = v + RPk * 128;
+        red = bits + 2048; bars = red + 1024; total = bars + 64;
+        // UMMA A operands always span 128 rows: keep the furthest such read (Q as A of S) inside the allocation
+        if (total < q + 16384) total = q + 16384;
+        total += 1024;
+    }
 };
 
-// Backward: 512 threads.  Thread (q = warp % 4, c = warp / 4, lane) owns query row q*32+lane and the 32 score /
-// dP columns of chunk c, which it reads from TMEM exactly once; D is combined across the four chunks through
-// shared memory.  dV / dK / dQ reuse the TMEM columns of S / dP once those are dead.
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, AttnBwdParams bp) {
     const AttnParams& p = bp.f;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bars = base + BwdSmem::BARS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + BwdSmem::BARS + 32);
-    uint8_t* mask_s = sm + BwdSmem::MASK;
-    float* red = reinterpret_cast<float*>(sm + BwdSmem::RED);      // [4 chunks][128 rows]
+    const int Lq = p.Lq, Lk = p.Lk;
+    const int RPq = (Lq + 15) & ~15, NS = (Lk + 15) & ~15;
+    const BwdLayout L(RPq, NS);
+    const uint32_t bars = base + L.bars;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bars + 32);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(sm + L.bits);
+    float* red = reinterpret_cast<float*>(sm + L.red);        // [2 halves][128 rows]
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int q = warp & 3, c = warp >> 2, row = q * 32 + lane;
-    const int Lq = p.Lq, Lk = p.Lk;
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
     if (t == 32) {
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -255,141 +292,137 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tmem = *tmem_slot;
     // TMEM columns: S [0,128)  dP [128,256); after the softmax pass: dV [0,64)  dK [64,128)  dQ [128,192)
     if (t == 0) {
-        mbar_expect_tx(bars, 4 * TILE);
-        tma_load_2d(base + BwdSmem::Q, &tmQ, h * 64, b * Lq, bars);
-        tma_load_2d(base + BwdSmem::K, &tmK, h * 64, b * Lk, bars);
-        tma_load_2d(base + BwdSmem::V, &tmV, h * 64, b * Lk, bars);
-        tma_load_2d(base + BwdSmem::DO, &tmDO, h * 64, b * Lq, bars);
+        mbar_expect_tx(bars, (uint32_t)(2 * RPq + 2 * NS) * 128u);
+        tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
+        tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
+        tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
+        tma_load_2d(base + L.dO, &tmDO, h * 64, b * Lq, bars);
     }
     const bool dense = p.mask_rstride != 0;
-    const uint8_t* mask_l = mask_s;
-    if (p.mask) mask_l = load_mask(p.mask + (size_t)b * p.mask_bstride, dense ? Lq * Lk : Lk, mask_s, t, 512);
+    if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
+    const bool qok = row < Lq;
+    // forward output row (32 of its 64 columns) for D = rowsum(dO * O): requested before the TMA wait
+    uint4 ov[4];
+    if (qok) {
+        const uint4* og = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.O) + ((size_t)b * Lq + row) * p.ldo + h * 64 + half * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ov[i] = og[i];
+    }
+    const float lse2 = qok ? p.lse[((size_t)b * p.H + h) * Lq + row] * kLog2e : 0.f;
     __syncthreads();
     mbar_wait(bars, 0);
-    const int NS = (Lk + 15) & ~15;
     if (t == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(128, NS, false, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem, make_smem_desc(base + BwdSmem::Q + k * 32, 16, 1024), make_smem_desc(base + BwdSmem::K + k * 32, 16, 1024),
-                      idesc, k > 0 ? 1u : 0u);
+            umma_bf16(tmem, make_smem_desc(base + L.q + k * 32, 16, 1024), make_smem_desc(base + L.k + k * 32, 16, 1024), idesc,
+                      k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + 128, make_smem_desc(base + BwdSmem::DO + k * 32, 16, 1024),
-                      make_smem_desc(base + BwdSmem::V + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+            umma_bf16(tmem + 128, make_smem_desc(base + L.dO + k * 32, 16, 1024), make_smem_desc(base + L.v + k * 32, 16, 1024),
+                      idesc, k > 0 ? 1u : 0u);
         umma_commit(bars + 8);
     }
+    float D = 0.f;
+    if (qok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 dv = *reinterpret_cast<const uint4*>(sm + L.dO + swz16(row, half * 4 + i));
+            const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&dv);
+            const __nv_bfloat162* o = reinterpret_cast<const __nv_bfloat162*>(&ov[i]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 af = __bfloat1622float2(a[e]), of = __bfloat1622float2(o[e]);
+                D = fmaf(af.x, of.x, D);
+                D = fmaf(af.y, of.y, D);
+            }
+        }
+    }
+    red[half * 128 + row] = D;
+    __syncthreads();
+    D = red[row] + red[128 + row];
+    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
+    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const bool wlive = q * 32 < RPq;                  // warp-uniform: rows the MN-major (query-row K dimension) reads touch
+    uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (p.mask) mb = *reinterpret_cast<const uint4*>(bits + (dense ? min(row, Lq - 1) : 0) * 4);
+    const float cs = p.scale * kLog2e;
+    const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
     mbar_wait(bars + 8, 0);
     __syncwarp();
     tcgen05_fence_after();
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    const int nch = (Lk + 31) >> 5;
-    const bool qok = row < Lq;
-    const bool live = c < nch;                        // warp-uniform: this chunk holds keys
-    const uint8_t* mrow = p.mask ? (mask_l + (dense ? min(row, Lq - 1) * Lk : 0)) : nullptr;
-    const float lse = qok ? p.lse[((size_t)b * p.H + h) * Lq + row] : 0.f;
-    const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
-    float s[32], g[32], pd_keep[32];
-    const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
-    float D = 0.f;
-    if (live) {
-        tmem_ld32(trow + c * 32, s);
-        tmem_ld32(trow + 128 + c * 32, g);
+    if (wlive) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = c * 32 + jj;
-            float pr = 0.f, gd = 0.f;
-            if (qok && j < Lk) {
-                float sc = s[jj] * p.scale;
-                const bool masked = mrow && mrow[j] == 0;
-                if (masked) sc = -1e9f;
-                pr = __expf(sc - lse);
-                gd = masked ? CUDART_INF_F : g[jj];   // INF marks "no gradient through a masked score" (pr is 0 there anyway)
-            }
-            s[jj] = pr;
-            g[jj] = gd;
-        }
-        // dropout: one hash per element pair, the same mask for the probability (Pd) and for its gradient
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c16 = cbeg + ci;
+            if (c16 < cend) {
+                float s[16], g[16];
+                tmem_ld16(trow + c16 * 16, s);
+                tmem_ld16(trow + 128 + c16 * 16, g);
+                const uint32_t m16 = mask16(mb, c16);
+                const int nvalid = Lk - c16 * 16;
+                if (nvalid >= 16) score16<false>(s, m16, cs, 16);
+                else score16<true>(s, m16, cs, nvalid);
+                uint32_t pk[8], dk[8];
+                const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) pd_keep[jj] = s[jj];
-        if (p.drop.thresh) {
-            const uint32_t pair0 = (drow32 + (uint32_t)(c * 32)) >> 1;
-            const uint32_t t16 = p.drop.thresh >> 16;
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-                const uint32_t hsh = mix32(p.drop.seed + (pair0 + jj) * 0x9e3779b9U);
-                const float k0 = ((hsh & 0xffffU) < t16) ? 0.f : p.drop.scale, k1 = ((hsh >> 16) < t16) ? 0.f : p.drop.scale;
-                pd_keep[2 * jj] *= k0; pd_keep[2 * jj + 1] *= k1;
-                if (g[2 * jj] != CUDART_INF_F) g[2 * jj] *= k0;
-                if (g[2 * jj + 1] != CUDART_INF_F) g[2 * jj + 1] *= k1;
+                for (int i = 0; i < 8; ++i) {
+                    const float2 d = __fadd2_rn(make_float2(s[2 * i], s[2 * i + 1]), make_float2(-lse2, -lse2));
+                    const float2 pr = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                    const float2 keep = drop_mult_pair<true>(p.drop, pair0 + i);
+                    const float2 pd = __fmul2_rn(pr, keep);
+                    const float2 gd = __ffma2_rn(make_float2(g[2 * i], g[2 * i + 1]), keep, make_float2(-D, -D));
+                    float2 ds = __fmul2_rn(__fmul2_rn(pr, make_float2(p.scale, p.scale)), gd);     // 1/sqrt(dk) of dQ / dK folded in
+                    // no gradient through a masked score (the reference's masked_fill); a padded column has pr = 0 already
+                    if (!(m16 & (1u << (2 * i)))) ds.x = 0.f;
+                    if (!(m16 & (2u << (2 * i)))) ds.y = 0.f;
+                    pk[i] = qok ? pack_bf16(pd.x, pd.y) : 0u;
+                    dk[i] = qok ? pack_bf16(ds.x, ds.y) : 0u;
+                }
+                const uint32_t blk = (uint32_t)(c16 >> 2) * (uint32_t)L.BS;
+                const int ch = (c16 & 3) * 2;
+                if (row < RPq) {      // a block holds RPq rows: rows past it would land in the next block / tile
+                    *reinterpret_cast<uint4*>(sm + L.pd + blk + swz16(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(sm + L.pd + blk + swz16(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+                    *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch + 1)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+                }
             }
         }
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            if (g[jj] != CUDART_INF_F) D += s[jj] * g[jj];
-        }
-    }
-    red[c * 128 + row] = D;
-    tcgen05_fence_before();
-    __syncthreads();
-    D = red[row] + red[128 + row] + red[256 + row] + red[384 + row];
-    if (live) {
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = c * 32 + jj;
-            const float pr = s[jj];
-            float ds = 0.f, pd = 0.f;
-            if (qok && j < Lk) {
-                pd = pd_keep[jj];
-                ds = (g[jj] == CUDART_INF_F) ? 0.f : pr * (g[jj] - D) * p.scale;   // 1/sqrt(dk) of dQ / dK folded in
-            }
-            s[jj] = pd;
-            g[jj] = ds;
-        }
-    } else {
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) { s[jj] = 0.f; g[jj] = 0.f; }
-    }
-    // every chunk (also the key-less ones) is written: the MN-major reads below touch all 128 key columns
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-        st_row8(sm + BwdSmem::PD, row, c * 32 + q4 * 8, s + q4 * 8);
-        st_row8(sm + BwdSmem::DS, row, c * 32 + q4 * 8, g + q4 * 8);
     }
     fence_async_smem();
     tcgen05_fence_before();
     __syncthreads();
     if (t == 0) {
         tcgen05_fence_after();
-        // dV[key, dk] = Pd^T dO : M = keys (MN-major A, two 64-key blocks TILE apart), K = query rows, N = dk
+        const int nq = RPq >> 4, nk = NS >> 4;
+        // dV[key, dk] = Pd^T dO : M = keys (MN-major A, two 64-key blocks BS apart), K = query rows, N = dk
         const uint32_t idT = make_idesc(128, 64, true, true);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)       // 16 query rows per MMA
-            umma_bf16(tmem, make_smem_desc(base + BwdSmem::PD + k * 2048, TILE, 1024),
-                      make_smem_desc(base + BwdSmem::DO + k * 2048, 8192, 1024), idT, k > 0 ? 1u : 0u);
+        for (int k = 0; k < nq; ++k)          // 16 query rows per MMA
+            umma_bf16(tmem, make_smem_desc(base + L.pd + k * 2048, (uint32_t)L.BS, 1024),
+                      make_smem_desc(base + L.dO + k * 2048, 8192, 1024), idT, k > 0 ? 1u : 0u);
         // dK[key, dk] = dS^T Q
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + 64, make_smem_desc(base + BwdSmem::DS + k * 2048, TILE, 1024),
-                      make_smem_desc(base + BwdSmem::Q + k * 2048, 8192, 1024), idT, k > 0 ? 1u : 0u);
+        for (int k = 0; k < nq; ++k)
+            umma_bf16(tmem + 64, make_smem_desc(base + L.ds + k * 2048, (uint32_t)L.BS, 1024),
+                      make_smem_desc(base + L.q + k * 2048, 8192, 1024), idT, k > 0 ? 1u : 0u);
         // dQ[q, dk] = dS K : A = dS K-major over keys, B = K MN-major
         const uint32_t idQ = make_idesc(128, 64, false, true);
-        const int nk = (Lk + 15) >> 4;
         for (int k = 0; k < nk; ++k)
-            umma_bf16(tmem + 128, make_smem_desc(base + BwdSmem::DS + (k >> 2) * TILE + (k & 3) * 32, 16, 1024),
-                      make_smem_desc(base + BwdSmem::K + k * 2048, 8192, 1024), idQ, k > 0 ? 1u : 0u);
+            umma_bf16(tmem + 128, make_smem_desc(base + L.ds + (k >> 2) * L.BS + (k & 3) * 32, 16, 1024),
+                      make_smem_desc(base + L.k + k * 2048, 8192, 1024), idQ, k > 0 ? 1u : 0u);
         umma_commit(bars + 16);
     }
     mbar_wait(bars + 16, 0);
     __syncwarp();
     tcgen05_fence_after();
-    // six 32-column result chunks over the 16 warps: chunk id = c (dV lo, dV hi, dK lo, dK hi), then c < 2: dQ lo / hi
-    auto store_chunk = [&](uint32_t col, void* dst, int ld, int L, int coff) {
+    // each thread: 32 of the 64 columns of its dV / dK row (row = key) and of its dQ row (row = query)
+    auto store_chunk = [&](uint32_t col, void* dst, int ld, int Lr) {
         float v[32];
-        tmem_ld32(trow + col, v);
-        if (row < L) {
-            bf16* og = reinterpret_cast<bf16*>(dst) + ((size_t)b * L + row) * ld + h * 64 + coff;
+        tmem_ld32(trow + col + half * 32, v);
+        if (row < Lr) {
+            bf16* og = reinterpret_cast<bf16*>(dst) + ((size_t)b * Lr + row) * ld + h * 64 + half * 32;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
                 f8 o;
@@ -399,54 +432,58 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     };
-    if (c < 2) {
-        store_chunk(c * 32, bp.dV, bp.lddv, Lk, c * 32);
-        store_chunk(128 + c * 32, bp.dQ, bp.lddq, Lq, c * 32);
-    } else {
-        store_chunk(64 + (c - 2) * 32, bp.dK, bp.lddk, Lk, (c - 2) * 32);
+    if (q * 32 < Lk) {
+        store_chunk(0, bp.dV, bp.lddv, Lk);
+        store_chunk(64, bp.dK, bp.lddk, Lk);
     }
+    if (q * 32 < Lq) store_chunk(128, bp.dQ, bp.lddq, Lq);
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-static int operand_map(const void* ptr, int ld, int rows, int H, CUtensorMap* out) {
-    return get_tensor_map(ptr, (uint64_t)H * 64, (uint64_t)rows, (uint64_t)ld * 2, 64, 128, out);
+static int operand_map(const void* ptr, int ld, int rows, int H, int box_rows, CUtensorMap* out) {
+    return get_tensor_map(ptr, (uint64_t)H * 64, (uint64_t)rows, (uint64_t)ld * 2, 64, (uint32_t)box_rows, out);
 }
 
 static bool supported(const AttnParams& p) {
-    return p.Lq <= 128 && p.Lk <= 128 && p.Lk >= 1 && (p.ldq % 8) == 0 && (p.ldk % 8) == 0 && (p.ldv % 8) == 0 &&
-           (!p.mask || p.mask_rstride == 0 || p.Lq * p.Lk <= 16384);
+    return p.Lq <= 128 && p.Lk <= 128 && p.Lk >= 1 && p.Lq >= 1 && (p.ldq % 8) == 0 && (p.ldk % 8) == 0 && (p.ldv % 8) == 0 &&
+           (p.ldo % 8) == 0;
 }
 
 static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+    const int RPq = (p.Lq + 15) & ~15, RPk = (p.Lk + 15) & ~15;
     CUtensorMap tq, tk, tv;
-    GCT_TRY(operand_map(p.Q, p.ldq, p.B * p.Lq, p.H, &tq));
-    GCT_TRY(operand_map(p.K, p.ldk, p.B * p.Lk, p.H, &tk));
-    GCT_TRY(operand_map(p.V, p.ldv, p.B * p.Lk, p.H, &tv));
+    GCT_TRY(operand_map(p.Q, p.ldq, p.B * p.Lq, p.H, RPq, &tq));
+    GCT_TRY(operand_map(p.K, p.ldk, p.B * p.Lk, p.H, RPk, &tk));
+    GCT_TRY(operand_map(p.V, p.ldv, p.B * p.Lk, p.H, RPk, &tv));
     static bool attr = false;
     if (!attr) {
-        GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+        GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout(128, 128).total));
+        GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdSmem::TOTAL, st>>>(tq, tk, tv, p);
+    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, p);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
 
 static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
     const AttnParams& p = bp.f;
+    GCT_REQUIRE(p.O, "attention bwd (tcgen05): the forward output is required (D = rowsum(dO * O))");
+    const int RPq = (p.Lq + 15) & ~15, RPk = (p.Lk + 15) & ~15;
     CUtensorMap tq, tk, tv, tdo;
-    GCT_TRY(operand_map(p.Q, p.ldq, p.B * p.Lq, p.H, &tq));
-    GCT_TRY(operand_map(p.K, p.ldk, p.B * p.Lk, p.H, &tk));
-    GCT_TRY(operand_map(p.V, p.ldv, p.B * p.Lk, p.H, &tv));
-    GCT_TRY(operand_map(bp.dO, bp.lddo, p.B * p.Lq, p.H, &tdo));
+    GCT_TRY(operand_map(p.Q, p.ldq, p.B * p.Lq, p.H, RPq, &tq));
+    GCT_TRY(operand_map(p.K, p.ldk, p.B * p.Lk, p.H, RPk, &tk));
+    GCT_TRY(operand_map(p.V, p.ldv, p.B * p.Lk, p.H, RPk, &tv));
+    GCT_TRY(operand_map(bp.dO, bp.lddo, p.B * p.Lq, p.H, RPq, &tdo));
     static bool attr = false;
     if (!attr) {
-        GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
+        GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout(128, 128).total));
+        GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    attn_bwd_tc_kernel<<<p.B * p.H, 512, BwdSmem::TOTAL, st>>>(tq, tk, tv, tdo, bp);
+    attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, bp);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }

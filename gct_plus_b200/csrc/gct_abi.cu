@@ -99,11 +99,12 @@ int gct_attention_fwd(const void* q, int ldq, const void* k, int ldk, const void
 }
 
 int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
-                      int64_t mask_bstride, int mask_rstride, const float* lse, const void* dout, int lddo, void* dq, int lddq,
+                      int64_t mask_bstride, int mask_rstride, const float* lse, const void* out, int ldo, const void* dout, int lddo,
+                      void* dq, int lddq,
                       void* dk, int lddk, void* dv, int lddv, int B, int H, int Lq, int Lk, int dtype, void* stream) {
     AttnBwdParams bp;
-    bp.f = make_attn(q, ldq, k, ldk, v, ldv, mask, mask_bstride, mask_rstride, nullptr, 0, const_cast<float*>(lse), nullptr, B, H,
-                     Lq, Lk);
+    bp.f = make_attn(q, ldq, k, ldk, v, ldv, mask, mask_bstride, mask_rstride, const_cast<void*>(out), ldo, const_cast<float*>(lse),
+                     nullptr, B, H, Lq, Lk);
     bp.dO = dout; bp.lddo = lddo; bp.dQ = dq; bp.dK = dk; bp.dV = dv; bp.lddq = lddq; bp.lddk = lddk; bp.lddv = lddv;
     return dtype == GCT_DTYPE_F32 ? attn_bwd_dispatch<float>(bp, ST(stream)) : attn_bwd_dispatch<bf16>(bp, ST(stream));
 }

@@ -23,7 +23,7 @@ static int attn_fwd_dispatch(const AttnParams& p, cudaStream_t st) {
 template <typename T>
 static int attn_bwd_dispatch(const AttnBwdParams& bp, cudaStream_t st) {
     if constexpr (sizeof(T) == 2) {
-        if (!g_gct_simt_attn && atc::supported(bp.f)) return atc::launch_bwd(bp, st);
+        if (!g_gct_simt_attn && atc::supported(bp.f) && bp.f.O) return atc::launch_bwd(bp, st);
     }
     return launch_attn_bwd<T>(bp, st);
 }
@@ -173,12 +173,12 @@ struct Model {
         return attn_fwd_dispatch<T>(p, st);
     }
     int attention_bwd(const T* q, int ldq, const T* k, const T* v, int ldkv, const uint8_t* mask, long long mb, int mr,
-                      const float* lse, const T* dO, T* dq, int lddq, T* dk, T* dv, int lddkv, int B, int Lq, int Lk,
+                      const float* lse, const T* out, const T* dO, T* dq, int lddq, T* dk, T* dv, int lddkv, int B, int Lq, int Lk,
                       DropCtx dc) {
         AttnBwdParams bp;
         AttnParams& p = bp.f;
         p.Q = q; p.K = k; p.V = v; p.ldq = ldq; p.ldk = ldkv; p.ldv = ldkv; p.mask = mask; p.mask_bstride = mb;
-        p.mask_rstride = mr; p.O = nullptr; p.ldo = d; p.lse = const_cast<float*>(lse); p.probs = nullptr; p.B = B; p.H = H;
+        p.mask_rstride = mr; p.O = const_cast<T*>(out); p.ldo = d; p.lse = const_cast<float*>(lse); p.probs = nullptr; p.B = B; p.H = H;
         p.Lq = Lq; p.Lk = Lk; p.scale = 0.125f; p.drop = dc;
         bp.dO = dO; bp.lddo = d; bp.dQ = dq; bp.dK = dk; bp.dV = dv; bp.lddq = lddq; bp.lddk = lddkv; bp.lddv = lddkv;
         return attn_bwd_dispatch<T>(bp, st);
@@ -515,7 +515,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                 GCT_TRY(m.gemm(S.dyT, false, d, m.WT(m.dec_slot(l, D_O2_W)), true, d, Md, d, d, e));
             }
             T* dq2 = S.dqkvT;                      // [Md, d]
-            GCT_TRY(m.attention_bwd(a.q2, d, a.kv2, a.kv2 + d, 2 * d, A.cross_mask, Sm, 0, a.lse2, S.dattT, dq2, d, S.dkv2T,
+            GCT_TRY(m.attention_bwd(a.q2, d, a.kv2, a.kv2 + d, 2 * d, A.cross_mask, Sm, 0, a.lse2, a.att2, S.dattT, dq2, d, S.dkv2T,
                                     S.dkv2T + d, 2 * d, B, Ld, Sm, m.site(sb + DS_ATTN2)));
             GCT_TRY(m.wgrad(dq2, d, a.a2, d, Md, d, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), true));
             GCT_TRY(m.wgrad(S.dkv2T, 2 * d, A.mem, d, Mm, 2 * d, d, m.dec_slot(l, D_KV2_W), m.dec_slot(l, D_KV2_B), true));
@@ -537,7 +537,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                 GCT_TRY(m.gemm(S.dyT, false, d, m.WT(m.dec_slot(l, D_O1_W)), true, d, Md, d, d, e));
             }
             GCT_TRY(m.attention_bwd(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.trg_mask, (long long)Ld * Ld, Ld, a.lse1,
-                                    S.dattT, S.dqkvT, 3 * d, S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Ld, Ld, m.site(sb + DS_ATTN1)));
+                                    a.att1, S.dattT, S.dqkvT, 3 * d, S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Ld, Ld, m.site(sb + DS_ATTN1)));
             GCT_TRY(m.wgrad(S.dqkvT, 3 * d, a.a1, d, Md, 3 * d, d, m.dec_slot(l, D_QKV_W), m.dec_slot(l, D_QKV_B), true));
             {
                 Epilogue e = Model<T>::epi(nullptr, d); e.out32 = other;
@@ -613,7 +613,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             Epilogue e = Model<T>::epi(nullptr, d); e.outT = S.dattT;
             GCT_TRY(m.gemm(S.dyT, false, d, m.WT(m.enc_slot(l, E_O_W)), true, d, Me, d, d, e));
         }
-        GCT_TRY(m.attention_bwd(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.src_mask, Se, 0, a.lse, S.dattT, S.dqkvT, 3 * d,
+        GCT_TRY(m.attention_bwd(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.src_mask, Se, 0, a.lse, a.att, S.dattT, S.dqkvT, 3 * d,
                                 S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Se, Se, m.site(sb + ES_ATTN)));
         GCT_TRY(m.wgrad(S.dqkvT, 3 * d, a.a1, d, Me, 3 * d, d, m.enc_slot(l, E_QKV_W), m.enc_slot(l, E_QKV_B), true));
         {   // dA1 = dqkv Wqkv + dX1

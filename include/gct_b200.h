@@ -106,9 +106,9 @@ int gct_attention_fwd(const void* q, int ldq, const void* k, int ldk, const void
                       int64_t mask_bstride, int mask_rstride, void* out, int ldo, float* lse, float* probs, int B,
                       int H, int Lq, int Lk, int dtype, void* stream);
 int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
-                      int64_t mask_bstride, int mask_rstride, const float* lse, const void* dout, int lddo, void* dq,
-                      int lddq, void* dk, int lddk, void* dv, int lddv, int B, int H, int Lq, int Lk, int dtype,
-                      void* stream);
+                      int64_t mask_bstride, int mask_rstride, const float* lse, const void* out, int ldo, const void* dout,
+                      int lddo, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int H, int Lq, int Lk,
+                      int dtype, void* stream);      /* out = the forward result (softmax-backward row term D = rowsum(dout*out)) */
 /* masks: Model/modules.py:33-58 as byte arrays */
 int gct_src_mask(const int64_t* tok, int B, int L, int nc, int pad, uint8_t* out, void* stream);
 int gct_trg_mask(const int64_t* tok, int B, int T, int nc_cond2dec, int pad, uint8_t* out, void* stream);

@@ -85,7 +85,7 @@ def test_attention_fwd_bwd(dtype, tol, Lq, Lk, dense):
     dO = torch.randn(B, Lq, d, device=DEV).to(tdt)
     ref.backward(dO.float())
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    L.check(lib.gct_attention_bwd(L.ptr(q), d, L.ptr(k), d, L.ptr(v), d, L.ptr(m8), mb, mr, L.ptr(lse), L.ptr(dO), d, L.ptr(dq), d,
+    L.check(lib.gct_attention_bwd(L.ptr(q), d, L.ptr(k), d, L.ptr(v), d, L.ptr(m8), mb, mr, L.ptr(lse), L.ptr(out), d, L.ptr(dO), d, L.ptr(dq), d,
                                   L.ptr(dk), d, L.ptr(dv), d, B, H, Lq, Lk, dt, L.stream_ptr()))
     torch.cuda.synchronize()
     for got, want in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
