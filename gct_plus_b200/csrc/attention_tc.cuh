@@ -104,8 +104,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
     if (t == 32) {
+        // the thread that initialises the barriers also starts the loads: they are in flight before the TMEM allocation
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bars, (uint32_t)(RPq + 2 * NS) * 128u);
+        tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
+        tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
+        tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
@@ -116,12 +121,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (t == 0) {
-        mbar_expect_tx(bars, (uint32_t)(RPq + 2 * NS) * 128u);
-        tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
-        tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
-        tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
-    }
     const bool dense = p.mask_rstride != 0;
     if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
     __syncthreads();
@@ -249,10 +248,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 struct BwdLayout {
-    int BS, pd, ds, dO, q, k, v, bits, red, bars, total;      // BS = bytes of one [RPq][64] block
+    // BS = bytes of one [RPq][64] block.  Pd block 0 is written over the V tile (dead once dP = dO V^T has completed),
+    // Pd block 1 follows it; LBOP = their distance (the MN-major descriptor's leading-dimension byte offset).
+    int BS, LBOP, pd, ds, dO, q, k, v, bits, red, bars, total;
     __host__ __device__ BwdLayout(int RPq, int RPk) {
         BS = RPq * 128;
-        pd = 0; ds = 2 * BS; dO = 4 * BS; q = 5 * BS; k = 6 * BS; v = k + RPk * 128; bits = v + RPk * 128;
+        const int VB = RPk * 128;
+        LBOP = VB > BS ? VB : BS;
+        v = 0; pd = 0;
+        ds = LBOP + BS; dO = ds + 2 * BS; q = dO + BS; k = q + BS; bits = k + VB;
         red = bits + 2048; bars = red + 1024; total = bars + 64;
         // UMMA A operands always span 128 rows: keep the furthest such read (Q as A of S) inside the allocation
         if (total < q + 16384) total = q + 16384;
@@ -280,6 +284,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (t == 32) {
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bars, (uint32_t)(2 * RPq + 2 * NS) * 128u);
+        tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
+        tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
+        tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
+        tma_load_2d(base + L.dO, &tmDO, h * 64, b * Lq, bars);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
@@ -291,13 +300,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     // TMEM columns: S [0,128)  dP [128,256); after the softmax pass: dV [0,64)  dK [64,128)  dQ [128,192)
-    if (t == 0) {
-        mbar_expect_tx(bars, (uint32_t)(2 * RPq + 2 * NS) * 128u);
-        tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
-        tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
-        tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
-        tma_load_2d(base + L.dO, &tmDO, h * 64, b * Lq, bars);
-    }
     const bool dense = p.mask_rstride != 0;
     if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
     const bool qok = row < Lq;
@@ -381,11 +383,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     pk[i] = qok ? pack_bf16(pd.x, pd.y) : 0u;
                     dk[i] = qok ? pack_bf16(ds.x, ds.y) : 0u;
                 }
-                const uint32_t blk = (uint32_t)(c16 >> 2) * (uint32_t)L.BS;
+                const uint32_t blk = (uint32_t)(c16 >> 2) * (uint32_t)L.BS, blkp = (uint32_t)(c16 >> 2) * (uint32_t)L.LBOP;
                 const int ch = (c16 & 3) * 2;
                 if (row < RPq) {      // a block holds RPq rows: rows past it would land in the next block / tile
-                    *reinterpret_cast<uint4*>(sm + L.pd + blk + swz16(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(sm + L.pd + blk + swz16(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    *reinterpret_cast<uint4*>(sm + L.pd + blkp + swz16(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(sm + L.pd + blkp + swz16(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
                     *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch + 1)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
                 }
@@ -401,7 +403,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // dV[key, dk] = Pd^T dO : M = keys (MN-major A, two 64-key blocks BS apart), K = query rows, N = dk
         const uint32_t idT = make_idesc(128, 64, true, true);
         for (int k = 0; k < nq; ++k)          // 16 query rows per MMA
-            umma_bf16(tmem, make_smem_desc(base + L.pd + k * 2048, (uint32_t)L.BS, 1024),
+            umma_bf16(tmem, make_smem_desc(base + L.pd + k * 2048, (uint32_t)L.LBOP, 1024),
                       make_smem_desc(base + L.dO + k * 2048, 8192, 1024), idT, k > 0 ? 1u : 0u);
         // dK[key, dk] = dS^T Q
         for (int k = 0; k < nq; ++k)

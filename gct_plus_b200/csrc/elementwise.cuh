@@ -48,7 +48,7 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ tok, int Ltok, const
 // backward of the above.  The table is tiny (<= 128 ids) and the rows are many (~40k): each block reduces a
 // chunk of rows into a [vocab][128-column] tile in shared memory (thread = column, so no intra-block
 // conflicts), then flushes the tile with one atomic per (id, column).  dx is the gradient w.r.t. `out`.
-constexpr int EMB_BWD_ROWS = 256;
+constexpr int EMB_BWD_ROWS = 128;
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, int B, int Ltok, int nc, const float* __restrict__ dx,
                                  int d, float scale, DropCtx drop, float* __restrict__ dtable, int vocab) {
     extern __shared__ float acc[];           // [vocab][128]
@@ -58,11 +58,23 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, int B, int Lto
     const int L = nc + Ltok;
     const long long p0 = (long long)blockIdx.x * EMB_BWD_ROWS, p1 = min((long long)B * Ltok, p0 + EMB_BWD_ROWS);
     if (c < d) {
-        for (long long p = p0; p < p1; ++p) {
-            long long v = tok[p];
-            if (v < 0 || v >= vocab) v = 0;
-            const size_t row = (size_t)(p / Ltok) * L + nc + (size_t)(p % Ltok);
-            acc[v * 128 + threadIdx.x] += drop_apply(drop, (uint64_t)row * d + c, dx[row * d + c]);
+        constexpr int U = 8;                 // rows per batch of independent loads
+        for (long long pb = p0; pb < p1; pb += U) {
+            int vv[U];
+            float gg[U];
+            size_t rr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long p = min(pb + u, p1 - 1);
+                long long v = tok[p];
+                if (v < 0 || v >= vocab) v = 0;
+                vv[u] = (int)v;
+                rr[u] = (size_t)(p / Ltok) * L + nc + (size_t)(p % Ltok);
+                gg[u] = dx[rr[u] * d + c];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (pb + u < p1) acc[vv[u] * 128 + threadIdx.x] += drop_apply(drop, (uint64_t)rr[u] * d + c, gg[u]);
         }
         for (int v = 0; v < vocab; ++v) {
             const float a = acc[v * 128 + threadIdx.x];
@@ -72,6 +84,8 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, int B, int Lto
 }
 
 // cond-token linear backward: dW[l*d+c, k] += scale * sum_b dx[b,l,c]*conds[b,k]; dB[l*d+c] += scale*sum_b dx
+// grid (nc, d/128, batch slices): each CTA reduces COND_BWD_BATCH batch rows and adds its partial atomically.
+constexpr int COND_BWD_BATCH = 16;
 __global__ void cond_embed_bwd_kernel(const float* __restrict__ dx, int B, int L, int nc, int d,
                                       const float* __restrict__ conds, float scale, DropCtx drop, int use_drop_index,
                                       float* __restrict__ dW, float* __restrict__ dB) {
@@ -80,15 +94,26 @@ __global__ void cond_embed_bwd_kernel(const float* __restrict__ dx, int B, int L
     if (c >= d) return;
     float aw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float ab = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const size_t row = (size_t)b * L + l;
-        float g = dx[row * d + c];
-        if (use_drop_index) g = drop_apply(drop, (uint64_t)row * d + c, g);
-        ab += g;
-        for (int k = 0; k < nc; ++k) aw[k] = fmaf(g, conds[(size_t)b * nc + k], aw[k]);
+    const int b0 = blockIdx.z * COND_BWD_BATCH, b1 = min(B, b0 + COND_BWD_BATCH);
+    float g[COND_BWD_BATCH];
+#pragma unroll
+    for (int i = 0; i < COND_BWD_BATCH; ++i) {          // all loads in flight before the first use
+        const size_t row = (size_t)min(b0 + i, B - 1) * L + l;
+        g[i] = dx[row * d + c];
     }
-    dB[(size_t)l * d + c] += ab * scale;
-    for (int k = 0; k < nc; ++k) dW[((size_t)l * d + c) * nc + k] += aw[k] * scale;
+#pragma unroll
+    for (int i = 0; i < COND_BWD_BATCH; ++i) {
+        const int b = b0 + i;
+        if (b < b1) {
+            const size_t row = (size_t)b * L + l;
+            float gv = g[i];
+            if (use_drop_index) gv = drop_apply(drop, (uint64_t)row * d + c, gv);
+            ab += gv;
+            for (int k = 0; k < nc; ++k) aw[k] = fmaf(gv, conds[(size_t)b * nc + k], aw[k]);
+        }
+    }
+    atomicAdd(dB + (size_t)l * d + c, ab * scale);
+    for (int k = 0; k < nc; ++k) atomicAdd(dW + ((size_t)l * d + c) * nc + k, aw[k] * scale);
 }
 
 // cond2lat tokens written into the decoder memory: mem[b, j, :] = W[j*d+c,:].conds[b] + B[j*d+c]
@@ -160,19 +185,23 @@ __global__ void norm_fwd_kernel(const float* __restrict__ x, const float* __rest
 
 // Norm backward.  dx = r*(g - mean(g)) - c*xc,  g = dy*alpha, c = r^2*sum(g*xc)/((d-1)*std)
 //   (+ `add` : gradient arriving on the residual path).  dalpha/dbias accumulated with atomics.
-template <int NV>
-__global__ void norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+// Optional fused consumer prologue: dropT = T(dropmask(dc) * dx) and its column sums (the bias gradient of the
+// projection whose output carried that dropout) -- the operand the next dgrad / wgrad GEMMs read, so the fp32 dx is
+// not re-read by a separate cast kernel.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, (NV <= 4) ? 2 : 1)
+norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
                                 const float* __restrict__ dy, const float* __restrict__ add,
                                 float* __restrict__ dx, float* __restrict__ dalpha, float* __restrict__ dbias,
-                                int rows, float eps) {
+                                int rows, float eps, T* __restrict__ dropT, DropCtx dc, float* __restrict__ dropsum) {
     const int d = NV * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    float4 da[NV], db[NV], al[NV];
+    float4 da[NV], db[NV], dsum[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         da[i] = make_float4(0, 0, 0, 0);
         db[i] = make_float4(0, 0, 0, 0);
-        al[i] = *reinterpret_cast<const float4*>(alpha + (i * 32 + lane) * 4);
+        dsum[i] = make_float4(0, 0, 0, 0);
     }
     for (int row = blockIdx.x * nwarp + warp; row < rows; row += gridDim.x * nwarp) {
         const float* xr = x + (size_t)row * d;
@@ -200,7 +229,8 @@ __global__ void norm_bwd_kernel(const float* __restrict__ x, const float* __rest
             db[i].x += g[i].x; db[i].y += g[i].y; db[i].z += g[i].z; db[i].w += g[i].w;
             da[i].x += g[i].x * v[i].x * r; da[i].y += g[i].y * v[i].y * r;
             da[i].z += g[i].z * v[i].z * r; da[i].w += g[i].w * v[i].w * r;
-            g[i].x *= al[i].x; g[i].y *= al[i].y; g[i].z *= al[i].z; g[i].w *= al[i].w;
+            const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + (i * 32 + lane) * 4));      // 2 KB, L1-resident
+            g[i].x *= al.x; g[i].y *= al.y; g[i].z *= al.z; g[i].w *= al.w;
             sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
             sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
         }
@@ -217,11 +247,25 @@ __global__ void norm_bwd_kernel(const float* __restrict__ x, const float* __rest
                 o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
             }
             *reinterpret_cast<float4*>(dx + off) = o;
+            if (dropT) {
+                drop_pair(dc, (uint32_t)(off >> 1), o.x, o.y);           // identical decisions to drop_apply(off + k)
+                drop_pair(dc, (uint32_t)(off >> 1) + 1, o.z, o.w);
+                if constexpr (sizeof(T) == 4) {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(dropT) + off) = o;
+                } else {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&p0);
+                    u.y = *reinterpret_cast<uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(dropT) + off) = u;
+                }
+                dsum[i].x += o.x; dsum[i].y += o.y; dsum[i].z += o.z; dsum[i].w += o.w;
+            }
         }
     }
     // block reduce of the parameter partials through shared memory, then one atomic per column
-    extern __shared__ float sm[];              // [2][d]
-    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+    extern __shared__ float sm[];              // [3][d]
+    for (int c = threadIdx.x; c < 3 * d; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -230,11 +274,16 @@ __global__ void norm_bwd_kernel(const float* __restrict__ x, const float* __rest
         atomicAdd(&sm[c + 2], da[i].z); atomicAdd(&sm[c + 3], da[i].w);
         atomicAdd(&sm[d + c + 0], db[i].x); atomicAdd(&sm[d + c + 1], db[i].y);
         atomicAdd(&sm[d + c + 2], db[i].z); atomicAdd(&sm[d + c + 3], db[i].w);
+        if (dropsum) {
+            atomicAdd(&sm[2 * d + c + 0], dsum[i].x); atomicAdd(&sm[2 * d + c + 1], dsum[i].y);
+            atomicAdd(&sm[2 * d + c + 2], dsum[i].z); atomicAdd(&sm[2 * d + c + 3], dsum[i].w);
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
         atomicAdd(dalpha + c, sm[c]);
         atomicAdd(dbias + c, sm[d + c]);
+        if (dropsum) atomicAdd(dropsum + c, sm[2 * d + c]);
     }
 }
 

@@ -55,8 +55,9 @@ int gct_norm_bwd(const float* x, const float* alpha, const float* dy, const floa
     GCT_REQUIRE(d % 128 == 0 && d <= 1024, "norm: d=%d must be a multiple of 128, <= 1024", d);
     if (rows <= 0) return GCT_OK;
     dim3 grid(min(cdiv(rows, 8), 148 * 4));
-    const size_t sm = 2 * d * sizeof(float);
-#define CASE(NV) case NV: norm_bwd_kernel<NV><<<grid, 256, sm, ST(stream)>>>(x, alpha, dy, add, dx, dalpha, dbias, rows, 1e-6f); break;
+    const size_t sm = 3 * d * sizeof(float);
+    DropCtx nodrop; nodrop.seed = 0; nodrop.thresh = 0; nodrop.scale = 1.f;
+#define CASE(NV) case NV: norm_bwd_kernel<float, NV><<<grid, 256, sm, ST(stream)>>>(x, alpha, dy, add, dx, dalpha, dbias, rows, 1e-6f, (float*)nullptr, nodrop, (float*)nullptr); break;
     switch (d / 128) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
 #undef CASE
     GCT_LAUNCH_CHECK();

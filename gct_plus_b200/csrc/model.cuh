@@ -145,11 +145,13 @@ struct Model {
         GCT_LAUNCH_CHECK();
         return GCT_OK;
     }
-    int norm_bwd(const float* x, int aslot, int bslot, const float* dy, const float* add, float* dx, int rows) {
+    // dropT / dc / dropsum: fused prologue of the consumer (see norm_bwd_kernel); null = plain Norm backward
+    int norm_bwd(const float* x, int aslot, int bslot, const float* dy, const float* add, float* dx, int rows,
+                 T* dropT = nullptr, DropCtx dc = DropCtx{0, 0, 1.f}, float* dropsum = nullptr) {
         const int nv = d / 128;
         dim3 grid(min(cdiv(rows, 8), 148 * 4));
-        const size_t sm = 2 * d * sizeof(float);
-#define GCT_NORMB_CASE(NV) case NV: norm_bwd_kernel<NV><<<grid, 256, sm, st>>>(x, P(aslot), dy, add, dx, G(aslot), G(bslot), rows, 1e-6f); break;
+        const size_t sm = 3 * d * sizeof(float);
+#define GCT_NORMB_CASE(NV) case NV: norm_bwd_kernel<T, NV><<<grid, 256, sm, st>>>(x, P(aslot), dy, add, dx, G(aslot), G(bslot), rows, 1e-6f, dropT, dc, dropsum); break;
         switch (nv) { GCT_NORMB_CASE(1) GCT_NORMB_CASE(2) GCT_NORMB_CASE(3) GCT_NORMB_CASE(4) GCT_NORMB_CASE(5) GCT_NORMB_CASE(6)
                       GCT_NORMB_CASE(7) GCT_NORMB_CASE(8) default: GCT_FAIL(GCT_ERR_UNSUPPORTED, "norm width %d", d); }
 #undef GCT_NORMB_CASE
@@ -452,9 +454,10 @@ struct BwdScratch {
 template <typename T>
 static int ffn_backward(Model<T>& m, BwdScratch<T>& S, int M, const float* dout, const T* a, const T* hpre, const T* g,
                         int f1w, int f1b, int f2w, int f2b, DropCtx drop_out, DropCtx drop_ff, const float* add_to_dA,
-                        float* dA) {
+                        float* dA, bool dyT_ready = false) {
     const int d = m.d, dff = m.dff;
-    GCT_TRY(m.cast_drop(dout, S.dyT, M, d, drop_out, m.G(f2b)));
+    // dyT_ready: the Norm backward that produced dout already wrote S.dyT = dropO'(dout) and the b2 gradient
+    if (!dyT_ready) GCT_TRY(m.cast_drop(dout, S.dyT, M, d, drop_out, m.G(f2b)));
     GCT_TRY(m.wgrad(S.dyT, d, g, dff, M, d, dff, f2w, f2b, false));
     {   // dHpre = (dY W2) * [keepF * gelu'(pre)]  -- the bracket was saved by the forward epilogue (EPI_GELU_GRAD)
         (void)drop_ff;
@@ -493,7 +496,10 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         }
         const float* ylast = A.dec[N - 1].yout;
         float* dy = S.dxb;          // gradient of the residual stream entering the final norm
-        GCT_TRY(m.norm_bwd(ylast, GCT_SLOT_DEC_NORM_A, GCT_SLOT_DEC_NORM_B, S.dxa, nullptr, dy, Md));
+        // every Norm backward below also emits S.dyT = T(dropout'(dx)) + the bias gradient for the projection that
+        // consumes it next (FFN linear_2 / out-projections), replacing a separate cast pass over the fp32 gradient
+        GCT_TRY(m.norm_bwd(ylast, GCT_SLOT_DEC_NORM_A, GCT_SLOT_DEC_NORM_B, S.dxa, nullptr, dy, Md, S.dyT,
+                           m.site(S_DEC_BASE + (N - 1) * DS_COUNT + DS_DROP3), m.G(m.dec_slot(N - 1, D_F2_B))));
         GCT_CUDA(cudaMemsetAsync(S.dmem, 0, (size_t)Mm * d * sizeof(float), st));
         float* other = S.dxa;       // free buffer
         float* third = S.dxc;
@@ -504,11 +510,11 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             // FFN: dA3 -> other ; dY2 = norm3_bwd(y2, dA3) + dy -> third
             GCT_TRY(ffn_backward(m, S, Md, dy, a.a3, a.hpre, a.g, m.dec_slot(l, D_F1_W), m.dec_slot(l, D_F1_B),
                                  m.dec_slot(l, D_F2_W), m.dec_slot(l, D_F2_B), m.site(sb + DS_DROP3), m.site(sb + DS_FF), nullptr,
-                                 other));
-            GCT_TRY(m.norm_bwd(a.y2, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), other, dy, third, Md));
+                                 other, true));
+            GCT_TRY(m.norm_bwd(a.y2, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), other, dy, third, Md, S.dyT, m.site(sb + DS_DROP2),
+                               m.G(m.dec_slot(l, D_O2_B))));
             // cross attention
             float* dY2 = third;
-            GCT_TRY(m.cast_drop(dY2, S.dyT, Md, d, m.site(sb + DS_DROP2), m.G(m.dec_slot(l, D_O2_B))));
             GCT_TRY(m.wgrad(S.dyT, d, a.att2, d, Md, d, d, m.dec_slot(l, D_O2_W), m.dec_slot(l, D_O2_B), false));
             {
                 Epilogue e = Model<T>::epi(nullptr, d); e.outT = S.dattT;
@@ -528,9 +534,9 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                 GCT_TRY(m.gemm(dq2, false, d, m.WT(m.dec_slot(l, D_Q2_W)), true, d, Md, d, d, e));
             }
             // dY1 = norm2_bwd(y1, dA2) + dY2 -> dy
-            GCT_TRY(m.norm_bwd(a.y1, m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), other, dY2, dy, Md));
+            GCT_TRY(m.norm_bwd(a.y1, m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), other, dY2, dy, Md, S.dyT, m.site(sb + DS_DROP1),
+                               m.G(m.dec_slot(l, D_O1_B))));
             // self attention
-            GCT_TRY(m.cast_drop(dy, S.dyT, Md, d, m.site(sb + DS_DROP1), m.G(m.dec_slot(l, D_O1_B))));
             GCT_TRY(m.wgrad(S.dyT, d, a.att1, d, Md, d, d, m.dec_slot(l, D_O1_W), m.dec_slot(l, D_O1_B), false));
             {
                 Epilogue e = Model<T>::epi(nullptr, d); e.outT = S.dattT;
@@ -544,7 +550,11 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                 GCT_TRY(m.gemm(S.dqkvT, false, 3 * d, m.WT(m.dec_slot(l, D_QKV_W)), true, d, Md, d, 3 * d, e));
             }
             // dYin = norm1_bwd(yin, dA1) + dY1 -> third ; rotate
-            GCT_TRY(m.norm_bwd(yin, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), other, dy, third, Md));
+            if (l > 0)
+                GCT_TRY(m.norm_bwd(yin, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), other, dy, third, Md, S.dyT,
+                                   m.site(S_DEC_BASE + (l - 1) * DS_COUNT + DS_DROP3), m.G(m.dec_slot(l - 1, D_F2_B))));
+            else
+                GCT_TRY(m.norm_bwd(yin, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), other, dy, third, Md));
             float* t = dy; dy = third; third = t;
         }
         // decoder embedding (+ cond2dec tokens)
@@ -554,7 +564,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                                                    m.G(GCT_SLOT_DEC_EMB), m.c.trg_vocab);
             GCT_LAUNCH_CHECK();
             if (c2d) {
-                dim3 g2(nc, cdiv(d, 128));
+                dim3 g2(nc, cdiv(d, 128), cdiv(B, COND_BWD_BATCH));
                 cond_embed_bwd_kernel<<<g2, 128, 0, st>>>(dy, B, Ld, nc, d, io.dconds, sqd, m.site(S_DEC_PE), 1,
                                                           m.G(GCT_SLOT_DEC_C2D_W), m.G(GCT_SLOT_DEC_C2D_B));
                 GCT_LAUNCH_CHECK();
@@ -562,7 +572,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         }
         // memory: cond2lat tokens, fc_z
         if (c2l) {
-            dim3 g2(nc, cdiv(d, 128));
+            dim3 g2(nc, cdiv(d, 128), cdiv(B, COND_BWD_BATCH));
             cond_embed_bwd_kernel<<<g2, 128, 0, st>>>(S.dmem, B, Sm, nc, d, io.dconds, 1.f, m.site(0), 0,
                                                       m.G(GCT_SLOT_DEC_C2L_W), m.G(GCT_SLOT_DEC_C2L_B));
             GCT_LAUNCH_CHECK();
@@ -596,7 +606,8 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         GCT_TRY(m.gemm(S.dmulvT, false, 2 * lat, m.WT(GCT_SLOT_MULV_W), true, d, Me, d, 2 * lat, e));
     }
     float* dx = S.dxb;
-    GCT_TRY(m.norm_bwd(A.enc[N - 1].xout, GCT_SLOT_ENC_NORM_A, GCT_SLOT_ENC_NORM_B, S.dxa, nullptr, dx, Me));
+    GCT_TRY(m.norm_bwd(A.enc[N - 1].xout, GCT_SLOT_ENC_NORM_A, GCT_SLOT_ENC_NORM_B, S.dxa, nullptr, dx, Me, S.dyT,
+                       m.site(S_ENC_BASE + (N - 1) * ES_COUNT + ES_DROP2), m.G(m.enc_slot(N - 1, E_F2_B))));
     float* other = S.dxa;
     float* third = S.dxc;
     for (int l = N - 1; l >= 0; --l) {
@@ -605,9 +616,9 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         const uint32_t sb = S_ENC_BASE + l * ES_COUNT;
         // xout = a2_32 + drop2(ffn(a2)) : dA2 = dHpre W1 + dx (residual on the normalised stream)
         GCT_TRY(ffn_backward(m, S, Me, dx, a.a2, a.hpre, a.g, m.enc_slot(l, E_F1_W), m.enc_slot(l, E_F1_B), m.enc_slot(l, E_F2_W),
-                             m.enc_slot(l, E_F2_B), m.site(sb + ES_DROP2), m.site(sb + ES_FF), dx, other));
-        GCT_TRY(m.norm_bwd(a.x1, m.enc_slot(l, E_N2A), m.enc_slot(l, E_N2B), other, nullptr, third, Me));   // dX1
-        GCT_TRY(m.cast_drop(third, S.dyT, Me, d, m.site(sb + ES_DROP1), m.G(m.enc_slot(l, E_O_B))));
+                             m.enc_slot(l, E_F2_B), m.site(sb + ES_DROP2), m.site(sb + ES_FF), dx, other, true));
+        GCT_TRY(m.norm_bwd(a.x1, m.enc_slot(l, E_N2A), m.enc_slot(l, E_N2B), other, nullptr, third, Me, S.dyT, m.site(sb + ES_DROP1),
+                           m.G(m.enc_slot(l, E_O_B))));   // dX1
         GCT_TRY(m.wgrad(S.dyT, d, a.att, d, Me, d, d, m.enc_slot(l, E_O_W), m.enc_slot(l, E_O_B), false));
         {
             Epilogue e = Model<T>::epi(nullptr, d); e.outT = S.dattT;
@@ -620,14 +631,18 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             Epilogue e = Model<T>::epi(nullptr, d); e.res32 = third; e.out32 = other;
             GCT_TRY(m.gemm(S.dqkvT, false, 3 * d, m.WT(m.enc_slot(l, E_QKV_W)), true, d, Me, d, 3 * d, e));
         }
-        GCT_TRY(m.norm_bwd(xin, m.enc_slot(l, E_N1A), m.enc_slot(l, E_N1B), other, nullptr, dx, Me));
+        if (l > 0)
+            GCT_TRY(m.norm_bwd(xin, m.enc_slot(l, E_N1A), m.enc_slot(l, E_N1B), other, nullptr, dx, Me, S.dyT,
+                               m.site(S_ENC_BASE + (l - 1) * ES_COUNT + ES_DROP2), m.G(m.enc_slot(l - 1, E_F2_B))));
+        else
+            GCT_TRY(m.norm_bwd(xin, m.enc_slot(l, E_N1A), m.enc_slot(l, E_N1B), other, nullptr, dx, Me));
     }
     {
         dim3 grid(cdiv((long long)B * A.S, EMB_BWD_ROWS), cdiv(d, 128));
         embed_bwd_kernel<<<grid, 128, (size_t)m.c.src_vocab * 128 * sizeof(float), st>>>(io.src, B, A.S, nc, dx, d, sqd, m.site(S_ENC_PE), m.G(GCT_SLOT_ENC_EMB), m.c.src_vocab);
         GCT_LAUNCH_CHECK();
         if (nc > 0) {
-            dim3 g2(nc, cdiv(d, 128));
+            dim3 g2(nc, cdiv(d, 128), cdiv(B, COND_BWD_BATCH));
             cond_embed_bwd_kernel<<<g2, 128, 0, st>>>(dx, B, Se, nc, d, io.econds, sqd, m.site(S_ENC_PE), 1,
                                                       m.G(GCT_SLOT_ENC_C2E_W), m.G(GCT_SLOT_ENC_C2E_B));
             GCT_LAUNCH_CHECK();
