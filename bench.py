@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
-  * sampling: one sample_smiles call = one batch of --batch latent draws (default 8192; the reference driver's
-    -batch_size flag, whose default is 512, is also measured and reported under "batch512") decoded to
-    max_strlen=100 (99 KV-cached multinomial steps), vaetf; default batch 8192 (4 calls cover cfg 2's 30k draws);
+  * sampling: one sample_smiles call = one batch of --batch latent draws (default 30000 = cfg 2's 30k draws in one call;
+    the reference driver's -batch_size flag, whose default is 512, is also measured and reported under "batch512")
+    decoded to max_strlen=100 (99 KV-cached multinomial steps), vaetf;
   * training (reported under "train"): one optimiser step (fwd + loss + bwd [+ allreduce] + Adam),
     pvaetf B=512 S=78 T=79 at N=1 (cfg 3), pscavaetf B=512/GPU S=98 T=99 data-parallel at N>1 (cfg 4).
 `value` is timed with inputs resident in HBM; `e2e` goes through the public API
@@ -142,11 +142,15 @@ def sample_inputs(sampler, n_batches, seed, pinned=True):
     return out
 
 
-def decode_alg_bytes(cfg_layers, B, Sm, steps, esize, d=512, dff=2048):
-    """sum over steps of KV read + KV write + weight read."""
-    kv = sum(cfg_layers * B * (2 * (t + 1) * d + 2 * Sm * d) * esize for t in range(steps))
+def decode_alg_bytes(cfg_layers, B, Sm, steps, esize, d=512, dff=2048, latent_form=False, lat=128, heads=8):
+    """sum over steps of KV read + KV write + weight read.  latent_form: the cross-attention term of this
+    build's algorithm (decode_zattn.cuh): per layer the latent rows [Sm, lat] + the folded query / context vectors
+    [heads*lat] instead of the memory's K and V projections [Sm, d] x 2; the folded q / out weights are [heads*lat, d]."""
+    cross = (Sm * lat + 2 * heads * lat) if latent_form else 2 * Sm * d
+    kv = sum(cfg_layers * B * (2 * (t + 1) * d + cross) * esize for t in range(steps))
     kvw = steps * cfg_layers * B * 2 * d * esize
-    wr = steps * cfg_layers * (8 * d * d + 2 * d * dff) * esize
+    wq = (6 * d * d + 2 * heads * lat * d) if latent_form else 8 * d * d
+    wr = steps * cfg_layers * (wq + 2 * d * dff) * esize
     return kv + kvw + wr
 
 
@@ -155,7 +159,7 @@ def time_decode_attention(sampler, dev, steps, Sm):
     decode (n_cached = t), caches of all layers in rotation (6 x 2 x 52 MB bf16 > L2).  CUDA events on the launch stream."""
     import gct_plus_b200._lib as L
     lib = L.lib()
-    d, H, N, B = 512, 8, 6, BATCH
+    d, H, N, B = 512, 8, 6, min(BATCH, 8192)        # 8192 rows x 6 layers x 2 x 100 keys = 10 GB of cache: far beyond L2
     Lmax = steps + 1
     kc = torch.randn(N, B, Lmax, d, device=dev).bfloat16()
     vc = torch.randn(N, B, Lmax, d, device=dev).bfloat16()
@@ -187,7 +191,7 @@ def time_decode_attention(sampler, dev, steps, Sm):
     launches = steps * N
     # algorithmic bytes of one launch at step t: read t cached K and V rows + this step's q,k,v, write k,v rows and the output
     alg = sum(B * (2 * t * d + 3 * d + 2 * d + d) * 2 for t in range(steps)) * N
-    return alg / launches, ms / launches, launches
+    return alg / launches, ms / launches, launches, B
 
 
 def run_sampling(args, rank, world, dev):
@@ -239,7 +243,7 @@ def run_sampling(args, rank, world, dev):
     d2h = BATCH * MAX_STRLEN * 8
     cfg = sampler.model._cfg()
     per_step = L.lib().gct_decode_launches_per_step(cfg)
-    launches = K * (3 + 2 * 6 + (n_steps_run // max(K, 1)) * per_step)
+    launches = K * (L.lib().gct_decode_begin_launches(cfg, int(inputs[W][1].size(1))) + (n_steps_run // max(K, 1)) * per_step)
     Sm_mean = float(np.mean([z.size(1) for _, z in inputs[W:]]))
     Sm_true = float(np.mean([np.mean(tl) for tl, _ in inputs[W:]]))       # keys actually attended (rows differ in length)
     return dict(value=value, ms_per_step=ms / K, e2e_value=world * K * BATCH / (t_e2e / 1e3), h2d=h2d, d2h=d2h, clocks=ck,
@@ -412,7 +416,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)        # 8 sample_smiles calls of --batch draws
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=8192, help="latent draws per sample_smiles call")
+    ap.add_argument("--batch", type=int, default=30000, help="latent draws per sample_smiles call (cfg 2: 30k draws = one call)")
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--train-batch", type=int, default=512)
     ap.add_argument("--no-train", action="store_true")
@@ -448,9 +452,10 @@ def main():
                 "e2e": r["e2e_value"], "note": "the reference driver's default -batch_size (uc_sampling.py:16-23)"}
         BATCH = big
     steps = MAX_STRLEN - 1
-    alg_per_launch, ms_per_launch, nl = time_decode_attention(s["sampler"], dev, steps, s["Sm_mean"])
+    alg_per_launch, ms_per_launch, nl, roof_rows = time_decode_attention(s["sampler"], dev, steps, s["Sm_mean"])
     achieved = alg_per_launch / (ms_per_launch / 1e3) / 1e9
-    total_alg = decode_alg_bytes(6, BATCH, s["Sm_true"], steps, 2)
+    total_alg = decode_alg_bytes(6, BATCH, s["Sm_true"], steps, 2, latent_form=True)
+    total_kv_form = decode_alg_bytes(6, BATCH, s["Sm_true"], steps, 2)
     train = None
     if not args.no_train:
         s.pop("sampler")
@@ -468,9 +473,14 @@ def main():
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                              "traffic": NCU_TRAFFIC,
                              "peak_source": peak_src, "launches_timed": nl, "us_per_launch": ms_per_launch * 1e3,
+                             "rows_per_launch": roof_rows,
                              "whole_decode": {"algorithmic_bytes_per_batch": total_alg,
                                               "achieved_GBps": total_alg / (s["ms_per_step"] / 1e3) / 1e9,
-                                              "frac": total_alg / (s["ms_per_step"] / 1e3) / 1e9 / hbm_peak}},
+                                              "frac": total_alg / (s["ms_per_step"] / 1e3) / 1e9 / hbm_peak,
+                                              "note": "bytes of this build's algorithm (cross-attention over the latent rows); "
+                                                      "kv_form_* = SURVEY 8(d)'s K/V-projection form of the same decode",
+                                              "kv_form_bytes_per_batch": total_kv_form,
+                                              "kv_form_equivalent_GBps": total_kv_form / (s["ms_per_step"] / 1e3) / 1e9}},
                 "cpu_baseline": cpu, "batch512": b512, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:

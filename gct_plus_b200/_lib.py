@@ -54,6 +54,7 @@ _PROTOS = {
     "gct_set_tma_store": (C.c_int, [C.c_int]),
     "gct_set_decode_attn_config": (C.c_int, [C.c_int]),
     "gct_set_attention_backend": (C.c_int, [C.c_int]),
+    "gct_set_latent_cross_attention": (C.c_int, [C.c_int]),
     "gct_set_persistent_gemm": (C.c_int, [C.c_int]),
     "gct_norm_fwd": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]),
     "gct_norm_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]),
@@ -82,6 +83,7 @@ _PROTOS = {
     "gct_decode_steps": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), C.c_int, C.c_int,
                                    vp, sz, vp]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
+    "gct_decode_begin_launches": (C.c_int, [C.POINTER(GctConfig), C.c_int]),
     "gct_decode_attention": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
                                        C.c_int, C.c_int, C.c_int, vp]),
     "gct_allreduce_grads": (C.c_int, [vp, vp, i64, vp]),

@@ -9,6 +9,7 @@ int g_gct_simt_only = 0;
 int g_gct_pdl = 1;
 int g_da_cfg = 0;
 int g_gct_simt_attn = 0;
+int g_gct_zattn = 1;
 int g_gct_persist = 1;
 int g_gct_tma_store = 1;
 
@@ -30,6 +31,7 @@ int gct_set_gemm_backend(int simt_only) { g_gct_simt_only = simt_only; return GC
 int gct_set_pdl(int enabled) { g_gct_pdl = enabled; return GCT_OK; }
 int gct_set_decode_attn_config(int cfg) { g_da_cfg = cfg; return GCT_OK; }
 int gct_set_attention_backend(int simt_only) { g_gct_simt_attn = simt_only; return GCT_OK; }
+int gct_set_latent_cross_attention(int enabled) { g_gct_zattn = enabled; return GCT_OK; }
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 
@@ -293,7 +295,10 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
                                        : decode_steps_impl<bf16>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream);
 }
 int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
-int gct_decode_begin_launches(const gct_config_t* cfg) { return 3 + 2 * cfg->n_layers + (cfg->nconds > 0 ? 1 : 0); }
+int gct_decode_begin_launches(const gct_config_t* cfg, int Lz) {
+    if (cfg->dtype != GCT_DTYPE_F32 && DecodeWs<bf16>::want_zmode(*cfg, Lz)) return 2 + cfg->n_layers * (4 + 3 * cfg->heads);
+    return 3 + 2 * cfg->n_layers + (cfg->nconds > 0 ? 1 : 0);
+}
 
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,
                          int64_t cache_bstride, int pitch, int n_cached, const uint8_t* key_valid, int kv_stride, void* out,

@@ -6,12 +6,14 @@
 #include "attention.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
+#include "decode_zattn.cuh"
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 
 extern int g_gct_simt_only;
 extern int g_gct_simt_attn;
+extern int g_gct_zattn;
 
 template <typename T>
 static int attn_fwd_dispatch(const AttnParams& p, cudaStream_t st) {
@@ -657,20 +659,39 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
 template <typename T>
 struct DecodeWs {
     int B, Lz, Sm, Lmax;
-    T* zpad; T* mem; T* kx; T* vx;  // cross-attention keys / values: [N][B*Sm][d] each
+    bool zmode;                     // cross-attention in latent space (decode_zattn.cuh): no per-layer K/V of the memory
+    T* zpad; T* mem; T* kx; T* vx;  // cross-attention keys / values: [N][B*Sm][d] each (K/V form only)
     T* kc; T* vc;                   // [N][B][Lmax][d]
     float* x; T* xn; T* qkv; T* att; T* q2; T* hbuf; float* logits;
     uint8_t* key_valid; uint8_t* cross_mask; uint8_t* done;
+    // latent-space form: folded projections (per layer) and their scratch
+    T* wqz; float* bqz; T* woz; float* boz;      // [N][H*lat][d], [N][H*lat], [N][d][H*lat], [N][d]
+    float* mk; float* mv; float* tvec;           // (Wk Wz) [d][lat], (Wv Wz) [d][lat], Wv bz + bv [d]
+    T* qz; T* zbar;                              // [B][H*lat]
     size_t bytes;
+    static bool want_zmode(const gct_config_t& c, int Lz_) {
+        const bool cond_rows = c.use_cond2lat && c.nconds > 0 && !c.use_cond2dec;
+        return sizeof(T) == 2 && g_gct_zattn && !cond_rows && zattn_supported(c.latent_dim, c.heads, Lz_);
+    }
     void carve(const gct_config_t& c, int B_, int Lz_, int max_len, void* ws) {
         Bump bp(ws);
         B = B_; Lz = Lz_; Lmax = max_len;
-        const int d = c.d_model, nc = c.nconds, N = c.n_layers;
+        const int d = c.d_model, nc = c.nconds, N = c.n_layers, lat = c.latent_dim, HL = c.heads * c.latent_dim;
         Sm = Lz + ((c.use_cond2lat && nc > 0 && !(c.use_cond2dec)) ? nc : 0);
-        zpad = bp.arr<T>((size_t)B * Sm * c.latent_dim);
-        mem = bp.arr<T>((size_t)B * Sm * d);
-        kx = bp.arr<T>((size_t)N * B * Sm * d);
-        vx = bp.arr<T>((size_t)N * B * Sm * d);
+        zmode = want_zmode(c, Lz_);
+        zpad = bp.arr<T>((size_t)B * Sm * lat);
+        mem = kx = vx = nullptr;
+        wqz = woz = qz = zbar = nullptr; bqz = boz = mk = mv = tvec = nullptr;
+        if (!zmode) {
+            mem = bp.arr<T>((size_t)B * Sm * d);
+            kx = bp.arr<T>((size_t)N * B * Sm * d);
+            vx = bp.arr<T>((size_t)N * B * Sm * d);
+        } else {
+            wqz = bp.arr<T>((size_t)N * HL * d); bqz = bp.arr<float>((size_t)N * HL);
+            woz = bp.arr<T>((size_t)N * d * HL); boz = bp.arr<float>((size_t)N * d);
+            mk = bp.arr<float>((size_t)d * lat); mv = bp.arr<float>((size_t)d * lat); tvec = bp.arr<float>(d);
+            qz = bp.arr<T>((size_t)B * HL); zbar = bp.arr<T>((size_t)B * HL);
+        }
         kc = bp.arr<T>((size_t)N * B * Lmax * d);
         vc = bp.arr<T>((size_t)N * B * Lmax * d);
         x = bp.arr<float>((size_t)B * d); xn = bp.arr<T>((size_t)B * d); qkv = bp.arr<T>((size_t)B * 3 * d);
@@ -681,6 +702,51 @@ struct DecodeWs {
         bytes = bp.off + 256;
     }
 };
+
+// Folds fc_z and the cross-attention k / v / out projections of every decoder layer into the two latent-space
+// operands of decode_zattn.cuh.  fp32 SIMT GEMMs over the master weights (about 0.8 GFLOP, once per decode call);
+// results are rounded once to the operand type.  nn.Linear weights are [out, in] row-major.
+template <typename T>
+static int decode_zprep(Model<T>& m, DecodeWs<T>& W) {
+    const int d = m.d, lat = m.lat, N = m.N, H = m.H, HL = H * lat;
+    cudaStream_t st = m.st;
+    const float* Wz = m.P(GCT_SLOT_FCZ_W);      // [d, lat]
+    const float* bz = m.P(GCT_SLOT_FCZ_B);
+    for (int l = 0; l < N; ++l) {
+        const float* Wq = m.P(m.dec_slot(l, D_Q2_W)); const float* bq = m.P(m.dec_slot(l, D_Q2_B));
+        const float* Wk = m.P(m.dec_slot(l, D_KV2_W)); const float* Wv = Wk + (size_t)d * d;
+        const float* bv = m.P(m.dec_slot(l, D_KV2_B)) + d;
+        const float* Wo = m.P(m.dec_slot(l, D_O2_W)); const float* bo = m.P(m.dec_slot(l, D_O2_B));
+        {   // mk[c, a] = sum_m Wk[c, m] Wz[m, a] ;  mv likewise
+            Epilogue e = Model<T>::epi(nullptr, lat); e.out32 = W.mk;
+            GCT_TRY((launch_gemm_simt<float, float, float>(Wk, d, 1, Wz, 1, lat, d, lat, d, 1, e, st)));
+            e.out32 = W.mv;
+            GCT_TRY((launch_gemm_simt<float, float, float>(Wv, d, 1, Wz, 1, lat, d, lat, d, 1, e, st)));
+        }
+        {   // tvec = Wv bz + bv ;  boz = Wo tvec + bo
+            Epilogue e = Model<T>::epi(bv, 1); e.flags = EPI_BIAS_ROW; e.out32 = W.tvec;
+            GCT_TRY((launch_gemm_simt<float, float, float>(Wv, d, 1, bz, 0, 1, d, 1, d, 1, e, st)));
+            Epilogue e2 = Model<T>::epi(bo, 1); e2.flags = EPI_BIAS_ROW; e2.out32 = W.boz + (size_t)l * d;
+            GCT_TRY((launch_gemm_simt<float, float, float>(Wo, d, 1, W.tvec, 0, 1, d, 1, d, 1, e2, st)));
+        }
+        for (int h = 0; h < H; ++h) {
+            const float* mkh = W.mk + (size_t)h * 64 * lat;
+            const float* mvh = W.mv + (size_t)h * 64 * lat;
+            {   // Wqz[h*lat + a, n] = (1/8) sum_i mk[h*64+i, a] Wq[h*64+i, n]
+                Epilogue e = Model<T>::epi(nullptr, d); e.alpha = 0.125f; e.outT = W.wqz + ((size_t)l * HL + (size_t)h * lat) * d;
+                GCT_TRY((launch_gemm_simt<float, float, T>(mkh, 1, lat, Wq + (size_t)h * 64 * d, 1, d, lat, d, 64, 1, e, st)));
+                // bqz[h*lat + a] = (1/8) sum_i mk[h*64+i, a] bq[h*64+i]
+                Epilogue eb = Model<T>::epi(nullptr, 1); eb.alpha = 0.125f; eb.out32 = W.bqz + (size_t)l * HL + (size_t)h * lat;
+                GCT_TRY((launch_gemm_simt<float, float, float>(mkh, 1, lat, bq + h * 64, 0, 1, lat, 1, 64, 1, eb, st)));
+            }
+            {   // Woz[n, h*lat + a] = sum_i Wo[n, h*64+i] mv[h*64+i, a]
+                Epilogue e = Model<T>::epi(nullptr, HL); e.outT = W.woz + (size_t)l * d * HL + (size_t)h * lat;
+                GCT_TRY((launch_gemm_simt<float, float, T>(Wo + h * 64, d, 1, mvh, 1, lat, d, lat, 64, 1, e, st)));
+            }
+        }
+    }
+    return GCT_OK;
+}
 
 template <typename T>
 static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
@@ -694,19 +760,23 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
     GCT_LAUNCH_CHECK();
     cross_mask_kernel<<<cdiv(B * Sm, 256), 256, 0, st>>>(D.src_mask, B, Lz, Sm, W.cross_mask);
     GCT_LAUNCH_CHECK();
-    GCT_TRY(m.linear_T(W.zpad, B * Sm, lat, GCT_SLOT_FCZ_W, GCT_SLOT_FCZ_B, d, W.mem));
-    if (Sm > Lz) {
-        GCT_REQUIRE(D.dconds, "decode: dconds missing");
-        cond_tokens_kernel<T><<<B * nc, 128, 0, st>>>(D.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, W.mem, Sm);
-        GCT_LAUNCH_CHECK();
-    }
-    for (int l = 0; l < N; ++l) {
-        // K and V of the memory as two contiguous [B*Sm, d] slabs (rows [0,d) / [d,2d) of the fused k;v weight)
-        const int ws = m.dec_slot(l, D_KV2_W), bs = m.dec_slot(l, D_KV2_B);
-        Epilogue ek = Model<T>::epi(m.P(bs), d); ek.outT = W.kx + (size_t)l * B * Sm * d;
-        GCT_TRY(m.gemm(W.mem, false, d, m.WT(ws), false, d, B * Sm, d, d, ek));
-        Epilogue ev = Model<T>::epi(m.P(bs) + d, d); ev.outT = W.vx + (size_t)l * B * Sm * d;
-        GCT_TRY(m.gemm(W.mem, false, d, m.WT(ws) + (size_t)d * d, false, d, B * Sm, d, d, ev));
+    if (W.zmode) {
+        GCT_TRY(decode_zprep(m, W));
+    } else {
+        GCT_TRY(m.linear_T(W.zpad, B * Sm, lat, GCT_SLOT_FCZ_W, GCT_SLOT_FCZ_B, d, W.mem));
+        if (Sm > Lz) {
+            GCT_REQUIRE(D.dconds, "decode: dconds missing");
+            cond_tokens_kernel<T><<<B * nc, 128, 0, st>>>(D.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, W.mem, Sm);
+            GCT_LAUNCH_CHECK();
+        }
+        for (int l = 0; l < N; ++l) {
+            // K and V of the memory as two contiguous [B*Sm, d] slabs (rows [0,d) / [d,2d) of the fused k;v weight)
+            const int ws = m.dec_slot(l, D_KV2_W), bs = m.dec_slot(l, D_KV2_B);
+            Epilogue ek = Model<T>::epi(m.P(bs), d); ek.outT = W.kx + (size_t)l * B * Sm * d;
+            GCT_TRY(m.gemm(W.mem, false, d, m.WT(ws), false, d, B * Sm, d, d, ek));
+            Epilogue ev = Model<T>::epi(m.P(bs) + d, d); ev.outT = W.vx + (size_t)l * B * Sm * d;
+            GCT_TRY(m.gemm(W.mem, false, d, m.WT(ws) + (size_t)d * d, false, d, B * Sm, d, d, ev));
+        }
     }
     GCT_CUDA(cudaMemsetAsync(W.done, 0, B, st));
     GCT_CUDA(cudaMemsetAsync(D.status, 0, 2 * sizeof(int), st));
@@ -737,18 +807,38 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             GCT_TRY(m.gemm(W.att, false, d, m.WT(m.dec_slot(l, D_O1_W)), false, d, B, d, d, e));
         }
         GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), W.xn, nullptr, B));
-        GCT_TRY(m.linear_T(W.xn, B, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), d, W.q2));
-        {
-            DecAttnParams p;
-            p.q = W.q2; p.ldq = d; p.knew = nullptr; p.vnew = nullptr; p.ldnew = 0;
-            p.kcache = W.kx + (size_t)l * B * Sm * d; p.vcache = W.vx + (size_t)l * B * Sm * d;
-            p.cache_bstride = (long long)Sm * d; p.pitch = d; p.n_cached = Sm;
-            p.key_valid = W.cross_mask; p.kv_stride = Sm; p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
-            GCT_TRY(launch_decode_attn<T>(p, B, st));
+        if constexpr (sizeof(T) == 2) {
+            if (W.zmode) {
+                // cross-attention in latent space (decode_zattn.cuh): q and out projections carry the folded k / v / fc_z
+                const int HL = m.H * m.lat;
+                {
+                    Epilogue e = Model<T>::epi(W.bqz + (size_t)l * HL, HL); e.outT = W.qz;
+                    GCT_TRY(m.gemm(W.xn, false, d, W.wqz + (size_t)l * HL * d, false, d, B, HL, d, e));
+                }
+                ZAttnParams zp;
+                zp.qz = W.qz; zp.ldq = HL; zp.z = W.zpad; zp.z_bstride = (long long)Sm * m.lat; zp.key_valid = W.cross_mask;
+                zp.kv_stride = Sm; zp.n_keys = Sm; zp.out = W.zbar; zp.ldo = HL; zp.H = m.H; zp.B = B;
+                GCT_TRY(launch_decode_zattn(zp, m.lat, st));
+                {
+                    Epilogue e = Model<T>::epi(W.boz + (size_t)l * d, d); e.res32 = W.x; e.out32 = W.x;
+                    GCT_TRY(m.gemm(W.zbar, false, HL, W.woz + (size_t)l * d * HL, false, HL, B, d, HL, e));
+                }
+            }
         }
-        {
-            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O2_B)), d); e.res32 = W.x; e.out32 = W.x;
-            GCT_TRY(m.gemm(W.att, false, d, m.WT(m.dec_slot(l, D_O2_W)), false, d, B, d, d, e));
+        if (!W.zmode) {
+            GCT_TRY(m.linear_T(W.xn, B, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), d, W.q2));
+            {
+                DecAttnParams p;
+                p.q = W.q2; p.ldq = d; p.knew = nullptr; p.vnew = nullptr; p.ldnew = 0;
+                p.kcache = W.kx + (size_t)l * B * Sm * d; p.vcache = W.vx + (size_t)l * B * Sm * d;
+                p.cache_bstride = (long long)Sm * d; p.pitch = d; p.n_cached = Sm;
+                p.key_valid = W.cross_mask; p.kv_stride = Sm; p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
+                GCT_TRY(launch_decode_attn<T>(p, B, st));
+            }
+            {
+                Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O2_B)), d); e.res32 = W.x; e.out32 = W.x;
+                GCT_TRY(m.gemm(W.att, false, d, m.WT(m.dec_slot(l, D_O2_W)), false, d, B, d, d, e));
+            }
         }
         GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), W.xn, nullptr, B));
         {

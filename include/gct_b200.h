@@ -84,6 +84,8 @@ int gct_num_slots(int n_layers);
 int gct_set_gemm_backend(int simt_only);            /* test hook: 1 routes bf16 GEMMs through the SIMT kernel */
 int gct_set_persistent_gemm(int enabled);          /* persistent, TMEM double-buffered GEMM for > 148 tiles (default on) */
 int gct_set_attention_backend(int simt_only);       /* test hook: 1 keeps bf16 attention on the SIMT kernel */
+int gct_set_latent_cross_attention(int enabled);    /* bf16 decode: 1 (default) evaluates cross-attention in latent space when the
+                                                       memory has no condition rows, 0 keeps the per-layer K/V form */
 int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring stages*10 + rows per CTA (0 = default) */
 int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue (default on) */
 int gct_set_pdl(int enabled);                       /* programmatic dependent launch on the decode path (default on) */
@@ -183,7 +185,7 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
                      int step_end, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
 int gct_decode_launches_per_step(const gct_config_t* cfg);
-int gct_decode_begin_launches(const gct_config_t* cfg);
+int gct_decode_begin_launches(const gct_config_t* cfg, int Lz);
 /* the step's attention kernel on its own (unit tests, roofline timing): one query per (batch, head) over
  * n_cached cached keys (+ this step's knew/vnew row, which is appended to the cache when non-NULL) */
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,

@@ -109,3 +109,38 @@ def test_eos_stops_the_loop_like_the_reference():
     want = O.sampling_decode({k: v.cpu() for k, v in sd2.items()}, cfg, d["zs"], d["ys0"], d["src_mask"], max_strlen=14)
     assert torch.equal(ys, want)
     assert ys.size(1) == d["ys0"].size(1) + 1
+
+
+@pytest.mark.parametrize("latent_form", [True, False])
+def test_bf16_cross_attention_forms_follow_the_oracle(latent_form):
+    """bf16 tier, ragged latent lengths: the first sampled token (six layers of cross-attention deep) must follow the fp32
+    oracle's step-0 distribution both in the latent-space form of the cross-attention (decode_zattn.cuh, default when the
+    memory has no condition rows) and in the per-layer K/V form."""
+    import gct_plus_b200._lib as L
+    fx = load_golden("vaetf_full")
+    L.lib().gct_set_latent_cross_attention(int(latent_form))
+    try:
+        s, sd = _sampler(fx, "bf16", algo="multinomial", max_strlen=3, use_cuda_graph=False)
+        per, Lz = 512, 45
+        lens = [45, 31, 17, 1]
+        g = torch.Generator().manual_seed(23)
+        z1 = torch.randn(len(lens), Lz, 128, generator=g)
+        zs = z1.repeat_interleave(per, dim=0).contiguous().to(DEV)
+        n = zs.size(0)
+        ys0 = torch.full((n, 1), 2, dtype=torch.long, device=DEV)
+        mask1 = torch.arange(Lz)[None, None, :] < torch.tensor(lens)[:, None, None]
+        mask = mask1.repeat_interleave(per, dim=0).to(DEV)
+        u = torch.rand(2, n, generator=g)
+        ys = s._decode_cached(zs=zs, ys=ys0, src_mask=mask, uniforms=u.to(DEV)).cpu()
+        cfg = cfg_from_fixture(fx)
+        for gi in range(len(lens)):
+            logits = O.decode_logits(sd, cfg, ys0[:1].cpu(), z1[gi:gi + 1], mask1[gi:gi + 1], O.trg_mask(ys0[:1].cpu(), 1))
+            prob = torch.softmax(logits[0, -1], dim=-1)
+            rows = slice(gi * per, (gi + 1) * per)
+            want = O.inverse_cdf_draw(prob.expand(per, -1), u[0, rows])
+            agree = float((ys[rows, 1] == want).float().mean())
+            assert agree > 0.95, (latent_form, lens[gi], agree)      # bf16 tier: draws flip only next to a CDF boundary
+            hist = torch.bincount(ys[rows, 1], minlength=32).float() / per
+            assert float((hist - prob).abs().max()) < 0.08, (latent_form, lens[gi])
+    finally:
+        L.lib().gct_set_latent_cross_attention(1)
