@@ -75,15 +75,38 @@ class Sampling:
         return smi
 
     def ids_to_smiles(self, outs: np.ndarray):
-        """Batch version of id_to_smi: cut each row at its first <eos>, drop <sos>, join."""
-        is_eos = outs == self.eos_id
-        end = np.where(is_eos.any(axis=1), is_eos.argmax(axis=1), outs.shape[1])
-        itos, sos = self._itos, self.sos_id
-        res = []
-        for row, e in zip(outs, end):
-            r = row[:e]
-            res.append(''.join(itos[r[r != sos]]))
-        return res
+        """Batch version of id_to_smi (Inference/sampling_tool.py:54-61 of the reference): cut each row at its first
+        <eos>, drop <sos>, join the token strings.  One pass in the library's host-side detokeniser (gct_detokenize)
+        writes newline-terminated rows; Python only decodes and splits the blob."""
+        outs = np.ascontiguousarray(outs, dtype=np.int16)
+        n, width = outs.shape
+        vt = self._vocab_table()
+        if vt is None or n == 0:              # a token contains a newline: row-by-row join
+            itos, sos, eos = self._itos, self.sos_id, self.eos_id
+            is_eos = outs == eos
+            end = np.where(is_eos.any(axis=1), is_eos.argmax(axis=1), width)
+            return [''.join(itos[row[:e][row[:e] != sos]]) for row, e in zip(outs, end)]
+        blob, voff, maxlen = vt
+        out = np.empty(n * (width * maxlen + 1), dtype=np.uint8)
+        nb = L.lib().gct_detokenize(outs.ctypes.data, n, width, blob.ctypes.data, voff.ctypes.data, len(voff) - 1, int(self.eos_id),
+                                    int(self.sos_id), out.ctypes.data, out.size)
+        if nb < 0:
+            L.check(int(nb), "gct_detokenize")
+        return out[:nb].tobytes().decode('utf-8').split('\n')[:-1]
+
+    def _vocab_table(self):
+        vt = getattr(self, '_vocab_tab', False)
+        if vt is False:
+            enc = [str(t).encode('utf-8') for t in self._itos]
+            if any(b'\n' in e for e in enc):
+                vt = None
+            else:
+                voff = np.zeros(len(enc) + 1, dtype=np.int32)
+                voff[1:] = np.cumsum([len(e) for e in enc])
+                blob = np.frombuffer(b''.join(enc) + b'\x00', dtype=np.uint8).copy()
+                vt = (blob, voff, max(1, max(len(e) for e in enc)))
+            self._vocab_tab = vt
+        return vt
 
     def smi_to_id(self, smi, add_sos=False, add_sep=False, add_eos=False):
         ids = []
@@ -254,7 +277,7 @@ class Sampling:
 
     # ------------------------------------------------------------------ shared tail of sample_smiles
     def _finish(self, outs, strip):
-        outs = outs.cpu().numpy()
+        outs = outs.to(torch.int16).cpu().numpy()          # ids < 2^15: a quarter of the int64 device->host bytes
         smiles = self.ids_to_smiles(outs[:, strip:])
         toklen_gen = [len(self.TRG.tokenize(smi)) for smi in smiles]
         return smiles, toklen_gen

@@ -82,6 +82,7 @@ _PROTOS = {
     "gct_decode_begin": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), vp, sz, vp]),
     "gct_decode_steps": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), C.c_int, C.c_int,
                                    vp, sz, vp]),
+    "gct_detokenize": (i64, [vp, i64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, i64]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
     "gct_decode_begin_launches": (C.c_int, [C.POINTER(GctConfig), C.c_int]),
     "gct_decode_attention": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,

@@ -192,6 +192,48 @@ __device__ __forceinline__ float2 gelu_pair_fwd(float2 x, float2 m) {
     return __fmul2_rn(__fmul2_rn(x, m), phi);
 }
 
+// The same evaluation for NP independent pairs written stage by stage, so that the dependent FFMA2 chains of different
+// pairs interleave in the instruction stream (a lone Horner chain stalls ~4 cycles per step on its own result).
+// WITH_GRAD = false skips dg.
+template <int NP, bool WITH_GRAD>
+__device__ __forceinline__ void gelu_pairs(const float2* x, const float2* m, float2* g, float2* dg) {
+    float2 t[NP], e[NP], p[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) t[i] = __ffma2_rn(make_float2(fabsf(x[i].x), fabsf(x[i].y)), f2(GCT_AS_P), f2(1.f));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) e[i] = __fmul2_rn(__fmul2_rn(x[i], x[i]), f2(GCT_NEG_HALF_LOG2E));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) t[i] = make_float2(rcp_approx(t[i].x), rcp_approx(t[i].y));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) e[i] = make_float2(ex2_approx(e[i].x), ex2_approx(e[i].y));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = __ffma2_rn(t[i], f2(GCT_AS_A5), f2(GCT_AS_A4));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = __ffma2_rn(p[i], t[i], f2(GCT_AS_A3));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = __ffma2_rn(p[i], t[i], f2(GCT_AS_A2));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = __ffma2_rn(p[i], t[i], f2(GCT_AS_A1));
+#pragma unroll
+    for (int i = 0; i < NP; ++i) t[i] = __fmul2_rn(t[i], e[i]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = __ffma2_rn(__fmul2_rn(p[i], t[i]), f2(-1.f), f2(0.5f));      // 0.5 - Phi(-|x|)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { p[i].x = copysignf(p[i].x, x[i].x); p[i].y = copysignf(p[i].y, x[i].y); }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = __fadd2_rn(p[i], f2(0.5f));                                  // Phi(x)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) t[i] = __fmul2_rn(x[i], m[i]);                                      // keep * x
+#pragma unroll
+    for (int i = 0; i < NP; ++i) g[i] = __fmul2_rn(t[i], p[i]);
+    if (WITH_GRAD) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) p[i] = __fmul2_rn(p[i], m[i]);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) dg[i] = __ffma2_rn(__fmul2_rn(t[i], e[i]), f2(GCT_INV_SQRT_2PI), p[i]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // counter-based dropout RNG: keep(seed, site, idx) is a pure function, so backward regenerates
 // the same mask without storing it.  (Parity with torch's Philox stream is statistical only.)

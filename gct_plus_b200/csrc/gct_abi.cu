@@ -248,6 +248,38 @@ double gct_noam_lr(int64_t step, int d_model, int64_t warmup) {
     return pow((double)d_model, -0.5) * (head < tail ? head : tail);
 }
 
+// Host-side detokeniser (Inference/sampling_tool.py:54-61 for a whole batch): each row of ids is cut at its first
+// <eos>, <sos> ids are dropped, the token strings (UTF-8, concatenated in `vocab` with offsets `voff[V+1]`) are joined
+// and the row is terminated by '\n'.  `out` must hold n*(width*max_token_bytes + 1) bytes; returns the bytes written
+// or a negative code.  Plain C loop on the calling thread: 3 M tokens take a few milliseconds.
+int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* vocab, const int32_t* voff, int V, int eos_id,
+                       int sos_id, char* out, int64_t out_bytes) {
+    if (!ids || !vocab || !voff || !out || n < 0 || width < 0 || V <= 0) {
+        snprintf(g_gct_err, sizeof(g_gct_err), "detokenize: bad arguments");
+        return GCT_ERR_ARG;
+    }
+    int maxlen = 0;
+    for (int v = 0; v < V; ++v) maxlen = voff[v + 1] - voff[v] > maxlen ? voff[v + 1] - voff[v] : maxlen;
+    if (out_bytes < n * ((int64_t)width * maxlen + 1)) {
+        snprintf(g_gct_err, sizeof(g_gct_err), "detokenize: output buffer too small");
+        return GCT_ERR_ARG;
+    }
+    char* o = out;
+    for (int64_t r = 0; r < n; ++r) {
+        const int16_t* row = ids + r * width;
+        for (int j = 0; j < width; ++j) {
+            const int t = row[j];
+            if (t == eos_id) break;
+            if (t == sos_id || t < 0 || t >= V) continue;
+            const int len = voff[t + 1] - voff[t];
+            memcpy(o, vocab + voff[t], (size_t)len);
+            o += len;
+        }
+        *o++ = '\n';
+    }
+    return (int64_t)(o - out);
+}
+
 // ---------------- decode ----------------
 size_t gct_decode_workspace_bytes(const gct_config_t* cfg, int B, int Lz, int max_len) {
     if (cfg->dtype == GCT_DTYPE_F32) { DecodeWs<float> W; W.carve(*cfg, B, Lz, max_len, nullptr); return W.bytes; }

@@ -304,11 +304,13 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
         }
         if constexpr (WHICH == 1) return;        // aux-only pass: the pre-activation is all that was wanted
         const uint32_t pair0 = (uint32_t)(off >> 1);
+        float2 x[8], m[8], g[8];                 // packed fp32x2 GELU with the dropout multiplier folded in
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {            // packed fp32x2 GELU with the dropout multiplier folded in
-            const float2 g = gelu_pair_fwd(make_float2(v[2 * i], v[2 * i + 1]), drop_mult_pair(e.drop, pair0 + i));
-            v[2 * i] = g.x; v[2 * i + 1] = g.y;
-        }
+        for (int i = 0; i < 8; ++i) { x[i] = make_float2(v[2 * i], v[2 * i + 1]); m[i] = drop_mult_pair(e.drop, pair0 + i); }
+        gelu_pairs<4, false>(x, m, g, nullptr);
+        gelu_pairs<4, false>(x + 4, m + 4, g + 4, nullptr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[2 * i] = g[i].x; v[2 * i + 1] = g[i].y; }
     } else if (e.drop.thresh) {
         const uint32_t pair0 = (uint32_t)(off >> 1);
 #pragma unroll
@@ -362,6 +364,10 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
     }
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 // GELU forward that also saves the gradient factor, 16 columns of one row in ONE pass over the accumulator:
 //   gp[8] = bf16x2 pairs of keep*gelu(acc + bias),  dp[8] = bf16x2 pairs of keep*gelu'(acc + bias)
 __device__ __forceinline__ void epi_gelu16(const Epilogue& e, const float* __restrict__ bias, uint32_t taddr, size_t off, int col,
@@ -372,15 +378,20 @@ __device__ __forceinline__ void epi_gelu16(const Epilogue& e, const float* __res
     float v[16];
     tmem_ld16(taddr, v);
     const uint32_t pair0 = (uint32_t)(off >> 1);
+    float2 x[8], m[8], g[8], dg[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float2 bb = (i & 1) ? make_float2(b4[i >> 1].z, b4[i >> 1].w) : make_float2(b4[i >> 1].x, b4[i >> 1].y);
-        const float2 x = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), bb);
-        float2 g, dg;
-        gelu_pair(x, drop_mult_pair<false>(e.drop, pair0 + i), g, dg);
-        __nv_bfloat162 gh = __floats2bfloat162_rn(g.x, g.y), dh = __floats2bfloat162_rn(dg.x, dg.y);
-        gp[i] = *reinterpret_cast<uint32_t*>(&gh);
-        dp[i] = *reinterpret_cast<uint32_t*>(&dh);
+        x[i] = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), bb);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = drop_mult_pair<false>(e.drop, pair0 + i);
+    gelu_pairs<4, true>(x, m, g, dg);
+    gelu_pairs<4, true>(x + 4, m + 4, g + 4, dg + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        gp[i] = pack_bf16x2(g[i].x, g[i].y);
+        dp[i] = pack_bf16x2(dg[i].x, dg[i].y);
     }
 }
 

@@ -845,9 +845,12 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff); e.flags = EPI_GELU; e.outT = W.hbuf;
             GCT_TRY(m.gemm(W.xn, false, d, m.WT(m.dec_slot(l, D_F1_W)), false, d, B, dff, d, e));
         }
-        {   // x += hbuf W2^T + b2 : in-place accumulate lets the long-K GEMM use split-K (bias from split 0 only)
+        if (B <= 1024) {   // x += hbuf W2^T + b2 : in-place accumulate lets the long-K GEMM use split-K (bias from split 0 only)
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F2_B)), d); e.out32 = W.x; e.flags = EPI_ACCUM;
-            GCT_TRY(m.gemm(W.hbuf, false, dff, m.WT(m.dec_slot(l, D_F2_W)), false, dff, B, d, dff, e, B <= 1024 ? 2 : 1));
+            GCT_TRY(m.gemm(W.hbuf, false, dff, m.WT(m.dec_slot(l, D_F2_W)), false, dff, B, d, dff, e, 2));
+        } else {           // enough row tiles to fill the machine: residual form, served by the specialised epilogue
+            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F2_B)), d); e.res32 = W.x; e.out32 = W.x;
+            GCT_TRY(m.gemm(W.hbuf, false, dff, m.WT(m.dec_slot(l, D_F2_W)), false, dff, B, d, dff, e));
         }
     }
     if (!sample) return GCT_OK;      // prefix position: only the caches were needed

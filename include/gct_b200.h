@@ -184,6 +184,11 @@ int gct_decode_begin(const gct_config_t* cfg, const gct_weights_t* w, const gct_
 int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, int step_begin,
                      int step_end, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
+/* Host-side batch detokeniser (replaces the per-row Python loop of Inference/sampling_tool.py:54-61 `id_to_smi`): rows of
+ * int16 ids [n, width] are cut at the first eos_id, sos_id is dropped, token strings (UTF-8 blob `vocab`, offsets
+ * voff[V+1]) are joined, each row ends with '\n'.  out_bytes >= n*(width*max_token_bytes+1).  Returns bytes written. */
+int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* vocab, const int32_t* voff, int V, int eos_id,
+                       int sos_id, char* out, int64_t out_bytes);
 int gct_decode_launches_per_step(const gct_config_t* cfg);
 int gct_decode_begin_launches(const gct_config_t* cfg, int Lz);
 /* the step's attention kernel on its own (unit tests, roofline timing): one query per (batch, head) over

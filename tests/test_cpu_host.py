@@ -26,7 +26,7 @@ def test_library_exports_every_header_symbol(built):
     L = built
     lib = L.lib()
     hdr = open(os.path.join(ROOT, "include", "gct_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|size_t|double|const char\*)\s+(gct_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|size_t|double|const char\*)\s+(gct_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
     assert declared, "no declarations parsed"
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/gct_b200.h but not exported"
@@ -104,3 +104,26 @@ def test_kl_annealer():
     from gct_plus_b200.Train.trainer1 import KLAnnealer
     m = load_golden("misc")
     assert [KLAnnealer(e, 0.02, 0.02, 1) for e in range(1, 6)] == m["kla"]
+
+
+def test_batch_detokeniser_matches_id_to_smi(built):
+    """ids_to_smiles (host-side gct_detokenize) == the reference's per-row id_to_smi (Inference/sampling_tool.py:54-61),
+    including multi-character / multi-byte tokens, rows without <eos>, and the newline-in-token fallback."""
+    import numpy as np
+    from gct_plus_b200.Inference.sampling_tool import Sampling
+
+    class _V:
+        pass
+
+    for vocab in (["<unk>", "<pad>", "<sos>", "<eos>", "<sep>", "C", "c", "Cl", "Br", "[nH]", "(", ")", "1", "=", "é"],
+                  ["<unk>", "<pad>", "<sos>", "<eos>", "x\ny", "C"]):
+        s = Sampling.__new__(Sampling)
+        s.TRG = _V(); s.TRG.vocab = _V(); s.TRG.vocab.itos = vocab
+        s._itos = np.array(vocab, dtype=object)
+        s.sos_id, s.eos_id = 2, 3
+        rng = np.random.RandomState(0)
+        outs = rng.randint(0, len(vocab), size=(257, 40))
+        outs[:, 0] = 2
+        outs[5] = np.where(outs[5] == 3, 0, outs[5])          # a row that never emits <eos>
+        assert s.ids_to_smiles(outs) == [s.id_to_smi(r) for r in outs]
+    assert s.ids_to_smiles(np.zeros((0, 7), dtype=np.int64)) == []
