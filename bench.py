@@ -240,7 +240,7 @@ def run_sampling(args, rank, world, dev):
     t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     assert n_out == K * BATCH
     h2d = int(np.mean([z.numel() * 4 + BATCH * z.size(1) + BATCH * 8 for _, z in inputs[W:]]))
-    d2h = BATCH * MAX_STRLEN * 8
+    d2h = BATCH * MAX_STRLEN * 2          # int16 token ids
     cfg = sampler.model._cfg()
     per_step = L.lib().gct_decode_launches_per_step(cfg)
     launches = K * (L.lib().gct_decode_begin_launches(cfg, int(inputs[W][1].size(1))) + (n_steps_run // max(K, 1)) * per_step)
