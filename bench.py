@@ -324,6 +324,55 @@ def run_training(args, rank, world, dev):
             "peak_source": src, "dtype": "bf16", "loss_finite": bool(np.isfinite(loss))}
 
 
+def run_input_pipeline(dev, batch=512, nrows=20000, iters=50):
+    """batches of the training dict assembled on the device (gct_collate over the pre-tokenised corpus
+    in HBM) next to the CPU oracle port of the reference's SmilesDataset + collate_fn + Field.process path, both for
+    pscavaetf rows (scaffold <sep> smiles + 3 properties) of MOSES-like length.  Device leg: CUDA events; the index
+    upload (B x 8 bytes) is inside the timed region."""
+    import pandas as pd
+    from gct_plus_b200.Utils.dataset import DeviceDataLoader, TokenisedCorpus
+    from oracle import collate_oracle as CO          # cpu_baseline leg only
+    atoms = ["C", "c", "N", "n", "O", "o", "S", "s", "F", "Cl", "Br", "(", ")", "[nH]", "=", "#", "1", "2", "3", "-", "[C@@H]"]
+    rng = np.random.RandomState(5)
+    mk = lambda lo, hi: "".join(rng.choice(atoms, size=rng.randint(lo, hi)))      # noqa: E731
+    props = ["logP", "tPSA", "QED"]
+    df = {"src": [mk(20, 56) for _ in range(nrows)], "src_scaffold": [mk(8, 24) for _ in range(nrows)]}
+    for p_ in props:
+        df[f"src_{p_}"] = rng.randn(nrows).astype(np.float32)
+        df[f"trg_{p_}"] = rng.randn(nrows).astype(np.float32)
+    df = pd.DataFrame(df)
+    SRC, TRG = CO.smiles_fields(atoms, True)
+    t0 = time.perf_counter()
+    corpus = TokenisedCorpus(df, props, SRC, TRG, use_scaffold=True).to(dev)
+    t_tok = time.perf_counter() - t0
+    order = torch.randperm(nrows, generator=torch.Generator().manual_seed(0)).numpy()
+    dl = DeviceDataLoader(corpus, "pscavaetf", batch, order)
+    it = iter(dl)
+    for _ in range(3):
+        next(it)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nb, out_bytes = 0, 0
+    for b in it:
+        nb += 1
+        out_bytes += sum(v.numel() * v.element_size() for v in b.values())
+        if nb == iters:
+            break
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / nb
+    t0 = time.perf_counter()
+    ncpu = 0
+    for _ in CO.batches(df, order[:3 * batch], batch, "pscavaetf", SRC, TRG, props, True):
+        ncpu += 1
+    t_cpu = (time.perf_counter() - t0) / ncpu
+    return {"workload": f"pscavaetf training batches of {batch} rows from a {nrows}-row synthetic corpus", "device_batches_per_sec": 1e3 / ms,
+            "device_us_per_batch": ms * 1e3, "device_output_bytes_per_batch": out_bytes // nb,
+            "one_off_tokenisation_s": t_tok, "cpu_port_batches_per_sec": 1.0 / t_cpu,
+            "cpu_port": "oracle port of SmilesDataset.__getitem__ + scavaetf_collate_fn + Field.process, 1 thread (the reference uses num_workers=0)"}
+
+
 def base_config(batch, world, note):
     return {"workload": "cfg2 vaetf unconditioned sampling: multinomial decode to max_strlen 100 (99 steps per batch), latent lengths "
                         "round(N(35,7^2)) in [13,55], random-init weights (no <eos> early stop)",
@@ -461,6 +510,8 @@ def main():
         s.pop("sampler")
         torch.cuda.empty_cache()
         train = run_training(args, rank, world, dev)
+        if rank == 0 and not args.no_cpu:
+            train["input_pipeline"] = run_input_pipeline(dev)
     if rank == 0:
         cpu = None if args.no_cpu else cpu_baseline()
         line = {"metric": "sampled_smiles_per_sec", "value": s["value"], "unit": "SMILES/s", "n_gpus": world, "steps": args.steps,

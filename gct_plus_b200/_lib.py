@@ -44,6 +44,11 @@ class GctDecode(C.Structure):
                 ("status", vp)]
 
 
+class GctCorpus(C.Structure):
+    _fields_ = [("src_ids", vp), ("trg_ids", vp), ("tok_off", vp), ("sca_src_ids", vp), ("sca_trg_ids", vp), ("sca_off", vp),
+                ("econds", vp), ("dconds", vp), ("nconds", i32), ("n_rows", i64)]
+
+
 _PROTOS = {
     "gct_last_error": (C.c_char_p, []),
     "gct_version": (C.c_int, []),
@@ -82,6 +87,8 @@ _PROTOS = {
     "gct_decode_begin": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), vp, sz, vp]),
     "gct_decode_steps": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), C.c_int, C.c_int,
                                    vp, sz, vp]),
+    "gct_collate": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                              vp, vp]),
     "gct_detokenize": (i64, [vp, i64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, i64]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
     "gct_decode_begin_launches": (C.c_int, [C.POINTER(GctConfig), C.c_int]),

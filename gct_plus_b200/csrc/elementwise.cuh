@@ -538,3 +538,54 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] = pi;
     if (shadow) shadow[i] = __float2bfloat16_rn(pi);
 }
+
+// ==========================================================================================
+// input pipeline: batch assembly from the pre-tokenised corpus (Model/collate_fn.py + Field.process)
+// one CTA per batch row; int16 ids in, int64 padded rows out (the layout forward_propagation expects)
+// ==========================================================================================
+struct CollateParams {
+    const int16_t* src_ids; const int16_t* trg_ids; const int64_t* tok_off;
+    const int16_t* sca_src_ids; const int16_t* sca_trg_ids; const int64_t* sca_off;
+    const float* econds; const float* dconds; int nconds; long long n_rows;
+    const int64_t* rows; int B, S, T;
+    int pad_src, pad_trg, sos, eos, sep_src, sep_trg;
+    int64_t* src; int64_t* trg; float* econds_out; float* dconds_out;
+};
+__global__ void collate_kernel(CollateParams p) {
+    const int b = blockIdx.x;
+    long long r = p.rows[b];
+    if (r < 0 || r >= p.n_rows) r = 0;                    // out-of-range row ids are a caller bug; stay in bounds
+    const long long t0 = p.tok_off[r];
+    const int nt = (int)(p.tok_off[r + 1] - t0);
+    const bool sca = p.sep_src >= 0 && p.sca_off != nullptr;
+    const long long s0 = sca ? p.sca_off[r] : 0;
+    const int ns = sca ? (int)(p.sca_off[r + 1] - s0) : 0;
+    const int pre = sca ? ns + 1 : 0;                     // scaffold tokens + <sep>
+    if (p.src) {
+        int64_t* o = p.src + (size_t)b * p.S;
+        for (int j = threadIdx.x; j < p.S; j += blockDim.x) {
+            int64_t v = p.pad_src;
+            if (j < ns) v = p.sca_src_ids[s0 + j];
+            else if (sca && j == ns) v = p.sep_src;
+            else if (j - pre < nt) v = p.src_ids[t0 + (j - pre)];
+            o[j] = v;
+        }
+    }
+    if (p.trg) {
+        int64_t* o = p.trg + (size_t)b * p.T;
+        for (int j = threadIdx.x; j < p.T; j += blockDim.x) {
+            const int k = j - 1;                          // position after <sos>
+            int64_t v = p.pad_trg;
+            if (j == 0) v = p.sos;
+            else if (k < ns) v = p.sca_trg_ids[s0 + k];
+            else if (sca && k == ns) v = p.sep_trg;
+            else if (k - pre < nt) v = p.trg_ids[t0 + (k - pre)];
+            else if (k - pre == nt) v = p.eos;
+            o[j] = v;
+        }
+    }
+    if (threadIdx.x < p.nconds) {
+        if (p.econds_out) p.econds_out[(size_t)b * p.nconds + threadIdx.x] = p.econds[(size_t)r * p.nconds + threadIdx.x];
+        if (p.dconds_out) p.dconds_out[(size_t)b * p.nconds + threadIdx.x] = p.dconds[(size_t)r * p.nconds + threadIdx.x];
+    }
+}

@@ -280,6 +280,26 @@ int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* voc
     return (int64_t)(o - out);
 }
 
+// ---------------- input pipeline ----------------
+int gct_collate(const gct_corpus_t* c, const int64_t* rows, int B, int S, int T, int pad_src, int pad_trg, int sos_id, int eos_id,
+                int sep_src, int sep_trg, int64_t* src, int64_t* trg, float* econds_out, float* dconds_out, void* stream) {
+    GCT_REQUIRE(c && rows && B >= 0 && S >= 0 && T >= 0, "collate: bad arguments");
+    GCT_REQUIRE(c->tok_off && (!src || c->src_ids) && (!trg || c->trg_ids), "collate: corpus arrays missing");
+    GCT_REQUIRE(sep_src < 0 || (c->sca_off && c->sca_src_ids && c->sca_trg_ids), "collate: scaffold arrays missing");
+    GCT_REQUIRE(c->nconds >= 0 && c->nconds <= 32, "collate: nconds=%d outside [0,32]", c->nconds);
+    GCT_REQUIRE(!(econds_out && !c->econds) && !(dconds_out && !c->dconds), "collate: condition arrays missing");
+    if (B == 0) return GCT_OK;
+    CollateParams p;
+    p.src_ids = c->src_ids; p.trg_ids = c->trg_ids; p.tok_off = c->tok_off; p.sca_src_ids = c->sca_src_ids;
+    p.sca_trg_ids = c->sca_trg_ids; p.sca_off = c->sca_off; p.econds = c->econds; p.dconds = c->dconds; p.nconds = c->nconds;
+    p.n_rows = c->n_rows; p.rows = rows; p.B = B; p.S = S; p.T = T; p.pad_src = pad_src; p.pad_trg = pad_trg; p.sos = sos_id;
+    p.eos = eos_id; p.sep_src = sep_src; p.sep_trg = sep_trg; p.src = src; p.trg = trg; p.econds_out = econds_out;
+    p.dconds_out = dconds_out;
+    collate_kernel<<<B, 128, 0, ST(stream)>>>(p);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
 // ---------------- decode ----------------
 size_t gct_decode_workspace_bytes(const gct_config_t* cfg, int B, int Lz, int max_len) {
     if (cfg->dtype == GCT_DTYPE_F32) { DecodeWs<float> W; W.carve(*cfg, B, Lz, max_len, nullptr); return W.bytes; }

@@ -184,18 +184,38 @@ int gct_decode_begin(const gct_config_t* cfg, const gct_weights_t* w, const gct_
 int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, int step_begin,
                      int step_end, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
+int gct_decode_launches_per_step(const gct_config_t* cfg);
+int gct_decode_begin_launches(const gct_config_t* cfg, int Lz);
 /* Host-side batch detokeniser (replaces the per-row Python loop of Inference/sampling_tool.py:54-61 `id_to_smi`): rows of
  * int16 ids [n, width] are cut at the first eos_id, sos_id is dropped, token strings (UTF-8 blob `vocab`, offsets
  * voff[V+1]) are joined, each row ends with '\n'.  out_bytes >= n*(width*max_token_bytes+1).  Returns bytes written. */
 int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* vocab, const int32_t* voff, int V, int eos_id,
                        int sos_id, char* out, int64_t out_bytes);
-int gct_decode_launches_per_step(const gct_config_t* cfg);
-int gct_decode_begin_launches(const gct_config_t* cfg, int Lz);
 /* the step's attention kernel on its own (unit tests, roofline timing): one query per (batch, head) over
  * n_cached cached keys (+ this step's knew/vnew row, which is appended to the cache when non-NULL) */
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,
                          int64_t cache_bstride, int pitch, int n_cached, const uint8_t* key_valid, int kv_stride, void* out,
                          int ldo, int B, int H, int dtype, void* stream);
+
+/* ---- input pipeline: Model/collate_fn.py:4-124 + torchtext-0.6 Field.process, on a corpus that was
+ * tokenised once (Utils/dataset.py:251-289 tokenises every row again on every access) and lives in HBM as CSR arrays.
+ * One launch assembles a whole batch: src[b] = [scaffold <sep>] smiles <pad>..., trg[b] = <sos> [scaffold <sep>] smiles
+ * <eos> <pad>..., econds/dconds rows gathered.  S / T are the batch maxima the host computed from the row lengths. */
+typedef struct {
+    const int16_t* src_ids;     /* smiles tokens in the SRC vocabulary, all rows back to back      */
+    const int16_t* trg_ids;     /* the same tokens in the TRG vocabulary                           */
+    const int64_t* tok_off;     /* [n_rows + 1]                                                    */
+    const int16_t* sca_src_ids; /* scaffold tokens (SRC / TRG vocabulary) or NULL                  */
+    const int16_t* sca_trg_ids;
+    const int64_t* sca_off;     /* [n_rows + 1] or NULL                                            */
+    const float* econds;        /* [n_rows, nconds] or NULL                                        */
+    const float* dconds;
+    int32_t nconds;
+    int64_t n_rows;
+} gct_corpus_t;
+int gct_collate(const gct_corpus_t* corpus, const int64_t* rows, int B, int S, int T, int pad_src, int pad_trg, int sos_id,
+                int eos_id, int sep_src, int sep_trg, int64_t* src, int64_t* trg, float* econds_out, float* dconds_out,
+                void* stream);      /* sep_src < 0: no scaffold prefix */
 
 /* ---- data-parallel gradient exchange (train1.py:111-112 DDP) --------------------------------- */
 /* in-place sum over ranks through NCCL; comm is an ncclComm_t created by the host.  Returns

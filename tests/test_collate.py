@@ -1,0 +1,125 @@
+"""Input pipeline: oracle vs the reference's own collate_fn (golden), host-side corpus logic (CPU), and
+the device batch assembly (gct_collate) bit-exact against both (GPU)."""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import collate_oracle as CO  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "collate.pt")
+CASES = ["vaetf", "pvaetf", "scavaetf", "pscavaetf"]
+
+
+def _gold():
+    g = torch.load(GOLD, weights_only=False)
+    return g, pd.DataFrame(g["frame"])
+
+
+def test_tokeniser_regex():
+    tk = CO.MolTokenizer()
+    assert tk("CCl(Br)[nH]c1%12=O") == ["C", "Cl", "(", "Br", ")", "[nH]", "c", "1", "%12", "=", "O"]
+    tks = CO.MolTokenizer(add_sep=True)
+    assert tks("c1ccccc1<sep>CCO") == ["c", "1", "c", "c", "c", "c", "c", "1", "<sep>", "C", "C", "O"]
+    assert tks("CCO") == ["C", "C", "O"]
+
+
+def test_field_process_pads_to_the_longest_row():
+    SRC, TRG = CO.smiles_fields(["C", "N"])
+    s = SRC.process([["C", "N", "C"], ["N"], ["X"]])
+    assert s.tolist() == [[2, 3, 2], [3, 1, 1], [0, 1, 1]]          # <unk>=0, <pad>=1; no init / eos for SRC
+    t = TRG.process([["C", "N", "C"], ["N"]])
+    assert t.tolist() == [[2, 4, 5, 4, 3], [2, 5, 3, 1, 1]]         # <sos>=2 ... <eos>=3 <pad>=1
+
+
+@pytest.mark.parametrize("mt", CASES)
+def test_oracle_collate_matches_reference_collate_fn(mt):
+    g, df = _gold()
+    c = g["cases"][mt]
+    SRC, TRG = CO.smiles_fields(g["atoms"], c["add_sep"])
+    got = list(CO.batches(df, c["order"], c["batch_size"], mt, SRC, TRG, c["property_list"], c["use_scaffold"]))
+    assert len(got) == len(c["batches"])
+    for a, b in zip(got, c["batches"]):
+        assert set(a) == set(b)
+        for k in b:
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), (mt, k)
+
+
+def test_corpus_csr_matches_getitem():
+    from gct_plus_b200.Utils.dataset import TokenisedCorpus
+    g, df = _gold()
+    SRC, TRG = CO.smiles_fields(g["atoms"], True)
+    corpus = TokenisedCorpus(df, g["props"], SRC, TRG, use_scaffold=True)
+    assert len(corpus) == len(df)
+    for r in (0, 3, 5, len(df) - 1):
+        it = CO.getitem(df.iloc[r], SRC, TRG, g["props"], True)
+        a, b = corpus.tok_off[r], corpus.tok_off[r + 1]
+        assert corpus.src_ids[a:b].tolist() == [SRC.vocab.stoi[t] for t in it["src"]]
+        assert corpus.trg_ids[a:b].tolist() == [TRG.vocab.stoi[t] for t in it["trg"]]
+        a, b = corpus.sca_off[r], corpus.sca_off[r + 1]
+        assert corpus.sca_trg_ids[a:b].tolist() == [TRG.vocab.stoi[t] for t in it["trg_scaffold"]]
+        assert np.allclose(corpus.econds[r], it["econds"]) and np.allclose(corpus.dconds[r], it["dconds"])
+    rows = np.array([0, 3, 5])
+    S, T = corpus.batch_shape(rows, True)
+    assert S == max(corpus.tok_len[r] + corpus.sca_len[r] + 1 for r in rows) and T == S + 2
+    with pytest.raises(Exception):
+        TokenisedCorpus(df, [], SRC, TRG, randomize_prob=0.5)
+    with pytest.raises(Exception):
+        corpus.collate(rows, "pscavaetf")          # not uploaded: no CPU path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mt", CASES)
+def test_device_batches_equal_reference_batches(mt):
+    from gct_plus_b200.Utils.dataset import DeviceDataLoader, TokenisedCorpus
+    g, df = _gold()
+    c = g["cases"][mt]
+    SRC, TRG = CO.smiles_fields(g["atoms"], c["add_sep"])
+    corpus = TokenisedCorpus(df, c["property_list"], SRC, TRG, use_scaffold=c["use_scaffold"]).to("cuda:0")
+    got = list(DeviceDataLoader(corpus, mt, c["batch_size"], c["order"]))
+    assert len(got) == len(c["batches"])
+    for a, b in zip(got, c["batches"]):
+        assert set(a) == set(b)
+        for k in b:
+            assert a[k].is_cuda and a[k].dtype == b[k].dtype and torch.equal(a[k].cpu(), b[k]), (mt, k)
+
+
+@pytest.mark.gpu
+def test_device_loader_follows_torch_samplers_and_feeds_forward_propagation():
+    """world_size 2: each rank's DistributedSampler order, big ragged corpus, batches equal the oracle's; one batch goes
+    through forward_propagation unchanged."""
+    from torch.utils.data import DistributedSampler
+    from gct_plus_b200.Utils.dataset import DataloaderPreparation, _Rows
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_collate_golden import ATOMS, synthetic_frame
+    props = ["logP", "tPSA", "QED"]
+    df = synthetic_frame(1001, seed=9)
+    SRC, TRG = CO.smiles_fields(ATOMS, True)
+    for rank in (0, 1):
+        prep = DataloaderPreparation(0, SRC, TRG, "pscavaetf", props, world_size=2, use_scaffold=True)
+        prep.rank = 0                               # one visible GPU: device index 0, sampler rank below
+        dl = prep.get_dataloader(df, 64, is_train=True)
+        dl.sampler = DistributedSampler(_Rows(len(df)), 2, rank, shuffle=True)
+        dl.sampler.set_epoch(3)
+        ref_sampler = DistributedSampler(_Rows(len(df)), 2, rank, shuffle=True)
+        ref_sampler.set_epoch(3)
+        want = list(CO.batches(df, list(ref_sampler), 64, "pscavaetf", SRC, TRG, props, True))
+        got = list(dl)
+        assert len(got) == len(want) == len(dl)
+        for a, b in zip(got, want):
+            for k in b:
+                assert torch.equal(a[k].cpu(), b[k]), k
+    from gpu_common import build_model
+    from helpers import load_golden
+    from gct_plus_b200.Model.forward_propagation1 import forward_propagation
+    fx = load_golden("pscavaetf_small")
+    m, _ = build_model(fx, "bf16")
+    m.eval()
+    batch = {k: (v % 32 if v.dtype == torch.int64 else v) for k, v in got[0].items()}
+    out = forward_propagation["pscavaetf"](m, batch, 1, False)
+    assert torch.isfinite(out[1]).all()
