@@ -12,6 +12,7 @@ int g_gct_simt_attn = 0;
 int g_gct_zattn = 1;
 int g_gct_persist = 1;
 int g_gct_tma_store = 1;
+int g_gct_ew4 = 1;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -34,6 +35,7 @@ int gct_set_attention_backend(int simt_only) { g_gct_simt_attn = simt_only; retu
 int gct_set_latent_cross_attention(int enabled) { g_gct_zattn = enabled; return GCT_OK; }
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
+int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
                  void* stream) {

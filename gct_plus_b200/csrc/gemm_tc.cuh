@@ -20,6 +20,7 @@
 
 extern int g_gct_persist;
 extern int g_gct_tma_store;
+extern int g_gct_ew4;
 
 namespace tc {
 
@@ -645,23 +646,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Warp roles (576 threads): 0 = TMA producer, 1 = MMA issuer, 2..17 = epilogue (TMEM lane quarter =
 // warp % 4, column slice = (warp - 2) / 4); warp 2 owns the TMEM allocation.
 // ------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW = 2>
 struct PersistSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;            // 8 epilogue warps x 4 KB
-    static constexpr int BAR_OFF = STAGING_OFF + 8 * 4096;
+    static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;            // 4*EW epilogue warps x 4 KB
+    static constexpr int BAR_OFF = STAGING_OFF + 4 * EW * 4096;
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;
     static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(320, 1)
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EW = 2>
+__global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, int M, int N, int K,
                        int kb_per_split, int num_splits, Epilogue epi, int use_tma_store) {
-    using L = PersistSmem<BN, STAGES>;
+    using L = PersistSmem<BN, STAGES, EW>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + L::BAR_OFF;
@@ -683,7 +684,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -755,10 +756,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
     } else {
-        // 8 epilogue warps: TMEM lane quarter q = warp % 4, column half cs = (warp - 2) / 4 owns BN/2 columns,
+        // 4*EW epilogue warps: TMEM lane quarter q = warp % 4, column slice cs = (warp - 2) / 4 owns BN/EW columns,
         // walked in 16-column chunks; results leave through the warp's 4 KB staging tile as whole row segments
         const int q = warp & 3, cs = (warp - 2) >> 2;
-        constexpr int SLICE = BN / 2;
+        constexpr int SLICE = BN / EW;
         constexpr int NCH = (SLICE + 15) / 16;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -998,11 +999,11 @@ static int sm_count() {
     return n;
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EW = 2>
 static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int split_k, const Epilogue& epi,
                           cudaStream_t st) {
-    using L = PersistSmem<BN, STAGES>;
-    auto kern = gemm_tc_persist_kernel<BN, A_MN, B_MN, STAGES>;
+    using L = PersistSmem<BN, STAGES, EW>;
+    auto kern = gemm_tc_persist_kernel<BN, A_MN, B_MN, STAGES, EW>;
     static bool attr_set = false;
     if (!attr_set) {
         GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -1027,7 +1028,7 @@ static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, i
                 GCT_TRY(get_tensor_map(epi.aux_out, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 2, 64, 32, &taux, 2));
         }
     }
-    GCT_CUDA(launch_k(kern, grid, dim3(320), (size_t)L::TOTAL, st, true, ta, tb, tc_, taux, M, N, K, kps, split_k, epi, use_tma));
+    GCT_CUDA(launch_k(kern, grid, dim3((2 + 4 * EW) * 32), (size_t)L::TOTAL, st, true, ta, tb, tc_, taux, M, N, K, kps, split_k, epi, use_tma));
     return GCT_OK;
 }
 
@@ -1062,6 +1063,15 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
 
     if (g_gct_persist && (bn_hint / 1000) == 0 && (BN == 128 || BN == 256 || BN == 64) &&
         (long long)cdiv(M, BM) * cdiv(N, BN) * split_k > sm_count()) {
+        // 16 epilogue warps (3 pipeline stages make room for their staging tiles) for the activation epilogues (GELU,
+        // GELU + saved gradient, multiply-by-aux): twice the warps hide their MUFU / dependency / load latencies behind
+        // each other ([B200] 129 -> 99 us, 136 -> 126 us, 161 -> 154 us); the plain modes keep 8 warps and 4 stages,
+        // where the deeper pipeline is worth more than the extra warps (85 vs 95 us)
+        const int emode = epi_mode(epi);
+        if (g_gct_ew4 && BN == 256 && (emode == 3 || emode == 9 || emode == 10)) {
+            if (!a_mn && !b_mn) return launch_persist<256, false, false, 3, 4>(ta, tb, M, N, K, split_k, epi, st);
+            if (!a_mn && b_mn) return launch_persist<256, false, true, 3, 4>(ta, tb, M, N, K, split_k, epi, st);
+        }
 #define GCT_TCP_CASE(bn, amn, bmn, st_) \
         if (BN == bn && a_mn == amn && b_mn == bmn) return launch_persist<bn, amn, bmn, st_>(ta, tb, M, N, K, split_k, epi, st);
         GCT_TCP_CASE(64, false, false, 8)

@@ -14,6 +14,8 @@ flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 b_mn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 dev = torch.device("cuda:0")
 lib = L.lib()
+if os.environ.get("GCT_EW4") is not None:
+    lib.gct_set_epilogue_warps16(int(os.environ["GCT_EW4"]))
 A = torch.randn(M, K, device=dev).bfloat16()
 B = (torch.randn(K, N, device=dev) if b_mn else torch.randn(N, K, device=dev)).bfloat16()
 out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
