@@ -1047,7 +1047,14 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
         const long long mt = (M + BM - 1) / BM, sp = split_k, sms = sm_count();
         if (N <= 32) BN = 32;
         else if (N <= 64) BN = 64;
-        else if (N % 256 == 0 && mt * (N / 256) * sp >= sms) BN = 256;
+        else if (N % 256 == 0 && mt * (N / 256) * sp >= sms) {
+            BN = 256;
+            // short-K projections with an fp32 residual + fp32 output are bound by their epilogue traffic, not by the MMA:
+            // narrower tiles quantise better over the SMs ([B200] M=41472, N=K=512: 63 -> 59 us)
+            const long long t256 = mt * (N / 256) * sp;
+            const double eff256 = (double)t256 / (double)(((t256 + sms - 1) / sms) * sms);
+            if (K <= 512 && epi.res32 && epi.out32 && eff256 < 0.9) BN = 128;
+        }
         else if (mt * ((N + 127) / 128) * sp >= sms) BN = 128;
         else if (mt * ((N + 63) / 64) * sp >= sms) BN = 64;
         else if (mt * ((N + 31) / 32) * sp >= 100 || a_mn || b_mn) BN = 32;
