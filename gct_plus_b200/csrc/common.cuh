@@ -152,48 +152,11 @@ __device__ __forceinline__ float gelu_fast_grad(float x) {
     float phi, e; gelu_phi_e(x, phi, e);
     return fmaf(x * e, GCT_INV_SQRT_2PI, phi);
 }
-// Packed (fp32x2: FFMA2 / FMUL2 / FADD2 issue one instruction per element PAIR on sm_100) evaluation for two
-// pre-activations at once.  m = per-element multipliers applied to both results (dropout keep * 1/(1-p), or 1):
-//   g = m * gelu(x),  dg = m * gelu'(x)
+// Packed fp32x2 evaluation (FFMA2 / FMUL2 / FADD2: one instruction per element PAIR on sm_100).  m = per-element
+// multipliers applied to both results (dropout keep * 1/(1-p), or 1):  g = m * gelu(x),  dg = m * gelu'(x).
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ void gelu_pair(float2 x, float2 m, float2& g, float2& dg) {
-    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-    const float2 den = __ffma2_rn(ax, f2(GCT_AS_P), f2(1.f));
-    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-    const float2 ea = __fmul2_rn(__fmul2_rn(x, x), f2(GCT_NEG_HALF_LOG2E));
-    const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
-    float2 p = __ffma2_rn(t, f2(GCT_AS_A5), f2(GCT_AS_A4));
-    p = __ffma2_rn(p, t, f2(GCT_AS_A3));
-    p = __ffma2_rn(p, t, f2(GCT_AS_A2));
-    p = __ffma2_rn(p, t, f2(GCT_AS_A1));
-    const float2 h = __fmul2_rn(p, __fmul2_rn(t, e));
-    float2 u = __ffma2_rn(h, f2(-1.f), f2(0.5f));
-    u.x = copysignf(u.x, x.x); u.y = copysignf(u.y, x.y);
-    const float2 phi = __fadd2_rn(u, f2(0.5f));
-    const float2 xm = __fmul2_rn(x, m);
-    g = __fmul2_rn(xm, phi);
-    dg = __ffma2_rn(__fmul2_rn(xm, e), f2(GCT_INV_SQRT_2PI), __fmul2_rn(phi, m));
-}
-// gelu only (no saved gradient)
-__device__ __forceinline__ float2 gelu_pair_fwd(float2 x, float2 m) {
-    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-    const float2 den = __ffma2_rn(ax, f2(GCT_AS_P), f2(1.f));
-    const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-    const float2 ea = __fmul2_rn(__fmul2_rn(x, x), f2(GCT_NEG_HALF_LOG2E));
-    const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
-    float2 p = __ffma2_rn(t, f2(GCT_AS_A5), f2(GCT_AS_A4));
-    p = __ffma2_rn(p, t, f2(GCT_AS_A3));
-    p = __ffma2_rn(p, t, f2(GCT_AS_A2));
-    p = __ffma2_rn(p, t, f2(GCT_AS_A1));
-    const float2 h = __fmul2_rn(p, __fmul2_rn(t, e));
-    float2 u = __ffma2_rn(h, f2(-1.f), f2(0.5f));
-    u.x = copysignf(u.x, x.x); u.y = copysignf(u.y, x.y);
-    const float2 phi = __fadd2_rn(u, f2(0.5f));
-    return __fmul2_rn(__fmul2_rn(x, m), phi);
-}
-
-// The same evaluation for NP independent pairs written stage by stage, so that the dependent FFMA2 chains of different
-// pairs interleave in the instruction stream (a lone Horner chain stalls ~4 cycles per step on its own result).
+// NP independent pairs, written stage by stage so that the dependent FFMA2 chains of different pairs can interleave in
+// the instruction stream (a lone Horner chain stalls ~4 cycles per step on its own result).
 // WITH_GRAD = false skips dg.
 template <int NP, bool WITH_GRAD>
 __device__ __forceinline__ void gelu_pairs(const float2* x, const float2* m, float2* g, float2* dg) {

@@ -442,53 +442,6 @@ __host__ __device__ inline int epi_mode(const Epilogue& e) {
     return b ? (r ? 2 : 7) : (r ? 8 : 4);
 }
 
-// Same arithmetic as epi_finish for NJ 8-column groups, but the final values are handed back (vals[8*NJ]) so that
-// the caller can stage them in shared memory and write whole 128-byte row segments.  Not used for EPI_ACCUM.
-template <typename T, int NJ>
-__device__ __forceinline__ void epi_compute(const Epilogue& e, int row, int col, const float* acc, const EpiOperandsT<NJ>& o,
-                                            float* vals) {
-    const size_t idx = (size_t)row * e.ldc + col;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        f8 v;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v.v[k] = acc[8 * j + k] * e.alpha;
-        if (e.bias) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] += o.b[j].v[k];
-        }
-        if (e.flags & EPI_GELU) {
-            if (e.flags & EPI_GELU_GRAD) {
-                f8 dg;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) dg.v[k] = drop_mult(e.drop, idx + 8 * j + k) * gelu_fast_grad(v.v[k]);
-                st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, dg);
-            } else if (e.aux_out) st8(reinterpret_cast<T*>(e.aux_out) + idx + 8 * j, v);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] = gelu_fast(v.v[k]);
-        }
-        if (e.drop.thresh) {
-            const uint32_t pair0 = (uint32_t)((idx + 8 * j) >> 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) drop_pair(e.drop, pair0 + k, v.v[2 * k], v.v[2 * k + 1]);
-        }
-        if (e.flags & EPI_DGELU) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] *= gelu_fast_grad(o.h[j].v[k]);
-        }
-        if (e.flags & EPI_MUL_AUX) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] *= o.h[j].v[k];
-        }
-        if (e.res32) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v.v[k] += o.r[j].v[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) vals[8 * j + k] = v.v[k];
-    }
-}
-
 // Warp-private staging tile: 32 rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7).
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk16) { return (uint32_t)(row * 128 + ((chunk16 ^ (row & 7)) << 4)); }
 
