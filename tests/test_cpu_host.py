@@ -127,3 +127,22 @@ def test_batch_detokeniser_matches_id_to_smi(built):
         outs[5] = np.where(outs[5] == 3, 0, outs[5])          # a row that never emits <eos>
         assert s.ids_to_smiles(outs) == [s.id_to_smi(r) for r in outs]
     assert s.ids_to_smiles(np.zeros((0, 7), dtype=np.int64)) == []
+
+
+def test_dropout_hash_statistics():
+    """NumPy mirror of common.cuh's dropout decision (x = seed + pair*0x9e3779b9; x ^= x >> 15; x *= 0x2c1b3c6d; the two
+    16-bit halves against thresh >> 16): keep rate, cross-half, lag-1 and row-stride correlations stay inside 4.5 sigma."""
+    import numpy as np
+    n, p = 1 << 21, 0.1
+    t16 = int(min(4294967295.0, p * 4294967296.0)) >> 16
+    for seed in (12345, 0x9E3779B9, 7):
+        x = (seed + np.arange(n, dtype=np.uint64) * 0x9E3779B9) & 0xFFFFFFFF
+        x ^= x >> 15
+        x = (x * 0x2C1B3C6D) & 0xFFFFFFFF
+        lo, hi = (x & 0xFFFF) < t16, (x >> 16) < t16
+        sig = np.sqrt(p * (1 - p) / n)
+        for d in (lo, hi):
+            assert abs(d.mean() - t16 / 65536) < 4.5 * sig
+        c = lambda a, b: abs(np.corrcoef(a.astype(float), b.astype(float))[0, 1]) * np.sqrt(n)   # noqa: E731
+        assert c(lo, hi) < 4.5 and c(lo[:-1], lo[1:]) < 4.5 and c(hi[:-1], hi[1:]) < 4.5
+        assert c(lo[:-256], lo[256:]) < 4.5 and c(hi[:-1024], hi[1024:]) < 4.5 and c(lo[:-1], hi[1:]) < 4.5
