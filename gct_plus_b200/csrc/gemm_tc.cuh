@@ -1006,7 +1006,7 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
             // narrower tiles quantise better over the SMs ([B200] M=41472, N=K=512: 63 -> 59 us)
             const long long t256 = mt * (N / 256) * sp;
             const double eff256 = (double)t256 / (double)(((t256 + sms - 1) / sms) * sms);
-            if (K <= 512 && epi.res32 && epi.out32 && eff256 < 0.9) BN = 128;
+            if (K <= 1024 && epi.res32 && epi.out32 && eff256 < 0.9) BN = 128;
         }
         else if (mt * ((N + 127) / 128) * sp >= sms) BN = 128;
         else if (mt * ((N + 63) / 64) * sp >= sms) BN = 64;
