@@ -10,6 +10,7 @@ int g_gct_pdl = 1;
 int g_da_cfg = 0;
 int g_gct_simt_attn = 0;
 int g_gct_zattn = 1;
+int g_gct_ffn_classic = 0;
 int g_gct_persist = 1;
 int g_gct_tma_store = 1;
 int g_gct_ew4 = 1;
@@ -33,6 +34,7 @@ int gct_set_pdl(int enabled) { g_gct_pdl = enabled; return GCT_OK; }
 int gct_set_decode_attn_config(int cfg) { g_da_cfg = cfg; return GCT_OK; }
 int gct_set_attention_backend(int simt_only) { g_gct_simt_attn = simt_only; return GCT_OK; }
 int gct_set_latent_cross_attention(int enabled) { g_gct_zattn = enabled; return GCT_OK; }
+int gct_set_ffn_saved_activation(int preact) { g_gct_ffn_classic = preact; return GCT_OK; }
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }

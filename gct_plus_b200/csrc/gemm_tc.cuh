@@ -326,13 +326,20 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
             v[2 * i] = r.x; v[2 * i + 1] = r.y;
         }
     }
-    if constexpr (ACT == 2) {
-        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(h2);
+    if constexpr (ACT == 2) {       // v *= gelu'(pre) (the dropout multiplier was applied above), packed evaluation
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(h2);
+        float2 x[8], one[8], g[8], dg[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float2 hf = __bfloat1622float2(hp[i]);
-            v[2 * i] *= gelu_fast_grad(hf.x);
-            v[2 * i + 1] *= gelu_fast_grad(hf.y);
+            x[i] = make_float2(__uint_as_float(hw[i] << 16), __uint_as_float(hw[i] & 0xffff0000u));
+            one[i] = make_float2(1.f, 1.f);
+        }
+        gelu_pairs<4, true>(x, one, g, dg);
+        gelu_pairs<4, true>(x + 4, one + 4, g + 4, dg + 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 r = __fmul2_rn(make_float2(v[2 * i], v[2 * i + 1]), dg[i]);
+            v[2 * i] = r.x; v[2 * i + 1] = r.y;
         }
     }
     if constexpr (HAS_RES) {
@@ -1028,7 +1035,7 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
         // each other ([B200] 129 -> 99 us, 136 -> 126 us, 161 -> 154 us); the plain modes keep 8 warps and 4 stages,
         // where the deeper pipeline is worth more than the extra warps (85 vs 95 us)
         const int emode = epi_mode(epi);
-        if (g_gct_ew4 && BN == 256 && (emode == 3 || emode == 9 || emode == 10)) {
+        if (g_gct_ew4 && BN == 256 && (emode == 3 || emode == 6 || emode == 9 || emode == 10)) {
             if (!a_mn && !b_mn) return launch_persist<256, false, false, 3, 4>(ta, tb, M, N, K, split_k, epi, st);
             if (!a_mn && b_mn) return launch_persist<256, false, true, 3, 4>(ta, tb, M, N, K, split_k, epi, st);
         }

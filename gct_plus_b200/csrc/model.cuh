@@ -14,6 +14,7 @@
 extern int g_gct_simt_only;
 extern int g_gct_simt_attn;
 extern int g_gct_zattn;
+extern int g_gct_ffn_classic;
 
 template <typename T>
 static int attn_fwd_dispatch(const AttnParams& p, cudaStream_t st) {
@@ -326,7 +327,7 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
             GCT_TRY(m.norm_fwd(a.x1, m.enc_slot(l, E_N2A), m.enc_slot(l, E_N2B), a.a2, a.a2_32, Me));
             {   // g = drop(gelu(a2 W1^T + b1))
                 Epilogue e = Model<T>::epi(m.P(m.enc_slot(l, E_F1_B)), dff);
-                e.flags = EPI_GELU | EPI_GELU_GRAD; e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + ES_FF);
+                e.flags = g_gct_ffn_classic ? EPI_GELU : (EPI_GELU | EPI_GELU_GRAD); e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + ES_FF);
                 GCT_TRY(m.gemm(a.a2, false, d, m.WT(m.enc_slot(l, E_F1_W)), false, d, Me, dff, d, e));
             }
             {   // xout = a2 + drop(g W2^T + b2)
@@ -406,7 +407,7 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
         GCT_TRY(m.norm_fwd(a.y2, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), a.a3, nullptr, Md));
         {
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff);
-            e.flags = EPI_GELU | EPI_GELU_GRAD; e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + DS_FF);
+            e.flags = g_gct_ffn_classic ? EPI_GELU : (EPI_GELU | EPI_GELU_GRAD); e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + DS_FF);
             GCT_TRY(m.gemm(a.a3, false, d, m.WT(m.dec_slot(l, D_F1_W)), false, d, Md, dff, d, e));
         }
         {
@@ -462,9 +463,10 @@ static int ffn_backward(Model<T>& m, BwdScratch<T>& S, int M, const float* dout,
     if (!dyT_ready) GCT_TRY(m.cast_drop(dout, S.dyT, M, d, drop_out, m.G(f2b)));
     GCT_TRY(m.wgrad(S.dyT, d, g, dff, M, d, dff, f2w, f2b, false));
     {   // dHpre = (dY W2) * [keepF * gelu'(pre)]  -- the bracket was saved by the forward epilogue (EPI_GELU_GRAD)
-        (void)drop_ff;
         Epilogue e = Model<T>::epi(nullptr, dff);
-        e.flags = EPI_MUL_AUX; e.aux_in = hpre; e.outT = S.dhT;
+        e.aux_in = hpre; e.outT = S.dhT;
+        if (g_gct_ffn_classic) { e.flags = EPI_DGELU; e.drop = drop_ff; }      // hpre = pre-activation: regenerate mask, gelu'
+        else e.flags = EPI_MUL_AUX;                                             // hpre = keepF * gelu'(pre)
         GCT_TRY(m.gemm(S.dyT, false, d, m.WT(f2w), true, dff, M, dff, d, e));
     }
     GCT_TRY(m.wgrad(S.dhT, dff, a, d, M, dff, d, f1w, f1b, true));

@@ -84,6 +84,8 @@ int gct_num_slots(int n_layers);
 int gct_set_gemm_backend(int simt_only);            /* test hook: 1 routes bf16 GEMMs through the SIMT kernel */
 int gct_set_persistent_gemm(int enabled);          /* persistent, TMEM double-buffered GEMM for > 148 tiles (default on) */
 int gct_set_attention_backend(int simt_only);       /* test hook: 1 keeps bf16 attention on the SIMT kernel */
+int gct_set_ffn_saved_activation(int preact);        /* training FFN: 0 (default) save keep*gelu'(pre) in the forward, 1 save the
+                                                       pre-activation and evaluate gelu' + the mask in the backward epilogue */
 int gct_set_latent_cross_attention(int enabled);    /* bf16 decode: 1 (default) evaluates cross-attention in latent space when the
                                                        memory has no condition rows, 0 keeps the per-layer K/V form */
 int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring stages*10 + rows per CTA (0 = default) */

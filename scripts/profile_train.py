@@ -11,6 +11,9 @@ from gct_plus_b200.Model import Cvaetf  # noqa: E402
 from gct_plus_b200.Train.trainer1 import FusedTrainer  # noqa: E402
 
 dev = torch.device("cuda:0")
+if os.environ.get("GCT_FFN_PREACT") is not None:
+    import gct_plus_b200._lib as L
+    L.lib().gct_set_ffn_saved_activation(int(os.environ["GCT_FFN_PREACT"]))
 torch.manual_seed(0)
 B = int(os.environ.get("GCT_PROFILE_B", "512"))
 model = Cvaetf(32, 32, dropout=0.1, nconds=3, use_cond2lat=True, compute_dtype="bf16", **bench.ARCH).to(dev).train()

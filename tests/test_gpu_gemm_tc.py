@@ -54,6 +54,8 @@ def test_gelu_grad_and_mul_aux_small(dtype):
     aux_in = torch.randn(M, N, device=DEV).to(outT.dtype)
     _, out2, _ = gemm(A_, B_, M, N, K, flags=256, want_T=True, aux_in=aux_in, dtype=dtype)
     _close(out2, ref * aux_in.float(), tol)
+    _, out3, _ = gemm(A_, B_, M, N, K, flags=2, want_T=True, aux_in=aux_in, dtype=dtype)
+    _close(out3, ref * _gelu_grad(aux_in.float()), tol)
 
 
 def test_small_vocab_tile():
@@ -84,7 +86,7 @@ def test_split_k_accumulate():
 
 
 @pytest.mark.parametrize("N,K", [(512, 512), (1536, 512), (256, 512), (2048, 128), (384, 192)])
-@pytest.mark.parametrize("mode", ["bias_T", "bias_res_F32", "gelu", "gelu_grad", "mul_aux", "plain_F32", "plain_T", "bias_F32", "res_F32"])
+@pytest.mark.parametrize("mode", ["bias_T", "bias_res_F32", "gelu", "gelu_grad", "mul_aux", "dgelu", "plain_F32", "plain_T", "bias_F32", "res_F32"])
 def test_persistent_kernel_epilogue_modes(N, K, mode):
     """More tiles than SMs -> persistent kernel with the specialised, smem-staged epilogue; every mode the model uses."""
     M = 19 * 1024 + 128          # 153 full row tiles (+ a partial-tile run below)
@@ -110,6 +112,10 @@ def test_persistent_kernel_epilogue_modes(N, K, mode):
             aux_in = torch.randn(Mx, N, device=DEV).bfloat16()
             _, outT, _ = gemm(As, Bs, Mx, N, K, flags=256, want_T=True, aux_in=aux_in)
             _close(outT, ref * aux_in.float(), 1e-2)
+        elif mode == "dgelu":           # EPI_DGELU: out = acc * gelu'(aux_in)   (pre-activation form of the FFN backward)
+            aux_in = torch.randn(Mx, N, device=DEV).bfloat16()
+            _, outT, _ = gemm(As, Bs, Mx, N, K, flags=2, want_T=True, aux_in=aux_in)
+            _close(outT, ref * _gelu_grad(aux_in.float()), 1e-2)
         elif mode == "plain_F32":
             out, _, _ = gemm(As, Bs, Mx, N, K)
             _close(out, ref)

@@ -141,6 +141,17 @@ def test_fused_trainer_three_steps_vs_reference(dtype):
             assert rel_err(sd[k], full) < 2e-4, k
 
 
+def test_backward_in_the_preactivation_form_of_the_ffn():
+    """gct_set_ffn_saved_activation(1): the forward saves the FFN pre-activation and the backward epilogue evaluates
+    gelu' (EPI_DGELU) instead of multiplying by the saved keep*gelu' -- same gradients as the default form."""
+    import gct_plus_b200._lib as L
+    try:
+        L.lib().gct_set_ffn_saved_activation(1)
+        test_backward_matches_reference_golden("pvaetf_full", "bf16")
+    finally:
+        L.lib().gct_set_ffn_saved_activation(0)
+
+
 def test_dropout_is_statistically_right_and_backward_consistent():
     """Train mode: the dropout mask is regenerated in backward from (seed, site, index).  Check the keep rate
     through the PE dropout (the only one directly observable) and that two forwards with the same seed agree."""
