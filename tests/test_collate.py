@@ -123,3 +123,40 @@ def test_device_loader_follows_torch_samplers_and_feeds_forward_propagation():
     batch = {k: (v % 32 if v.dtype == torch.int64 else v) for k, v in got[0].items()}
     out = forward_propagation["pscavaetf"](m, batch, 1, False)
     assert torch.isfinite(out[1]).all()
+
+
+@pytest.mark.gpu
+def test_reference_epoch_loop_on_the_device_loader(tmp_path):
+    """train1.py-style run: DataloaderPreparation -> train_model (reference epoch loop, torch Adam through the autograd
+    bridge, per-epoch CSVs + checkpoint) for two epochs on the device-assembled batches; the checkpoint reloads."""
+    import argparse
+    from gct_plus_b200.Model.build_model import get_model, load_state
+    from gct_plus_b200.Train.trainer1 import train_model
+    from gct_plus_b200.Utils.dataset import DataloaderPreparation
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_collate_golden import ATOMS, synthetic_frame
+    props = ["logP", "tPSA", "QED"]
+    SRC, TRG = CO.smiles_fields(ATOMS, True)
+    df = synthetic_frame(96, seed=21)
+    args = argparse.Namespace(N=2, d_model=128, d_ff=256, H=2, latent_dim=32, dropout=0.1, use_cond2dec=False, use_cond2lat=True,
+                              variational=True, property_list=props, get_attn=False, model_type="pscavaetf", pad_id=1,
+                              lr_scheduler="WarmUpDefault", lr_WarmUpSteps=50, start_epoch=1, num_epoch=2, use_KLA=True,
+                              KLA_ini_beta=0.02, KLA_inc_beta=0.02, KLA_max_beta=1.0, KLA_beg_epoch=1,
+                              model_folder=str(tmp_path))
+    torch.manual_seed(0)
+    model = get_model(args, len(SRC.vocab), len(TRG.vocab), 0).to("cuda:0")       # train1.py:108 does model.to(rank)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-9)
+    prep = DataloaderPreparation(0, SRC, TRG, "pscavaetf", props, world_size=1, use_scaffold=True)
+    train_loader = prep.get_dataloader(df, 32, is_train=True)
+    valid_loader = prep.get_dataloader(df.iloc[:40].reset_index(drop=True), 32, is_train=False)
+    train_model(args, model, opt, train_loader, valid_loader, 0, 1, None)
+    t1 = pd.read_csv(tmp_path / "train_1.csv")
+    t2 = pd.read_csv(tmp_path / "train_2.csv")
+    assert len(t1) == len(train_loader) == 3 and np.isfinite(t1["LOSS"]).all() and np.isfinite(t2["LOSS"]).all()
+    assert t2["RCE"].mean() < t1["RCE"].mean()                 # it learns
+    assert os.path.exists(tmp_path / "valid_2.csv")
+    fresh = get_model(args, len(SRC.vocab), len(TRG.vocab), 0).to("cuda:0")
+    ck = torch.load(tmp_path / "model_2.pt", weights_only=False)
+    fresh.load_state_dict(ck["model_state_dict"])
+    for (k, a), (_, b) in zip(model.state_dict().items(), fresh.state_dict().items()):
+        assert torch.equal(a, b), k
