@@ -144,3 +144,27 @@ def test_bf16_cross_attention_forms_follow_the_oracle(latent_form):
             assert float((hist - prob).abs().max()) < 0.08, (latent_form, lens[gi])
     finally:
         L.lib().gct_set_latent_cross_attention(1)
+
+
+@pytest.mark.parametrize("name", ["vaetf_full", "pscavaetf_small"])
+def test_pipelined_sample_smiles_equals_single_pass(name):
+    """Requests of >= pipeline_rows rows decode as two overlapped halves; with greedy decoding and supplied latents the
+    strings must equal the single-pass result row for row (odd row count -> unequal halves)."""
+    fx = load_golden(name)
+    n = 11
+    g = torch.Generator().manual_seed(3)
+    res = []
+    for rows in (4, 10 ** 9):
+        s, _ = _sampler(fx, "fp32", max_strlen=12, pipeline_rows=rows)
+        np.random.seed(1)
+        if fx["model_type"] == "vaetf":
+            zs = torch.randn(n, 9, fx["arch"]["latent_dim"], generator=torch.Generator().manual_seed(3)).pin_memory()
+            res.append(s.sample_smiles(n, zs=zs, toklen=[9, 5, 7, 9, 3, 8, 9, 6, 4, 9, 2]))
+        else:
+            sm = fx["sample"]
+            dconds = np.tile(np.asarray(sm["dconds"])[:1], (n, 1)) + np.arange(n)[:, None] * 0.1
+            sca_len = len(FakeField().tokenize(sm["scaffold"]))
+            zs = torch.randn(n, sca_len + 1 + 6, fx["arch"]["latent_dim"], generator=torch.Generator().manual_seed(3))
+            res.append(s.sample_smiles(dconds, sm["scaffold"], zs=zs, toklen=[6, 3, 5, 6, 2, 6, 4, 6, 1, 5, 6]))
+    assert list(res[0][0]) == list(res[1][0])
+    assert list(res[0][2]) == list(res[1][2])
