@@ -34,10 +34,11 @@ ARCH = dict(N=6, d_model=512, dff=2048, h=8, latent_dim=128)
 VOCAB = 32
 MAX_STRLEN = 100
 BATCH = 512
-# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attn launch (ncu --set full, B=4096, 49 cached keys,
-# profiles/r01_decode_attn_b4096_t49_ncu_details.txt) next to the algorithmic bytes of that same launch
-NCU_TRAFFIC = {"dram_bytes_per_launch": 439313920, "algorithmic_bytes_same_launch": 436207616, "shape": "B=4096, 49 cached keys + 1 new",
-               "source": "profiles/r01_decode_attn_b4096_t49_ncu_details.txt"}
+# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attn launch (ncu --set full, B=8192 = the rows per launch of the
+# roofline leg, 49 cached keys, profiles/r01_decode_attn_b8192_t49_ncu_details.txt: 848.2 MB read + 26.7 MB written in 153.9 us)
+# next to the algorithmic bytes of that same launch
+NCU_TRAFFIC = {"dram_bytes_per_launch": 874883584, "algorithmic_bytes_same_launch": 872415232, "shape": "B=8192, 49 cached keys + 1 new",
+               "source": "profiles/r01_decode_attn_b8192_t49_ncu_details.txt"}
 ITOS = ["<unk>", "<pad>", "<sos>", "<eos>", "<sep>"] + list("CcNnOoSsFIBrl()[]=#123456+-H@/")[:27]
 
 
