@@ -58,6 +58,7 @@ _PROTOS = {
     "gct_set_pdl": (C.c_int, [C.c_int]),
     "gct_set_tma_store": (C.c_int, [C.c_int]),
     "gct_set_epilogue_warps16": (C.c_int, [C.c_int]),
+    "gct_set_cta_pair_gemm": (C.c_int, [C.c_int]),
     "gct_set_decode_attn_config": (C.c_int, [C.c_int]),
     "gct_set_attention_backend": (C.c_int, [C.c_int]),
     "gct_set_latent_cross_attention": (C.c_int, [C.c_int]),

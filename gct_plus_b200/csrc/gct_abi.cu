@@ -14,6 +14,7 @@ int g_gct_ffn_classic = 0;
 int g_gct_persist = 1;
 int g_gct_tma_store = 1;
 int g_gct_ew4 = 1;
+int g_gct_pair = 1;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -38,6 +39,7 @@ int gct_set_ffn_saved_activation(int preact) { g_gct_ffn_classic = preact; retur
 int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_OK; }
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
+int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
                  void* stream) {

@@ -21,6 +21,7 @@
 extern int g_gct_persist;
 extern int g_gct_tma_store;
 extern int g_gct_ew4;
+extern int g_gct_pair;
 
 namespace tc {
 
@@ -76,6 +77,47 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster each hold their own 128 rows of A and half of B's rows;
+// the leader (cluster rank 0) issues one M = 256 MMA per k-step, completion is multicast to the barriers of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose transaction bytes are credited to a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 // shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -606,10 +648,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Warp roles (576 threads): 0 = TMA producer, 1 = MMA issuer, 2..17 = epilogue (TMEM lane quarter =
 // warp % 4, column slice = (warp - 2) / 4); warp 2 owns the TMEM allocation.
 // ------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int EW = 2>
+template <int BN, int STAGES, int EW = 2, int CG = 1>
 struct PersistSmem {
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = (BN / CG) * BK * 2;            // CTA pair: each CTA stages half of B's rows
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;            // 4*EW epilogue warps x 4 KB
     static constexpr int BAR_OFF = STAGING_OFF + 4 * EW * 4096;
@@ -617,12 +659,17 @@ struct PersistSmem {
     static constexpr int TMEM_COLS = (2 * BN <= 64) ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES, int EW = 2>
+// CG = 2: launched as clusters of two CTAs (a CTA pair on one TPC).  One work item is a 256 x BN output tile: each CTA
+// loads its own 128 rows of A and BN/2 rows of B (32 KB per k-block instead of 48 KB: these short-K GEMMs are bound by
+// the L2 -> shared-memory operand fill), the leader issues tcgen05.mma.cta_group::2 (M = 256), each CTA drains its own
+// 128 x BN accumulator.  K-major operands only.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EW = 2, int CG = 1>
 __global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, int M, int N, int K,
                        int kb_per_split, int num_splits, Epilogue epi, int use_tma_store) {
-    using L = PersistSmem<BN, STAGES, EW>;
+    using L = PersistSmem<BN, STAGES, EW, CG>;
+    static_assert(CG == 1 || (!A_MN && !B_MN), "the CTA-pair variant covers K-major operands");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + L::BAR_OFF;
@@ -635,26 +682,39 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (K + BK - 1) / BK;
-    const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+    constexpr int BMT = BM * CG;                                  // rows of one work item (pair: 256)
+    const int m_tiles = (M + BMT - 1) / BMT, n_tiles = (N + BN - 1) / BN;
     const int total = m_tiles * n_tiles * num_splits;
+    const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;    // 0 = leader
+    const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
+    const int m_rank_off = (int)crank * BM;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EW); }
+        // pair: the leader's full barrier collects one arrive.expect_tx per CTA, its accumulator-empty barrier the epilogue
+        // warps of both CTAs
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EW * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"((uint32_t)L::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)L::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                         "r"((uint32_t)L::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     pdl_wait();
@@ -664,38 +724,46 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BM, z = tile / (n_tiles * m_tiles);
+            for (int tile = tile0; tile < total; tile += tile_step) {
+                const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BMT + m_rank_off, z = tile / (n_tiles * m_tiles);
                 const int kb_begin = z * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(empty_bar(s), phase ^ 1u);
-                    mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
                     const uint32_t sa = base + s * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-                    if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+                    if constexpr (CG == 2) {
+                        // this CTA's rows of A and its half of B's rows; bytes credited to the leader's full barrier
+                        const uint32_t lead_full = mapa_u32(full_bar(s), 0);
+                        mbar_expect_tx_cluster(lead_full, L::STAGE_BYTES);
+                        tma_load_2d_pair(sa, &tmA, kb * BK, m0, lead_full);
+                        tma_load_2d_pair(sb, &tmB, kb * BK, n0 + (int)crank * (BN / 2), lead_full);
                     } else {
+                        mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
+                        if constexpr (!A_MN) {
+                            tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, kb * BK, full_bar(s));
-                    }
-                    if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));
-                    } else {
+                            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, kb * BK, full_bar(s));
+                        }
+                        if constexpr (!B_MN) {
+                            tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(s));
+                            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(s));
+                        }
                     }
                     if (++s == STAGES) { s = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+        if (lane == 0 && crank == 0) {                    // pair: only the leader issues MMAs
+            constexpr uint32_t idesc = make_idesc(BMT, BN, A_MN, B_MN);
             int s = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int tile = tile0; tile < total; tile += tile_step) {
                 const int z = tile / (n_tiles * m_tiles);
                 const int kb_begin = z * kb_per_split, kb_end = min(num_kb, kb_begin + kb_per_split);
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue has drained this accumulator
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);       // epilogue (of both CTAs) has drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -706,12 +774,13 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
                         const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-                        umma_bf16(tacc, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        if constexpr (CG == 2) umma_bf16_pair(tacc, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        else umma_bf16(tacc, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(s));
+                    if constexpr (CG == 2) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
                     if (++s == STAGES) { s = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));
+                if constexpr (CG == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -725,8 +794,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint32_t acc_phase = 0;
         const bool atomic = num_splits > 1;
         const int mode = epi_mode(epi);
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BM, z = tile / (n_tiles * m_tiles);
+        for (int tile = tile0; tile < total; tile += tile_step) {
+            const int n0 = (tile % n_tiles) * BN, m0 = ((tile / n_tiles) % m_tiles) * BMT + m_rank_off, z = tile / (n_tiles * m_tiles);
             Epilogue e = epi;
             if (z != 0) e.bias = nullptr;
             const int row = ((e.flags & 32) ? 0 : m0) + q * 32 + lane;      // flag 32: measurement hook, every tile writes rows [0,128)
@@ -858,16 +927,21 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(acc)) : "memory");
+                if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));      // the leader's MMA warp waits on it
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(acc)) : "memory");
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();            // no CTA leaves (or frees TMEM) while its peer may still signal it
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
-                     : "memory");
+        if constexpr (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -992,6 +1066,49 @@ static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     return GCT_OK;
 }
 
+// CTA-pair launch (K-major operands): clusters of two CTAs, B tensor map with a BN/2-row box.
+template <int BN, int STAGES, int EW>
+static int launch_persist_pair(const CUtensorMap& ta, const bf16* B, long long ldb, int M, int N, int K, const Epilogue& epi,
+                               cudaStream_t st) {
+    using L = PersistSmem<BN, STAGES, EW, 2>;
+    auto kern = gemm_tc_persist_kernel<BN, false, false, STAGES, EW, 2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    CUtensorMap tb;
+    GCT_TRY(get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)(BN / 2), &tb));
+    const int num_kb = (K + BK - 1) / BK;
+    const long long total = (long long)cdiv(M, 2 * BM) * cdiv(N, BN);
+    long long ctas = 2 * total < (long long)(sm_count() & ~1) ? 2 * total : (long long)(sm_count() & ~1);
+    CUtensorMap tc_ = ta, taux = ta;
+    int use_tma = 0;
+    if (g_gct_tma_store && epi_mode(epi) != 0) {
+        const bool f32 = epi.out32 != nullptr;
+        const void* cptr = f32 ? (const void*)epi.out32 : (const void*)epi.outT;
+        const int esz = f32 ? 4 : 2;
+        if ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0 && ((size_t)epi.ldc * esz) % 16 == 0) {
+            GCT_TRY(get_tensor_map(cptr, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * esz, 128 / esz, 32, &tc_, esz));
+            use_tma = 1;
+            if ((epi.flags & EPI_GELU) && epi.aux_out)
+                GCT_TRY(get_tensor_map(epi.aux_out, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 2, 64, 32, &taux, 2));
+        }
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3((2 + 4 * EW) * 32); cfg.dynamicSmemBytes = (size_t)L::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_gct_pdl ? 2 : 1;
+    GCT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc_, taux, M, N, K, num_kb, 1, epi, use_tma));
+    return GCT_OK;
+}
+
 // A: K-major -> storage [M rows, K cols] with pitch lda; MN-major -> storage [K rows, M cols] with pitch lda.
 // B: K-major -> storage [N rows, K cols] with pitch ldb; MN-major -> storage [K rows, N cols] with pitch ldb.
 static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B, bool b_mn, long long ldb, int M, int N,
@@ -1034,6 +1151,9 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
         // GELU + saved gradient, multiply-by-aux): twice the warps hide their MUFU / dependency / load latencies behind
         // each other ([B200] 129 -> 99 us, 136 -> 126 us, 161 -> 154 us); the plain modes keep 8 warps and 4 stages,
         // where the deeper pipeline is worth more than the extra warps (85 vs 95 us)
+        // CTA pairs for the K-major (forward / decode) GEMMs with enough 256-row work items
+        if (g_gct_pair && BN == 256 && !a_mn && !b_mn && split_k == 1 && (long long)cdiv(M, 2 * BM) * cdiv(N, 256) * 2 > sm_count())
+            return launch_persist_pair<256, 6, 2>(ta, B, ldb, M, N, K, epi, st);
         const int emode = epi_mode(epi);
         if (g_gct_ew4 && BN == 256 && (emode == 3 || emode == 6 || emode == 9 || emode == 10)) {
             if (!a_mn && !b_mn) return launch_persist<256, false, false, 3, 4>(ta, tb, M, N, K, split_k, epi, st);

@@ -16,6 +16,8 @@ b_mn = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 res = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 dev = torch.device("cuda:0")
 lib = L.lib()
+if os.environ.get("GCT_PAIR") is not None:
+    lib.gct_set_cta_pair_gemm(int(os.environ["GCT_PAIR"]))
 if os.environ.get("GCT_EW4") is not None:
     lib.gct_set_epilogue_warps16(int(os.environ["GCT_EW4"]))
 A = torch.randn(M, K, device=dev).bfloat16()
