@@ -14,7 +14,7 @@ int g_gct_ffn_classic = 0;
 int g_gct_persist = 1;
 int g_gct_tma_store = 1;
 int g_gct_ew4 = 1;
-int g_gct_pair = 1;
+int g_gct_pair = 2;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 

@@ -662,14 +662,13 @@ struct PersistSmem {
 // CG = 2: launched as clusters of two CTAs (a CTA pair on one TPC).  One work item is a 256 x BN output tile: each CTA
 // loads its own 128 rows of A and BN/2 rows of B (32 KB per k-block instead of 48 KB: these short-K GEMMs are bound by
 // the L2 -> shared-memory operand fill), the leader issues tcgen05.mma.cta_group::2 (M = 256), each CTA drains its own
-// 128 x BN accumulator.  K-major operands only.
+// 128 x BN accumulator.
 template <int BN, bool A_MN, bool B_MN, int STAGES, int EW = 2, int CG = 1>
 __global__ void __launch_bounds__((2 + 4 * EW) * 32, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, int M, int N, int K,
                        int kb_per_split, int num_splits, Epilogue epi, int use_tma_store) {
     using L = PersistSmem<BN, STAGES, EW, CG>;
-    static_assert(CG == 1 || (!A_MN && !B_MN), "the CTA-pair variant covers K-major operands");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + L::BAR_OFF;
@@ -734,8 +733,19 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         // this CTA's rows of A and its half of B's rows; bytes credited to the leader's full barrier
                         const uint32_t lead_full = mapa_u32(full_bar(s), 0);
                         mbar_expect_tx_cluster(lead_full, L::STAGE_BYTES);
-                        tma_load_2d_pair(sa, &tmA, kb * BK, m0, lead_full);
-                        tma_load_2d_pair(sb, &tmB, kb * BK, n0 + (int)crank * (BN / 2), lead_full);
+                        if constexpr (!A_MN) {
+                            tma_load_2d_pair(sa, &tmA, kb * BK, m0, lead_full);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, &tmA, m0 + c * 64, kb * BK, lead_full);
+                        }
+                        const int nh = n0 + (int)crank * (BN / 2);
+                        if constexpr (!B_MN) {
+                            tma_load_2d_pair(sb, &tmB, kb * BK, nh, lead_full);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < BN / 2 / 64; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, nh + c * 64, kb * BK, lead_full);
+                        }
                     } else {
                         mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
                         if constexpr (!A_MN) {
@@ -1066,21 +1076,24 @@ static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, i
     return GCT_OK;
 }
 
-// CTA-pair launch (K-major operands): clusters of two CTAs, B tensor map with a BN/2-row box.
-template <int BN, int STAGES, int EW>
-static int launch_persist_pair(const CUtensorMap& ta, const bf16* B, long long ldb, int M, int N, int K, const Epilogue& epi,
-                               cudaStream_t st) {
+// CTA-pair launch: clusters of two CTAs; a K-major B needs its own tensor map with a BN/2-row box (MN-major operands are
+// fetched in 64-column boxes either way).
+template <int BN, bool A_MN, bool B_MN, int STAGES, int EW>
+static int launch_persist_pair(const CUtensorMap& ta, const CUtensorMap& tb_mn, const bf16* B, long long ldb, int M, int N, int K,
+                               int split_k, const Epilogue& epi, cudaStream_t st) {
     using L = PersistSmem<BN, STAGES, EW, 2>;
-    auto kern = gemm_tc_persist_kernel<BN, false, false, STAGES, EW, 2>;
+    auto kern = gemm_tc_persist_kernel<BN, A_MN, B_MN, STAGES, EW, 2>;
     static bool attr_set = false;
     if (!attr_set) {
         GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    CUtensorMap tb;
-    GCT_TRY(get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)(BN / 2), &tb));
+    CUtensorMap tb = tb_mn;
+    if (!B_MN) GCT_TRY(get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)(BN / 2), &tb));
     const int num_kb = (K + BK - 1) / BK;
-    const long long total = (long long)cdiv(M, 2 * BM) * cdiv(N, BN);
+    int kps = (num_kb + split_k - 1) / split_k;
+    split_k = (num_kb + kps - 1) / kps;
+    const long long total = (long long)cdiv(M, 2 * BM) * cdiv(N, BN) * split_k;
     long long ctas = 2 * total < (long long)(sm_count() & ~1) ? 2 * total : (long long)(sm_count() & ~1);
     CUtensorMap tc_ = ta, taux = ta;
     int use_tma = 0;
@@ -1105,7 +1118,7 @@ static int launch_persist_pair(const CUtensorMap& ta, const bf16* B, long long l
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_gct_pdl ? 2 : 1;
-    GCT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc_, taux, M, N, K, num_kb, 1, epi, use_tma));
+    GCT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc_, taux, M, N, K, kps, split_k, epi, use_tma));
     return GCT_OK;
 }
 
@@ -1152,8 +1165,11 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
         // each other ([B200] 129 -> 99 us, 136 -> 126 us, 161 -> 154 us); the plain modes keep 8 warps and 4 stages,
         // where the deeper pipeline is worth more than the extra warps (85 vs 95 us)
         // CTA pairs for the K-major (forward / decode) GEMMs with enough 256-row work items
-        if (g_gct_pair && BN == 256 && !a_mn && !b_mn && split_k == 1 && (long long)cdiv(M, 2 * BM) * cdiv(N, 256) * 2 > sm_count())
-            return launch_persist_pair<256, 6, 2>(ta, B, ldb, M, N, K, epi, st);
+        if (g_gct_pair && BN == 256 && (long long)cdiv(M, 2 * BM) * cdiv(N, 256) * split_k * 2 > sm_count()) {
+            if (!a_mn && !b_mn) return launch_persist_pair<256, false, false, 6, 2>(ta, tb, B, ldb, M, N, K, split_k, epi, st);
+            if (g_gct_pair > 1 && !a_mn && b_mn) return launch_persist_pair<256, false, true, 6, 2>(ta, tb, B, ldb, M, N, K, split_k, epi, st);
+            if (g_gct_pair > 1 && a_mn && b_mn) return launch_persist_pair<256, true, true, 6, 2>(ta, tb, B, ldb, M, N, K, split_k, epi, st);
+        }
         const int emode = epi_mode(epi);
         if (g_gct_ew4 && BN == 256 && (emode == 3 || emode == 6 || emode == 9 || emode == 10)) {
             if (!a_mn && !b_mn) return launch_persist<256, false, false, 3, 4>(ta, tb, M, N, K, split_k, epi, st);

@@ -90,7 +90,8 @@ int gct_set_latent_cross_attention(int enabled);    /* bf16 decode: 1 (default) 
                                                        memory has no condition rows, 0 keeps the per-layer K/V form */
 int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring stages*10 + rows per CTA (0 = default) */
 int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue (default on) */
-int gct_set_cta_pair_gemm(int enabled);             /* persistent GEMM, K-major operands: tcgen05.mma.cta_group::2 over CTA pairs */
+int gct_set_cta_pair_gemm(int level);               /* persistent GEMM over CTA pairs (tcgen05.mma.cta_group::2): 0 off, 1 K-major
+                                                       operands only, 2 (default) also dgrad / wgrad operand layouts */
 int gct_set_epilogue_warps16(int enabled);          /* persistent GEMM: 16 (default) or 8 epilogue warps for the specialised modes */
 int gct_set_pdl(int enabled);                       /* programmatic dependent launch on the decode path (default on) */
 
