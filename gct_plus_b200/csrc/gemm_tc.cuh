@@ -1165,7 +1165,9 @@ static int launch_gemm_tc(const bf16* A, bool a_mn, long long lda, const bf16* B
         // each other ([B200] 129 -> 99 us, 136 -> 126 us, 161 -> 154 us); the plain modes keep 8 warps and 4 stages,
         // where the deeper pipeline is worth more than the extra warps (85 vs 95 us)
         // CTA pairs for the K-major (forward / decode) GEMMs with enough 256-row work items
-        if (g_gct_pair && BN == 256 && (long long)cdiv(M, 2 * BM) * cdiv(N, 256) * split_k * 2 > sm_count()) {
+        // (the plain-GELU epilogue of the decode FFN keeps the single-CTA kernel with 16 epilogue warps: 99 vs 129 us at M = 30000)
+        if (g_gct_pair && BN == 256 && (long long)cdiv(M, 2 * BM) * cdiv(N, 256) * split_k * 2 > sm_count() &&
+            !(g_gct_ew4 && epi_mode(epi) == 3)) {
             if (!a_mn && !b_mn) return launch_persist_pair<256, false, false, 6, 2>(ta, tb, B, ldb, M, N, K, split_k, epi, st);
             if (g_gct_pair > 1 && !a_mn && b_mn) return launch_persist_pair<256, false, true, 6, 2>(ta, tb, B, ldb, M, N, K, split_k, epi, st);
             if (g_gct_pair > 1 && a_mn && b_mn) return launch_persist_pair<256, true, true, 6, 2>(ta, tb, B, ldb, M, N, K, split_k, epi, st);
