@@ -523,7 +523,7 @@ def main():
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                             "traffic": NCU_TRAFFIC,
+                             "traffic": NCU_TRAFFIC["dram_bytes_per_launch"], "traffic_detail": NCU_TRAFFIC,
                              "peak_source": peak_src, "launches_timed": nl, "us_per_launch": ms_per_launch * 1e3,
                              "rows_per_launch": roof_rows,
                              "whole_decode": {"algorithmic_bytes_per_batch": total_alg,
