@@ -289,7 +289,7 @@ class Sampling:
         outs = outs.to(torch.int16).cpu().numpy()          # ids < 2^15: a quarter of the int64 device->host bytes
         t0 = time.perf_counter()
         smiles = self.ids_to_smiles(outs[:, strip:])
-        toklen_gen = [len(self.TRG.tokenize(smi)) for smi in smiles]
+        toklen_gen = list(map(len, map(self.TRG.tokenize, smiles)))
         self._host_s_per_row = (time.perf_counter() - t0) / max(1, len(smiles))
         return smiles, toklen_gen
 
@@ -310,7 +310,7 @@ class Sampling:
             sl = self.host.numpy()[self.i:self.i + self.rows_per, self.strip:]
             s = self.o.ids_to_smiles(sl)
             self.smiles += s
-            self.toklen += [len(self.o.TRG.tokenize(x)) for x in s]
+            self.toklen += list(map(len, map(self.o.TRG.tokenize, s)))
             self.i += self.rows_per
 
         def finish(self):
