@@ -249,7 +249,11 @@ static int launch_decode_attn(const DecAttnParams& p, int B, cudaStream_t st) {
             case 1622: return launch_decode_attn_cfg<T, 16, 2, 2>(p, B, st);
             case 431: return launch_decode_attn_cfg<T, 4, 3, 1>(p, B, st);
             case 441: return launch_decode_attn_cfg<T, 4, 4, 1>(p, B, st);
-            default: return launch_decode_attn_cfg<T, 8, 3, 1>(p, B, st);     // 48 KB ring -> 4 CTAs/SM: best of the sweep
+            default:
+                // 48 KB ring -> 4 CTAs/SM: best of the sweep up to ~65 cached keys; longer rows stream better in 16-key chunks
+                // with a 2-stage ring ([B200] B=30000, 90 keys: 6.86 vs 6.57 TB/s; 49 keys: 6.01 vs 6.28)
+                if (p.n_cached >= 68) return launch_decode_attn_cfg<T, 16, 2, 1>(p, B, st);
+                return launch_decode_attn_cfg<T, 8, 3, 1>(p, B, st);
         }
     }
 }

@@ -11,7 +11,7 @@ import gct_plus_b200._lib as L  # noqa: E402
 dev = torch.device("cuda:0")
 lib = L.lib()
 d, H, Lmax, NL = 512, 8, 100, 6
-for B in (512, 4096):
+for B in ([int(x) for x in sys.argv[1:]] or [512, 4096]):
     kc = torch.randn(NL, B, Lmax, d, device=dev).bfloat16()
     vc = torch.randn(NL, B, Lmax, d, device=dev).bfloat16()
     qkv = torch.randn(B, 3 * d, device=dev).bfloat16()
