@@ -262,3 +262,43 @@ class FusedTrainer:
     def read_losses(self):
         loss, rce, _, kld = self.out4.tolist()
         return loss, rce, kld
+
+    # ------------------------------------------------------------------ checkpoint compatibility
+    def state_dict(self):
+        """The optimiser state in torch.optim.Adam's state_dict layout (parameter order = model.parameters(), as in the
+        reference's Adam(model.parameters(), ...), train1.py:116-119), so `save_checkpoint(args, model, trainer, path)`
+        writes the same 'opt_state_dict' a reference run would and reference tooling can load it."""
+        m = self.model
+        state = {}
+        if self.step_count > 0:
+            for i, p in enumerate(m._param_list):
+                off, n, shape = m._grad_views[id(p)]
+                state[i] = {'step': torch.tensor(float(self.step_count)),
+                            'exp_avg': self.exp_avg[off:off + n].view(shape).clone(),
+                            'exp_avg_sq': self.exp_avg_sq[off:off + n].view(shape).clone()}
+        group = {'lr': float(self.lr), 'betas': tuple(self.betas), 'eps': float(self.eps), 'weight_decay': 0, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'params': list(range(len(m._param_list)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd):
+        """Resumes from an Adam state_dict (this class's or torch.optim.Adam's / the reference's 'opt_state_dict')."""
+        m = self.model
+        group = sd['param_groups'][0]
+        if len(group['params']) != len(m._param_list):
+            raise L.GctError("optimizer state has %d parameters, the model %d" % (len(group['params']), len(m._param_list)))
+        self.lr, self.betas, self.eps = float(group['lr']), tuple(group['betas']), float(group['eps'])
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, p in enumerate(m._param_list):
+            st = sd['state'].get(i, sd['state'].get(str(i)))
+            if st is None:
+                continue
+            off, n, _ = m._grad_views[id(p)]
+            self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise L.GctError("per-parameter Adam step counts differ: %s" % sorted(steps))
+        self.step_count = steps.pop() if steps else 0

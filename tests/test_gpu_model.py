@@ -214,3 +214,44 @@ def test_full_size_properties_cfg1_shape():
     ys = trg[:, 1:].reshape(-1)
     loss, rce, _, kld = loss_function(1.0, None, outs["fp32"][0], None, ys, outs["fp32"][1], outs["fp32"][2], False, 1)
     assert torch.isfinite(loss) and float(rce) > 0 and float(kld) > 0
+
+
+def test_fused_trainer_checkpoint_round_trip(tmp_path):
+    """FusedTrainer.state_dict() is a torch.optim.Adam state_dict: save_checkpoint writes the reference's checkpoint layout,
+    torch.optim.Adam loads it, and a FusedTrainer resumed from it continues like the uninterrupted run."""
+    import argparse
+    from gct_plus_b200.Train.trainer1 import save_checkpoint
+    fx = load_golden("pvaetf_plain_small")
+    batch = _to_dev(fx["batch"])
+    eps = eps_for(fx).to(DEV)
+
+    def fresh():
+        m, _ = build_model(fx, "fp32", dropout=0.0)
+        m.train()
+        return m, FusedTrainer(m, fx["model_type"], pad_id=1, lr=1e-3, warmup=50)
+
+    m1, t1 = fresh()
+    for _ in range(2):
+        t1.step(batch, 0.3, eps_noise=eps)
+    a = fx["arch"]
+    args = argparse.Namespace(N=a["N"], d_model=a["d_model"], d_ff=a["dff"], H=a["h"], latent_dim=a["latent_dim"], dropout=0.0,
+                              use_cond2dec=False, use_cond2lat=fx.get("use_cond2lat", False), variational=True,
+                              property_list=["a"] * fx["nconds"])
+    path = tmp_path / "model_1.pt"
+    save_checkpoint(args, m1, t1, path)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"model_state_dict", "opt_state_dict", "model_params"}
+    adam = torch.optim.Adam(m1.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-9)
+    adam.load_state_dict(ck["opt_state_dict"])                   # torch accepts the layout
+    p0 = next(iter(m1.parameters()))
+    assert float(adam.state[p0]["step"]) == 2.0 and adam.param_groups[0]["lr"] == pytest.approx(t1.lr)
+    m2, t2 = fresh()
+    m2.load_state_dict(ck["model_state_dict"])
+    t2.load_state_dict(ck["opt_state_dict"])
+    t1.step(batch, 0.3, eps_noise=eps)
+    t2.step(batch, 0.3, eps_noise=eps)
+    assert t2.step_count == 3
+    for (k, x), (_, y) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        if k.endswith("k_linear.bias"):
+            continue          # mathematically zero gradient: rounding noise normalised by Adam (see test_fused_trainer...)
+        assert rel_err(x, y) < 1e-4, k
