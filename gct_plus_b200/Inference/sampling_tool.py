@@ -53,6 +53,7 @@ class Sampling:
         # detokenisation overlap the other half's decode.  None = decide from the measured host cost per row: worth it with a
         # regex tokeniser in TRG.tokenize (~10 us / row), not with a trivial one ([B200], 30k rows: 40.2k vs 41.6k SMILES/s)
         self.pipeline_rows = kwargs.get('pipeline_rows', None)
+        self.z_on_device = kwargs.get('z_on_device', False)
         self._host_s_per_row = 0.0
         self._side_stream = None
         self._graphs = {}
@@ -139,6 +140,11 @@ class Sampling:
         return p if self.SRC.batch_first else p.T
 
     def sample_z(self, toklen, n):
+        """z ~ N(0, 1), drawn on the HOST like the reference (Inference/sampling_tool.py:93-97) so that a seeded run draws
+        the same latents.  `z_on_device=True` (sampler kwarg, not in the reference) draws them with the CUDA generator
+        instead: for 30 000 x 55 x 128 latents the host draw + copy costs more than the whole decode."""
+        if self.z_on_device:
+            return torch.randn((n, toklen, self.latent_dim), device=self.device)
         return torch.normal(mean=0, std=1, size=(n, toklen, self.latent_dim))
 
     def transform(self, prop):
