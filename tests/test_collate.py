@@ -160,3 +160,28 @@ def test_reference_epoch_loop_on_the_device_loader(tmp_path):
     fresh.load_state_dict(ck["model_state_dict"])
     for (k, a), (_, b) in zip(model.state_dict().items(), fresh.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+def test_device_loader_order_equals_torch_dataloader():
+    """Host logic only (collate stubbed): the row order and batch boundaries are those of torch's DataLoader with the same
+    sampler -- RandomSampler under a seed, DistributedSampler per rank and epoch -- including the ragged last batch."""
+    from torch.utils.data import DataLoader, DistributedSampler, RandomSampler
+    from gct_plus_b200.Utils.dataset import DeviceDataLoader, _Rows
+
+    class _Corpus:
+        def collate(self, rows, model_type):
+            return list(map(int, rows))
+
+    n, bs = 103, 16
+    for make in (lambda: RandomSampler(_Rows(n)),
+                 lambda: DistributedSampler(_Rows(n), 2, 1, shuffle=True),
+                 lambda: DistributedSampler(_Rows(n), 4, 3, shuffle=False)):
+        s1, s2 = make(), make()
+        for s in (s1, s2):
+            if hasattr(s, "set_epoch"):
+                s.set_epoch(5)
+        torch.manual_seed(123)
+        got = list(DeviceDataLoader(_Corpus(), "vaetf", bs, s1))
+        torch.manual_seed(123)
+        want = [b.tolist() for b in DataLoader(list(range(n)), batch_size=bs, sampler=s2, drop_last=False)]
+        assert got == want and len(DeviceDataLoader(_Corpus(), "vaetf", bs, s1)) == len(want)
