@@ -151,6 +151,10 @@ class DeviceDataLoader:
         return (len(self.sampler) + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
+        # torch's DataLoader iterator draws its worker base seed from the global generator before the sampler draws its
+        # permutation seed (torch/utils/data/dataloader.py, _BaseDataLoaderIter.__init__, same in the reference's torch 1.10):
+        # consume the same number so that a seeded run visits the rows in the reference's order
+        torch.empty((), dtype=torch.int64).random_()
         order = np.fromiter(iter(self.sampler), dtype=np.int64)
         for i in range(0, len(order), self.batch_size):
             yield self.corpus.collate(order[i:i + self.batch_size], self.model_type)
