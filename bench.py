@@ -342,9 +342,22 @@ def run_input_pipeline(dev, batch=512, nrows=20000, iters=50):
         df[f"src_{p_}"] = rng.randn(nrows).astype(np.float32)
         df[f"trg_{p_}"] = rng.randn(nrows).astype(np.float32)
     df = pd.DataFrame(df)
-    SRC, TRG = CO.smiles_fields(atoms, True)
+    import re
+    rx = re.compile(r"(\[[^\]]+]|Br?|Cl?|N|O|S|P|F|I|b|c|n|o|s|p|\(|\)|\.|=|#|-|\+|\\|\/|:|~|@|\?|>|\*|\$|\%[0-9]{2}|[0-9])")
+
+    class _RxField(_Field):                  # the device leg's own duck-typed fields (regex of Utils/field.py:16)
+        def __init__(self, itos):
+            self.vocab = _Vocab()
+            self.vocab.itos = list(itos)
+            self.vocab.stoi = {t: i for i, t in enumerate(self.vocab.itos)}
+
+        def tokenize(self, smi):
+            return rx.findall(smi)
+
+    src_itos = ["<unk>", "<pad>", "<sep>"] + atoms
+    trg_itos = ["<unk>", "<pad>", "<sos>", "<eos>", "<sep>"] + atoms
     t0 = time.perf_counter()
-    corpus = TokenisedCorpus(df, props, SRC, TRG, use_scaffold=True).to(dev)
+    corpus = TokenisedCorpus(df, props, _RxField(src_itos), _RxField(trg_itos), use_scaffold=True).to(dev)
     t_tok = time.perf_counter() - t0
     order = torch.randperm(nrows, generator=torch.Generator().manual_seed(0)).numpy()
     dl = DeviceDataLoader(corpus, "pscavaetf", batch, order)
@@ -363,6 +376,9 @@ def run_input_pipeline(dev, batch=512, nrows=20000, iters=50):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / nb
+    # CPU leg: the oracle port with its own (torchtext-like) fields over the same vocabulary
+    SRC, TRG = CO.smiles_fields(atoms, True)
+    assert SRC.vocab.itos == src_itos and TRG.vocab.itos == trg_itos
     t0 = time.perf_counter()
     ncpu = 0
     for _ in CO.batches(df, order[:3 * batch], batch, "pscavaetf", SRC, TRG, props, True):

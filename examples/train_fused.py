@@ -40,7 +40,7 @@ class _Field:                      # duck-typed like torchtext's Field (only wha
     def __init__(self, itos):
         import re
         self.vocab = _Vocab(itos)
-        self._re = re.compile(r"(\[[^\]]+]|Br?|Cl?|N|O|S|P|F|I|b|c|n|o|s|p|\(|\)|\.|=|#|-|\+|\\\\|\/|:|~|@|\?|>|\*|\$|\%[0-9]{2}|[0-9])")
+        self._re = re.compile(r"(\[[^\]]+]|Br?|Cl?|N|O|S|P|F|I|b|c|n|o|s|p|\(|\)|\.|=|#|-|\+|\\|\/|:|~|@|\?|>|\*|\$|\%[0-9]{2}|[0-9])")
 
     def tokenize(self, s):
         return self._re.findall(s)

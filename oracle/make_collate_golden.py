@@ -42,7 +42,15 @@ def main():
     spec.loader.exec_module(ref)
     props = ["logP", "tPSA", "QED"]
     df = synthetic_frame(37, seed=3)
-    out = {"frame": df.to_dict(orient="list"), "atoms": ATOMS, "props": props, "cases": {}}
+    # the tokeniser regex exactly as the reference's source spells it (Utils/field.py:16; the module itself imports torchtext)
+    import ast
+    import re
+    import warnings
+    line = [l for l in open(os.path.join(REF, "Utils", "field.py")) if "generaral_pattern" in l and "=" in l][0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pattern = ast.literal_eval(re.search(r'=\s*(".*")\s*$', line.strip()).group(1))
+    out = {"frame": df.to_dict(orient="list"), "atoms": ATOMS, "props": props, "cases": {}, "tokenizer_pattern": pattern}
     for model_type, add_sep, use_sca, plist in (("vaetf", False, False, []), ("pvaetf", False, False, props),
                                                 ("scavaetf", True, True, []), ("pscavaetf", True, True, props)):
         SRC, TRG = CO.smiles_fields(ATOMS, add_sep)

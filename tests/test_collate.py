@@ -27,6 +27,12 @@ def test_tokeniser_regex():
     tks = CO.MolTokenizer(add_sep=True)
     assert tks("c1ccccc1<sep>CCO") == ["c", "1", "c", "c", "c", "c", "c", "1", "<sep>", "C", "C", "O"]
     assert tks("CCO") == ["C", "C", "O"]
+    assert tk("F/C=C\\F") == ["F", "/", "C", "=", "C", "\\", "F"]          # one literal backslash (Utils/field.py:16 is a non-raw string)
+    # the reference's literal (a NON-raw string: its "\\\\" is the two-character regex for one backslash)
+    ref = (r"(\[[^\]]+]|Br?|Cl?|N|O|S|P|F|I|b|c|n|o|s|p|\(|\)|\.|=|#|-|\+|" + "\\\\" +
+           r"|\/|:|~|@|\?|>|\*|\$|\%[0-9]{2}|[0-9])")
+    assert CO._PATTERN == ref
+    assert CO._PATTERN == _gold()[0]["tokenizer_pattern"]          # recorded from the reference's source by make_collate_golden.py
 
 
 def test_field_process_pads_to_the_longest_row():
