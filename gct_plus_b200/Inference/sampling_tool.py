@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import time
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -56,8 +57,11 @@ class Sampling:
         self.z_on_device = kwargs.get('z_on_device', False)
         self._host_s_per_row = 0.0
         self._side_stream = None
-        self._graphs = {}
-        self._static = {}
+        # static decode buffers / captured CUDA graphs per request shape: small LRUs (each entry pins O(n * Lz * latent)
+        # floats of HBM and a graph per chunk), graphs of a superseded workspace are dropped
+        self.cache_shapes = kwargs.get('cache_shapes', 4)
+        self._graphs = OrderedDict()
+        self._static = OrderedDict()
         self._itos = np.array(self.TRG.vocab.itos, dtype=object)
         model.pad_id = self.pad_id
         self.last_decode_steps = 0
@@ -222,6 +226,12 @@ class Sampling:
                       dconds=torch.zeros((n, max(nc, 1)), device=dev, dtype=torch.float32),
                       status_host=torch.zeros(2, dtype=torch.int32).pin_memory())
             self._static[key] = st
+            while len(self._static) > self.cache_shapes:
+                old, _ = self._static.popitem(last=False)
+                for gk in [gk for gk in self._graphs if gk[:len(old)] == old]:
+                    del self._graphs[gk]
+        else:
+            self._static.move_to_end(key)
         st['zs'][:, :Lz].copy_(zs, non_blocking=True)
         if Lzp > Lz:
             st['zs'][:, Lz:].zero_()
@@ -254,6 +264,8 @@ class Sampling:
 
         chunks = [(s, min(steps, s + self.sync_every)) for s in range(0, steps, self.sync_every)]
         gkey = key + (ws.data_ptr(), w.params_f32, w.params_bf16, self.sync_every)
+        for gk in [gk for gk in self._graphs if gk[len(key)] != ws.data_ptr()]:
+            del self._graphs[gk]                # the grow-only workspace was reallocated: those graphs point at freed memory
         graphs = self._graphs.get(gkey) if self.use_cuda_graph else None
         if self.use_cuda_graph and graphs is None and st.get('warm'):
             # second call with this shape: capture begin + every chunk once, replay from now on

@@ -22,10 +22,13 @@ def extract_params(args, src_vocab_len, trg_vocab_len):
     }
 
 
-def load_state(model, model_path, rank):
+def load_state(model, model_path, rank, allow_pickle=False):
     """Accepts {'model_state_dict': ...} checkpoints or a bare state_dict, with or without DDP's
-    'module.' prefix (reference build_model.py:59-76)."""
-    ckpt = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
+    'module.' prefix (reference build_model.py:59-76).  Checkpoints written by save_checkpoint hold tensors and plain
+    containers only, so they load with weights_only=True; `allow_pickle=True` (or GCT_B200_ALLOW_PICKLE=1) opts in to
+    full unpickling for legacy files from a trusted source."""
+    allow_pickle = allow_pickle or os.environ.get('GCT_B200_ALLOW_PICKLE') == '1'
+    ckpt = torch.load(model_path, map_location=torch.device('cpu'), weights_only=not allow_pickle)
     model_state = ckpt['model_state_dict'] if isinstance(ckpt, dict) and 'model_state_dict' in ckpt else ckpt
     if list(model_state.keys())[0].split('.')[0] == 'module':
         model_state = OrderedDict((k[7:], v) for k, v in model_state.items())

@@ -50,7 +50,7 @@ class TransformerVAE(nn.Module):
         assert self.compute_dtype in ("fp32", "bf16")
         self._flat = None
         self._shadow = None
-        self._shadow_version = -1
+        self._shadow_fresh = False
         self._ws = _Workspace()
         self._graph_ws = []
         self.pad_id = 1            # <pad> of the torchtext vocab; set by get_model / samplers
@@ -131,7 +131,7 @@ class TransformerVAE(nn.Module):
                 cur = (cur + p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         device = next(self.parameters()).device
         flat = torch.zeros(cur, dtype=torch.float32, device=device)
-        self._grad_views = {}
+        views = {}
         for t, off, mod, name, is_buf in plan:
             if t.dtype != torch.float32:
                 raise L.GctError("gct_plus_b200 keeps fp32 master parameters; use compute_dtype for bf16 math")
@@ -141,12 +141,14 @@ class TransformerVAE(nn.Module):
                 mod._buffers[name] = view
             else:
                 t.data = view
-                self._grad_views[id(t)] = (off, t.numel(), tuple(t.shape))
+                views[id(t)] = (off, t.numel(), tuple(t.shape))
         self._flat = flat
         self._offsets = offsets
         self._shadow = None
-        self._shadow_version = -1
+        self._shadow_fresh = False
         self._param_list = list(self.parameters())
+        # (offset, numel, shape) per parameter, in model.parameters() order (index-keyed: survives deepcopy / pickling)
+        self._grad_views = [views[id(p)] for p in self._param_list]
 
     def _apply(self, fn, recurse=True):
         super()._apply(fn, recurse)
@@ -169,25 +171,56 @@ class TransformerVAE(nn.Module):
                            dtype=L.DTYPE_BF16 if self.compute_dtype == "bf16" else L.DTYPE_F32, pad_id=int(self.pad_id),
                            dropout=float(e.pe.dropout.p if dropout is None else dropout))
 
-    def _versions(self) -> int:
-        return sum(p._version for p in self._param_list)
+    def _aliased(self) -> bool:
+        """True while every parameter still lives at its slot of the flat buffer (``p.data = other`` breaks that)."""
+        base = self._flat.data_ptr()
+        return all(p.data_ptr() == base + 4 * off for p, (off, _, _) in zip(self._param_list, self._grad_views))
 
-    def _weights(self, grads=None) -> L.GctWeights:
+    def sync_weights(self):
+        """Re-establishes the kernel view of the parameters after out-of-band edits: re-flattens if a parameter was
+        re-pointed (``p.data = t``, deepcopy, unpickling) and re-casts the bf16 operand copy.  Called automatically
+        before every kernel call; public so that callers can force it (e.g. after writing into ``model._flat``)."""
+        if len(self._param_list) != len(self._grad_views) or not self._aliased():
+            self._flatten()
+        self._shadow_fresh = False
+        return self
+
+    def _weights(self, grads=None, trust_shadow=False) -> L.GctWeights:
+        """Pointer struct for the library.  The bf16 operand copy is re-cast from the fp32 masters on every call (44 M
+        elements, ~50 us) -- autograd version counters miss writes through ``.data`` -- unless `trust_shadow`: the
+        fused trainer's Adam kernel writes master and shadow in the same pass and vouches for it."""
         if not self._flat.is_cuda:
             raise L.GctError("model parameters are on the CPU: move the model to a CUDA device (no CPU path)")
+        if not self._aliased():
+            self._flatten()
         shadow = None
         if self.compute_dtype == "bf16":
-            v = self._versions()
-            if self._shadow is None or self._shadow_version != v:
-                if self._shadow is None:
+            if self._shadow is None or not (trust_shadow and self._shadow_fresh):
+                if self._shadow is None or self._shadow.device != self._flat.device:
                     self._shadow = torch.empty(self._flat.numel(), dtype=torch.bfloat16, device=self._flat.device)
                 L.check(L.lib().gct_cast_f32_to_bf16(L.ptr(self._flat), L.ptr(self._shadow), self._flat.numel(),
                                                     L.stream_ptr()), "gct_cast_f32_to_bf16")
-                self._shadow_version = v
+            self._shadow_fresh = bool(trust_shadow)
             shadow = self._shadow
         return L.GctWeights(params_f32=self._flat.data_ptr(), params_bf16=shadow.data_ptr() if shadow is not None else None,
                             grads_f32=grads.data_ptr() if grads is not None else None,
                             slot_offsets_host=self._offsets.ctypes.data)
+
+    # ------------------------------------------------------------------ copy / pickle
+    _TRANSIENT = ("_flat", "_shadow", "_ws", "_graph_ws", "_param_list", "_grad_views", "_offsets")
+
+    def __getstate__(self):
+        """deepcopy / torch.save(model): the flat buffer, shadow and scratch are rebuilt on the other side."""
+        state = self.__dict__.copy()
+        for k in self._TRANSIENT:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._shadow, self._shadow_fresh = None, False
+        self._ws, self._graph_ws = _Workspace(), []
+        self._flatten()
 
     # ------------------------------------------------------------------ forward / backward
     def _run(self, src, trg, src_mask, trg_mask, econds, dconds, *, run_encoder=True, run_decoder=True, z_in=None,
@@ -277,8 +310,7 @@ class TransformerVAE(nn.Module):
 
     def grad_views(self, grads_flat):
         out = []
-        for p in self._param_list:
-            off, n, shape = self._grad_views[id(p)]
+        for off, n, shape in self._grad_views:
             out.append(grads_flat[off:off + n].view(shape))
         return out
 

@@ -178,7 +178,14 @@ class FusedTrainer:
                  use_cond2dec=False, process_group=None):
         self.model, self.model_type, self.pad_id = model, model_type, pad_id
         self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
-        self.use_cond2dec = use_cond2dec
+        if use_cond2dec or (getattr(model, 'use_cond2dec', False) and int(model.nconds) > 0):
+            # the reference loss adds MSE(prop_fc(logits[:, :nconds])) and pairs targets with logits[:, nconds:]
+            # (trainer1.py:24-26, cvaetf.py:184-186); the fused step has no property head -> refuse instead of
+            # training on a wrong loss.  run_epoch / loss_function (autograd path) cover use_cond2dec.
+            raise L.GctError("FusedTrainer does not implement the use_cond2dec property head (prop_fc + MSE); "
+                             "train use_cond2dec models through run_epoch / loss_function")
+        self.use_cond2dec = False
+        self.variational = model._variational()
         self.pg = process_group
         self.world = world_info(process_group)[1]
         flat = model._flat
@@ -222,17 +229,21 @@ class FusedTrainer:
         st = L.stream_ptr()
         L.check(lib.gct_src_mask(L.ptr(src), B, S, nc, self.pad_id, L.ptr(bf['sm']), st), "gct_src_mask")
         L.check(lib.gct_trg_mask(L.ptr(trg_in), B, T, nc if cfg.use_cond2dec else 0, self.pad_id, L.ptr(bf['tm']), st), "gct_trg_mask")
-        if eps_noise is None:
-            bf['eps'].normal_()
+        if not self.variational:
+            eps_ptr = None                      # z = mu (Sampler / Encoder.sampling with variational=False)
         else:
-            bf['eps'].copy_(eps_noise)
+            if eps_noise is None:
+                bf['eps'].normal_()
+            else:
+                bf['eps'].copy_(eps_noise)
+            eps_ptr = bf['eps'].data_ptr()
         if m._step_seed is None:
             m._step_seed = torch.initial_seed() & 0xFFFFFFFF
         m._step_seed = (m._step_seed * 1664525 + 1013904223) & 0xFFFFFFFF
-        w = m._weights(self.grads)
+        w = m._weights(self.grads, trust_shadow=True)
         io = L.GctIO(src=src.data_ptr(), trg=trg_in.data_ptr(), src_mask=bf['sm'].data_ptr(), trg_mask=bf['tm'].data_ptr(),
                      econds=econds.data_ptr() if econds is not None else None,
-                     dconds=dconds.data_ptr() if dconds is not None else None, eps=bf['eps'].data_ptr(), z_in=None,
+                     dconds=dconds.data_ptr() if dconds is not None else None, eps=eps_ptr, z_in=None,
                      B=B, S=S, T=T, train=int(train), seed=m._step_seed, run_encoder=1, run_decoder=1,
                      logits=bf['logits'].data_ptr(), mu=bf['mu'].data_ptr(), log_var=bf['lv'].data_ptr(), z=bf['z'].data_ptr(),
                      enc_attn=None, dec_attn1=None, dec_attn2=None)
@@ -254,8 +265,7 @@ class FusedTrainer:
         L.check(lib.gct_adam_step(L.ptr(m._flat), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
                                   L.ptr(shadow), m._flat.numel(), self.step_count, float(self.lr), self.betas[0], self.betas[1],
                                   self.eps, gscale, st), "gct_adam_step")
-        if shadow is not None:
-            m._shadow_version = m._versions()
+        m._shadow_fresh = shadow is not None       # Adam wrote master and shadow in the same pass
         self.lr = noam_lr(self.step_count, cfg.d_model, self.warmup)       # takes effect on the next step
         return self.out4
 
@@ -271,8 +281,7 @@ class FusedTrainer:
         m = self.model
         state = {}
         if self.step_count > 0:
-            for i, p in enumerate(m._param_list):
-                off, n, shape = m._grad_views[id(p)]
+            for i, (off, n, shape) in enumerate(m._grad_views):
                 state[i] = {'step': torch.tensor(float(self.step_count)),
                             'exp_avg': self.exp_avg[off:off + n].view(shape).clone(),
                             'exp_avg_sq': self.exp_avg_sq[off:off + n].view(shape).clone()}
@@ -295,7 +304,7 @@ class FusedTrainer:
             st = sd['state'].get(i, sd['state'].get(str(i)))
             if st is None:
                 continue
-            off, n, _ = m._grad_views[id(p)]
+            off, n, _ = m._grad_views[i]
             self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1))
             self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
             steps.add(int(float(st['step'])))

@@ -23,7 +23,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-           "-shared", "-DGCT_SM_TARGET=100", "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+           "-shared", "-DGCT_SM_TARGET=100", "-split-compile=0", "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

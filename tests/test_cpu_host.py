@@ -146,3 +146,47 @@ def test_dropout_hash_statistics():
         c = lambda a, b: abs(np.corrcoef(a.astype(float), b.astype(float))[0, 1]) * np.sqrt(n)   # noqa: E731
         assert c(lo, hi) < 4.5 and c(lo[:-1], lo[1:]) < 4.5 and c(hi[:-1], hi[1:]) < 4.5
         assert c(lo[:-256], lo[256:]) < 4.5 and c(hi[:-1024], hi[1024:]) < 4.5 and c(lo[:-1], hi[1:]) < 4.5
+
+
+def test_flat_storage_survives_deepcopy_pickle_and_data_reassignment(tmp_path):
+    """The kernels read one flat buffer; parameters must keep aliasing it after copy.deepcopy, torch.save(model) /
+    torch.load and ``p.data = other`` (sync_weights re-flattens), and gradient views are keyed by parameter index."""
+    import copy
+    from gct_plus_b200.Model import Cvaetf
+    torch.manual_seed(1)
+    a = Cvaetf(32, 32, nconds=3, use_cond2lat=True, dropout=0.1, **ARCH_SMALL)
+    assert a._aliased()
+    b = copy.deepcopy(a)
+    assert b._flat.data_ptr() != a._flat.data_ptr() and b._aliased()
+    assert torch.equal(b._flat, a._flat)
+    assert len(b._grad_views) == len(list(b.parameters()))
+    with torch.no_grad():
+        b.out.weight.mul_(2.0)
+    off = b._grad_views[[n for n, _ in b.named_parameters()].index("out.weight")][0]
+    assert torch.equal(b._flat[off:off + b.out.weight.numel()].view_as(b.out.weight), b.out.weight)   # write lands in _flat
+    assert not torch.equal(a.out.weight, b.out.weight)                                               # ... and only in the copy's
+    path = str(tmp_path / "whole_model.pt")
+    torch.save(a, path)
+    c = torch.load(path, weights_only=False)
+    assert c._aliased() and torch.equal(c._flat, a._flat)
+    # out-of-band re-pointing of a parameter: detected, repaired, new values reach the flat buffer
+    a.out.bias.data = torch.full_like(a.out.bias, 3.0)
+    assert not a._aliased()
+    a.sync_weights()
+    assert a._aliased()
+    offb = a._grad_views[[n for n, _ in a.named_parameters()].index("out.bias")][0]
+    assert float(a._flat[offb]) == 3.0
+    # a load_state_dict into the deep copy changes what the kernels would read
+    b.load_state_dict(a.state_dict())
+    assert torch.equal(b._flat, a._flat)
+
+
+def test_fused_trainer_rejects_the_property_head():
+    """use_cond2dec adds prop_fc + an MSE term and shifts the target rows (trainer1.py:24-26); the fused step does not
+    implement it and must refuse rather than train on a wrong loss."""
+    from gct_plus_b200._lib import GctError
+    from gct_plus_b200.Model import Cvaetf
+    from gct_plus_b200.Train.trainer1 import FusedTrainer
+    m = Cvaetf(32, 32, nconds=3, use_cond2dec=True, dropout=0.1, **ARCH_SMALL)
+    with pytest.raises(GctError):
+        FusedTrainer(m, "pvaetf")

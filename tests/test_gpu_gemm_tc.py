@@ -128,3 +128,59 @@ def test_persistent_kernel_epilogue_modes(N, K, mode):
         else:
             out, _, _ = gemm(As, Bs, Mx, N, K, res=res)
             _close(out, ref + res)
+
+
+@pytest.fixture
+def _pair_switch():
+    import gct_plus_b200._lib as L
+    yield L.lib().gct_set_cta_pair_gemm
+    L.lib().gct_set_cta_pair_gemm(2)
+
+
+@pytest.mark.parametrize("pair", [2, 0])
+@pytest.mark.parametrize("M,N,K", [(19584, 512, 512), (19584 - 40, 1536, 512), (41472, 2048, 512), (30000, 512, 2048)])
+def test_cta_pair_kmajor_at_training_shapes(_pair_switch, pair, M, N, K):
+    """CTA-pair (tcgen05.mma.cta_group::2) persistent GEMM at the cfg 3 / cfg 4 row counts against torch fp32 on the same
+    bf16 operands; pair=0 runs the single-CTA persistent kernel on the same inputs."""
+    _pair_switch(pair)
+    As, Bs, ref = _ops(M, N, K, False, False, seed=5)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    _, outT, _ = gemm(As, Bs, M, N, K, bias=bias, want_T=True)
+    _close(outT, ref + bias, 1e-2)
+    out, _, _ = gemm(As, Bs, M, N, K, bias=bias, res=res)
+    _close(out, ref + bias + res)
+    _, g, aux = gemm(As, Bs, M, N, K, bias=bias, flags=1 | 128, want_T=True)
+    _close(g, torch.nn.functional.gelu(ref + bias), 1e-2)
+    _close(aux, _gelu_grad(ref + bias), 1e-2)
+
+
+@pytest.mark.parametrize("pair", [2, 0])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,split", [
+    (41472, 512, 1536, False, True, 1),      # dgrad of the QKV projection at cfg 3 (B = 512, Se = 81): gemm_tc_persist_kernel<256,0,1,..>
+    (41472, 512, 2048, False, True, 1),      # dgrad of FFN linear_1
+    (41472, 2048, 512, False, True, 1),      # dgrad of FFN linear_2 (multiply-by-aux epilogue covered separately)
+    (1536, 512, 41472, True, True, 9),       # split-K wgrad of the QKV projection: gemm_tc_persist_kernel<256,1,1,..>
+    (2048, 512, 41472, True, True, 5),       # split-K wgrad of FFN linear_1
+    (512, 2048, 41472, True, True, 5),       # split-K wgrad of FFN linear_2
+    (512, 512, 40448, True, True, 37),       # split-K wgrad of an out-projection (B*T = 40448 decoder rows)
+    (512, 512, 51712, True, True, 37),       # cfg 4 encoder rows (B = 512, Se = 101)
+])
+def test_cta_pair_dgrad_and_split_k_wgrad(_pair_switch, pair, M, N, K, a_mn, b_mn, split):
+    """The operand layouts of the backward pass (activation gradients with an MN-major weight, weight gradients with both
+    operands MN-major and split-K accumulation into fp32) at the benched row counts, pair and single-CTA kernels."""
+    _pair_switch(pair)
+    As, Bs, ref = _ops(M, N, K, a_mn, b_mn, seed=9)
+    if split == 1:
+        out, _, _ = gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn)
+        _close(out, ref)
+        aux_in = torch.randn(M, N, device=DEV).bfloat16()
+        _, outT, _ = gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, flags=256, want_T=True, aux_in=aux_in)
+        _close(outT, ref * aux_in.float(), 1e-2)
+        res = torch.randn(M, N, device=DEV)
+        out, _, _ = gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, res=res)
+        _close(out, ref + res)
+    else:
+        out = torch.ones(M, N, device=DEV)
+        gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, flags=4, split_k=split, out32=out)
+        _close(out, ref + 1.0)

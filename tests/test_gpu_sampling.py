@@ -168,3 +168,27 @@ def test_pipelined_sample_smiles_equals_single_pass(name):
             res.append(s.sample_smiles(dconds, sm["scaffold"], zs=zs, toklen=[6, 3, 5, 6, 2, 6, 4, 6, 1, 5, 6]))
     assert list(res[0][0]) == list(res[1][0])
     assert list(res[0][2]) == list(res[1][2])
+
+
+def test_shape_caches_are_bounded_and_weight_edits_reach_the_kernels():
+    """(1) static buffers / CUDA graphs are kept for at most `cache_shapes` request shapes; (2) the bf16 operand copy
+    follows in-place writes through .data (no autograd version bump) and re-pointed parameters."""
+    fx = load_golden("vaetf_full")
+    s, _ = _sampler(fx, "bf16", max_strlen=6, cache_shapes=2, sync_every=2)
+    g = torch.Generator().manual_seed(5)
+    for n in (3, 5, 7, 3, 9):
+        zs = torch.randn(n, 10, 128, generator=g).to(DEV)
+        ys0 = torch.full((n, 1), 2, dtype=torch.long, device=DEV)
+        mask = torch.ones(n, 1, 10, dtype=torch.bool, device=DEV)
+        for _ in range(3):                       # warm, capture, replay
+            a = s.decode(zs=zs, ys=ys0, src_mask=mask)
+        assert len(s._static) <= 2 and len(s._graphs) <= 2
+    m = s.model
+    before = m.decode(ys0, zs, mask, torch.ones(n, 1, 1, dtype=torch.bool, device=DEV)).clone()
+    m.out.weight.data.mul_(2.0)                  # no _version bump
+    after = m.decode(ys0, zs, mask, torch.ones(n, 1, 1, dtype=torch.bool, device=DEV))
+    assert float((after - before).abs().max()) > 1e-3
+    m.out.bias.data = torch.full_like(m.out.bias, 5.0)      # breaks the aliasing with the flat buffer
+    moved = m.decode(ys0, zs, mask, torch.ones(n, 1, 1, dtype=torch.bool, device=DEV))
+    assert m._aliased()
+    assert float((moved - after).abs().max()) > 1.0
