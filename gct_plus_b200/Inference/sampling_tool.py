@@ -204,7 +204,8 @@ class Sampling:
                     break
         return ys
 
-    def _decode_cached(self, zs, ys, src_mask, dconds=None, uniforms=None, idle_work=None):
+    def _decode_cached(self, zs, ys, src_mask, dconds=None, uniforms=None, idle_work=None, forced=None, probs_out=None,
+                       logits_out=None):
         lib, model, dev = L.lib(), self.model, torch.device(self.device)
         cfg = model._cfg()
         n, t0 = ys.shape
@@ -252,7 +253,14 @@ class Sampling:
                           zs=st['zs'].data_ptr(), src_mask=st['mask'].data_ptr(),
                           dconds=st['dconds'].data_ptr() if nc > 0 else None,
                           uniforms=None if greedy else st['uni'].data_ptr(), ys=st['ys'].data_ptr(),
-                          status=st['status'].data_ptr())
+                          status=st['status'].data_ptr(), forced=L._p(forced), probs_out=L._p(probs_out),
+                          logits_out=L._p(logits_out))
+        probe = forced is not None or probs_out is not None or logits_out is not None
+        if forced is not None:
+            assert forced.is_cuda and forced.dtype == torch.int64 and tuple(forced.shape) == (n, max_len) and forced.is_contiguous()
+        for t in (probs_out, logits_out):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                                 and tuple(t.shape) == (steps, n, cfg.trg_vocab))
 
         def begin():
             L.check(lib.gct_decode_begin(C.byref(cfg), C.byref(w), C.byref(dec), L.ptr(ws), ws.numel(), L.stream_ptr()),
@@ -266,8 +274,9 @@ class Sampling:
         gkey = key + (ws.data_ptr(), w.params_f32, w.params_bf16, self.sync_every)
         for gk in [gk for gk in self._graphs if gk[len(key)] != ws.data_ptr()]:
             del self._graphs[gk]                # the grow-only workspace was reallocated: those graphs point at freed memory
-        graphs = self._graphs.get(gkey) if self.use_cuda_graph else None
-        if self.use_cuda_graph and graphs is None and st.get('warm'):
+        use_graph = self.use_cuda_graph and not probe      # probe buffers are per call: not baked into a graph
+        graphs = self._graphs.get(gkey) if use_graph else None
+        if use_graph and graphs is None and st.get('warm'):
             # second call with this shape: capture begin + every chunk once, replay from now on
             graphs = []
             for fn in [begin] + [(lambda a=a, b=b: run(a, b)) for a, b in chunks]:
@@ -301,6 +310,23 @@ class Sampling:
             steps_run = int(st['status_host'][1]) + 1
         self.last_decode_steps = steps_run
         return st['ys'][:, :t0 + steps_run].clone()
+
+    def teacher_forced_logits(self, zs, ys_full, src_mask, dconds=None, t0=1, want_probs=False):
+        """Runs the KV-cached decoder over GIVEN sequences: ys_full (n, t0 + max_strlen - 1) holds the prefix (t0 tokens)
+        and the tokens to append at every step.  Returns logits (steps, n, Vt) -- row s equals
+        model.decode(ys_full[:, :t0+s], ...)[:, -1] of the reference loop (Inference/sampling_tool.py:150-160) --
+        and optionally their softmax.  Not in the reference; used to score sequences and by the per-step parity tests."""
+        dev = torch.device(self.device)
+        n, steps = ys_full.size(0), self.max_strlen - 1
+        assert ys_full.size(1) == t0 + steps
+        V = self.model.out.out_features
+        forced = ys_full.to(dev).long().contiguous()
+        logits = torch.empty((steps, n, V), device=dev, dtype=torch.float32)
+        probs = torch.empty_like(logits) if want_probs else None
+        with torch.no_grad():
+            self._decode_cached(zs.to(dev), forced[:, :t0].contiguous(), src_mask.to(dev), dconds=dconds, forced=forced,
+                                probs_out=probs, logits_out=logits)
+        return (logits, probs) if want_probs else logits
 
     # ------------------------------------------------------------------ shared tail of sample_smiles
     def _finish(self, outs, strip):

@@ -41,7 +41,7 @@ class GctIO(C.Structure):
 class GctDecode(C.Structure):
     _fields_ = [("B", i32), ("Lz", i32), ("max_len", i32), ("prefix_len", i32), ("greedy", i32), ("eos_id", i32),
                 ("seed", C.c_uint32), ("zs", vp), ("src_mask", vp), ("dconds", vp), ("uniforms", vp), ("ys", vp),
-                ("status", vp)]
+                ("status", vp), ("forced", vp), ("probs_out", vp), ("logits_out", vp)]
 
 
 class GctCorpus(C.Structure):
@@ -147,6 +147,11 @@ def ptr(t):
     if t is None:
         return None
     return C.c_void_p(t.data_ptr())
+
+
+def _p(t):
+    """data_ptr or None."""
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr():

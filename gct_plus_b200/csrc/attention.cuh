@@ -261,11 +261,7 @@ static int launch_attn_fwd(const AttnParams& p, cudaStream_t st) {
     GCT_REQUIRE(p.Lk >= 1 && p.Lk <= 32 * ATT_MAXJ, "attention: Lk=%d outside [1,%d]", p.Lk, 32 * ATT_MAXJ);
     GCT_REQUIRE((p.ldk % 8) == 0 && (p.ldv % 8) == 0, "attention: K/V pitch must be a multiple of 8 elements");
     const size_t sm = attn_fwd_smem(p.Lk, 8);
-    static size_t cur = 0;
-    if (sm > cur) {
-        GCT_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        cur = sm;
-    }
+    GCT_SMEM_LIMIT(attn_fwd_kernel<T>, sm);
     attn_fwd_kernel<T><<<p.B * p.H, 256, sm, st>>>(p);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
@@ -277,11 +273,7 @@ static int launch_attn_bwd(const AttnBwdParams& bp, cudaStream_t st) {
     GCT_REQUIRE(p.Lk >= 1 && p.Lk <= 32 * ATT_MAXJ, "attention bwd: Lk=%d outside [1,%d]", p.Lk, 32 * ATT_MAXJ);
     const size_t sm = attn_bwd_smem<T>(p.Lq, p.Lk);
     if (sm > 227 * 1024) GCT_FAIL(GCT_ERR_UNSUPPORTED, "attention bwd: Lq=%d Lk=%d needs %zu B of shared memory", p.Lq, p.Lk, sm);
-    static size_t cur = 0;
-    if (sm > cur) {
-        GCT_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        cur = sm;
-    }
+    GCT_SMEM_LIMIT(attn_bwd_kernel<T>, sm);
     attn_bwd_kernel<T><<<p.B * p.H, 256, sm, st>>>(bp);
     GCT_LAUNCH_CHECK();
     return GCT_OK;

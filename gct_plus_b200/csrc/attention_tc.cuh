@@ -459,11 +459,13 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
     GCT_TRY(operand_map(p.Q, p.ldq, p.B * p.Lq, p.H, RPq, &tq));
     GCT_TRY(operand_map(p.K, p.ldk, p.B * p.Lk, p.H, RPk, &tk));
     GCT_TRY(operand_map(p.V, p.ldv, p.B * p.Lk, p.H, RPk, &tv));
-    static bool attr = false;
-    if (!attr) {
-        GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout(128, 128).total));
-        GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr = true;
+    {
+        static PerDeviceSize done_;
+        if (!done_.cur()) {
+            GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout(128, 128).total));
+            GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            done_.cur() = 1;
+        }
     }
     attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, p);
     GCT_LAUNCH_CHECK();
@@ -479,11 +481,13 @@ static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
     GCT_TRY(operand_map(p.K, p.ldk, p.B * p.Lk, p.H, RPk, &tk));
     GCT_TRY(operand_map(p.V, p.ldv, p.B * p.Lk, p.H, RPk, &tv));
     GCT_TRY(operand_map(bp.dO, bp.lddo, p.B * p.Lq, p.H, RPq, &tdo));
-    static bool attr = false;
-    if (!attr) {
-        GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout(128, 128).total));
-        GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr = true;
+    {
+        static PerDeviceSize done_;
+        if (!done_.cur()) {
+            GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout(128, 128).total));
+            GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            done_.cur() = 1;
+        }
     }
     attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, bp);
     GCT_LAUNCH_CHECK();

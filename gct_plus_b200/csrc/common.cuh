@@ -44,6 +44,29 @@ extern thread_local char g_gct_err[512];
 
 #define GCT_LAUNCH_CHECK() GCT_CUDA(cudaGetLastError())
 
+// Function attributes (dynamic shared-memory limit, carve-out) and the SM count belong to a DEVICE, not to the process:
+// the once-flags below are kept per device ordinal so that a process driving several GPUs sets them on each.
+constexpr int GCT_MAX_DEVICES = 64;
+static inline int gct_cur_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < GCT_MAX_DEVICES) ? d : 0;
+}
+struct PerDeviceSize {
+    size_t v[GCT_MAX_DEVICES] = {};
+    size_t& cur() { return v[gct_cur_device()]; }
+};
+// raises the kernel's dynamic shared-memory limit to `bytes` on the current device if it is below that
+#define GCT_SMEM_LIMIT(kern, bytes)                                                                              \
+    do {                                                                                                         \
+        static PerDeviceSize lim_;                                                                               \
+        size_t& cur_ = lim_.cur();                                                                               \
+        if ((size_t)(bytes) > cur_) {                                                                            \
+            GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+            cur_ = (size_t)(bytes);                                                                              \
+        }                                                                                                        \
+    } while (0)
+
 #define GCT_TRY(expr)                 \
     do {                              \
         int _r = (expr);              \

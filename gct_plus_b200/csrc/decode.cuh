@@ -212,12 +212,8 @@ template <typename T, int CH, int NS, int ROWS>
 static int launch_decode_attn_cfg(const DecAttnParams& p, int B, cudaStream_t st) {
     const size_t smem = (size_t)NS * 2 * CH * p.H * 64 * sizeof(T);
     if (smem > 227 * 1024) GCT_FAIL(GCT_ERR_UNSUPPORTED, "decode attention config needs %zu B of shared memory", smem);
-    static size_t cur = 0;
     auto kern = decode_attn_kernel<T, CH, NS, ROWS>;
-    if (smem > cur) {
-        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
-    }
+    GCT_SMEM_LIMIT(kern, smem);
     GCT_CUDA(launch_k(kern, dim3((B + ROWS - 1) / ROWS), dim3((p.H + 1) * 32), smem, st, true, p, B));
     return GCT_OK;
 }
@@ -288,6 +284,7 @@ struct SampleParams {
     int greedy; int eos_id;
     uint8_t* done; int* n_done; int* first_all_done; int B;
     float* probs_out;                             // optional [B, V]
+    float* logits_out;                            // optional [B, V]
 };
 
 // one warp per row, V <= 128.  Matches the reference's order of operations: softmax over the
@@ -305,6 +302,7 @@ __global__ void decode_sample_kernel(SampleParams p) {
     for (int i = 0; i < 4; ++i) {
         const int c = i * 32 + lane;
         v[i] = (c < p.V) ? lr[c] : -INFINITY;
+        if (p.logits_out && c < p.V) p.logits_out[(size_t)b * p.V + c] = v[i];
         mx = fmaxf(mx, v[i]);
     }
     mx = warp_max(mx);

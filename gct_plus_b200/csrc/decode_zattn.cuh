@@ -177,11 +177,7 @@ decode_zattn_kernel(ZAttnParams p) {
 template <int LAT>
 static int launch_decode_zattn_lat(const ZAttnParams& p, cudaStream_t st) {
     constexpr size_t smem = (size_t)ZA_WARPS * ZA_MAX_KEYS * (LAT * 2 + 16);
-    static bool attr = false;
-    if (!attr) {
-        GCT_CUDA(cudaFuncSetAttribute(decode_zattn_kernel<LAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    GCT_SMEM_LIMIT(decode_zattn_kernel<LAT>, smem);
     GCT_CUDA(launch_k(decode_zattn_kernel<LAT>, dim3((p.B + ZA_WARPS - 1) / ZA_WARPS), dim3(ZA_WARPS * 32), smem, st, true, p));
     return GCT_OK;
 }

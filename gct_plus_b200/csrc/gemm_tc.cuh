@@ -1019,11 +1019,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
                       cudaStream_t st) {
     using L = SmemLayout<BN, A_MN, B_MN, STAGES>;
     auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
-    }
+    GCT_SMEM_LIMIT(kern, L::TOTAL);
     const int num_kb = (K + BK - 1) / BK;
     int kps = (num_kb + split_k - 1) / split_k;
     split_k = (num_kb + kps - 1) / kps;
@@ -1033,10 +1029,10 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 }
 
 static int sm_count() {
-    static int n = 0;
+    static int per_dev[GCT_MAX_DEVICES] = {};
+    const int dev = gct_cur_device();
+    int& n = per_dev[dev];
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
@@ -1048,11 +1044,7 @@ static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, i
                           cudaStream_t st) {
     using L = PersistSmem<BN, STAGES, EW>;
     auto kern = gemm_tc_persist_kernel<BN, A_MN, B_MN, STAGES, EW>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
-    }
+    GCT_SMEM_LIMIT(kern, L::TOTAL);
     const int num_kb = (K + BK - 1) / BK;
     int kps = (num_kb + split_k - 1) / split_k;
     split_k = (num_kb + kps - 1) / kps;
@@ -1083,11 +1075,7 @@ static int launch_persist_pair(const CUtensorMap& ta, const CUtensorMap& tb_mn, 
                                int split_k, const Epilogue& epi, cudaStream_t st) {
     using L = PersistSmem<BN, STAGES, EW, 2>;
     auto kern = gemm_tc_persist_kernel<BN, A_MN, B_MN, STAGES, EW, 2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-        attr_set = true;
-    }
+    GCT_SMEM_LIMIT(kern, L::TOTAL);
     CUtensorMap tb = tb_mn;
     if (!B_MN) GCT_TRY(get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, (uint32_t)(BN / 2), &tb));
     const int num_kb = (K + BK - 1) / BK;

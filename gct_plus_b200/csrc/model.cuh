@@ -863,10 +863,13 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
     }
     SampleParams sp;
     sp.logits = W.logits; sp.ld = m.c.trg_vocab; sp.V = m.c.trg_vocab; sp.ys = D.ys; sp.ys_stride = D.max_len; sp.pos = pos;
-    sp.forced = nullptr; sp.forced_stride = 0;
+    sp.forced = D.forced ? D.forced + pos + 1 : nullptr; sp.forced_stride = D.max_len;
     sp.uniforms = D.uniforms ? D.uniforms + (size_t)step * B : nullptr;
     sp.seed = D.seed; sp.step = step; sp.greedy = D.greedy; sp.eos_id = D.eos_id; sp.done = W.done; sp.n_done = D.status;
-    sp.first_all_done = D.status + 1; sp.B = B; sp.probs_out = nullptr;
+    sp.first_all_done = D.status + 1; sp.B = B;
+    const size_t step_off = (size_t)step * B * m.c.trg_vocab;
+    sp.probs_out = D.probs_out ? D.probs_out + step_off : nullptr;
+    sp.logits_out = D.logits_out ? D.logits_out + step_off : nullptr;
     GCT_CUDA(launch_k(decode_sample_kernel, dim3(cdiv(B, 4)), dim3(128), 0, st, true, sp));
     return GCT_OK;
 }

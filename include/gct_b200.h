@@ -179,6 +179,10 @@ typedef struct {
     const float* uniforms;     /* optional [max_steps,B] U(0,1) numbers for multinomial     */
     int64_t* ys;               /* [B,max_len] int64, prefix filled by the caller            */
     int32_t* status;           /* device int[2]: {#rows that emitted <eos>, first step at which all had} */
+    const int64_t* forced;     /* optional [B,max_len]: teacher forcing -- step i appends forced[:, prefix_len+i] instead of
+                                  the drawn token (scoring given sequences; per-step parity tests); no <eos> bookkeeping */
+    float* probs_out;          /* optional [max_steps,B,Vt]: softmax(logits) of every step                       */
+    float* logits_out;         /* optional [max_steps,B,Vt]: the logits of every step (model.decode(...)[:, -1])  */
 } gct_decode_t;
 
 size_t gct_decode_workspace_bytes(const gct_config_t* cfg, int B, int Lz, int max_len);

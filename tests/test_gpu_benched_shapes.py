@@ -1,0 +1,258 @@
+"""Parity at the BENCHED shapes (BASELINE cfg 2 / cfg 3 / cfg 4), not only at the small golden fixtures.
+
+The oracle (oracle/gct_oracle.py, pinned against the reference by tests/test_oracle_golden.py) runs here in fp32 on the
+same GPU with TF32 off -- the reference's own numerics at sizes its CPU path would need minutes for.  What these cases
+add over tests/test_gpu_model.py / test_gpu_sampling.py (B = 3, S = 11):
+  * the full 6+6-layer, d_model 512 architecture at B = 512 rows (41 k - 52 k token rows): every GEMM of the step runs
+    through the persistent tcgen05 kernels, the CTA-pair (cta_group::2) forms included, in all three operand layouts
+    (fprop K-major, dgrad with an MN-major weight, split-K wgrad with both operands MN-major);
+  * the bf16 KV-cached decode over all 99 steps at B = 2048 (teacher-forced, so every step's logits can be compared with
+    the oracle's un-cached decoder on the same prefix), both ring configurations of decode_attn_kernel and the
+    latent-space cross-attention;
+  * gct_decode_attention on its own against O.attention for cache lengths around the configuration switch.
+Tolerances are north_star's: 1e-2 relative (to the tensor's max magnitude) in the bf16 tier, 1e-4 in the fp32 tier.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import gct_plus_b200._lib as L
+from gpu_common import DEV
+from helpers import FakeField, FakeScaler, O, rel_err
+from gct_plus_b200.Inference.sampling_tool import sampling_tool_dict
+from gct_plus_b200.Model import Cvaetf, Vaetf
+from gct_plus_b200.Train.trainer1 import FusedTrainer
+
+pytestmark = pytest.mark.gpu
+ARCH = dict(N=6, d_model=512, dff=2048, h=8, latent_dim=128)
+V = 32
+
+
+def _train_batch(B, S, nc, scaffold, seed):
+    """Synthetic MOSES-shaped rows (bench.py's generator): ragged lengths in [0.6 S, S], <sep> after the scaffold."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(int(S * 0.6), S + 1, (B,), generator=g)
+    lens[0] = S
+    toks = torch.randint(5, V, (B, S), generator=g)
+    if scaffold:
+        toks[:, scaffold] = 4
+    ar = torch.arange(S)[None, :]
+    src = torch.where(ar < lens[:, None], toks, torch.ones_like(toks))
+    trg = torch.ones(B, S + 2, dtype=torch.long)
+    trg[:, 0] = 2
+    trg[:, 1:S + 1] = src
+    trg[torch.arange(B), lens + 1] = 3
+    batch = {"src": src, "trg": trg}
+    if nc:
+        batch["econds"] = torch.randn(B, nc, generator=g)
+        batch["dconds"] = batch["econds"].clone()
+    return batch
+
+
+def _oracle_step(sd, cfg, batch, eps, beta):
+    """fp32 oracle forward + loss + backward on the GPU (TF32 off): returns outputs and the gradient of every parameter."""
+    assert not torch.backends.cuda.matmul.allow_tf32
+    params = {k: v.detach().to(DEV).clone().requires_grad_(not k.endswith("pe.pe")) for k, v in sd.items()}
+    b = {k: v.to(DEV) for k, v in batch.items()}
+    prop, mol, mu, lv, z = O.forward_propagation(params, cfg, b, 1, eps.to(DEV))
+    loss, rce, _, kld = O.loss_function(beta, prop, mol, None, b["trg"][:, 1:].reshape(-1), mu, lv, False, 1)
+    loss.backward()
+    grads = {k: p.grad for k, p in params.items() if p.grad is not None}
+    return dict(logits=mol.detach(), mu=mu.detach(), lv=lv.detach(), z=z.detach(), loss=float(loss), rce=float(rce),
+                kld=float(kld)), grads
+
+
+@pytest.mark.parametrize("mt,S,sca,dtype", [("pvaetf", 78, 0, "bf16"), ("pscavaetf", 98, 19, "bf16"), ("pvaetf", 78, 0, "fp32")])
+def test_training_step_at_cfg3_cfg4_shape_matches_oracle(mt, S, sca, dtype):
+    """cfg 3 (pvaetf B=512 S=78 T=79 -> 41 472 encoder rows) and cfg 4's per-GPU shape (pscavaetf B=512 S=98 T=99 ->
+    51 712 rows) through FusedTrainer.step -- the call bench.py times -- with dropout off and a supplied eps, against the
+    oracle's logits, mu / log_var / z, loss terms and the gradient of every parameter."""
+    B, nc, beta = 512, 3, 0.5
+    torch.manual_seed(0)
+    m = Cvaetf(V, V, dropout=0.0, nconds=nc, use_cond2lat=True, compute_dtype=dtype, **ARCH)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV).train()
+    batch = _train_batch(B, S, nc, sca, seed=50)
+    eps = torch.randn(B, nc + S, ARCH["latent_dim"], generator=torch.Generator().manual_seed(3))
+    cfg = O.ModelCfg(model_type=mt, src_vocab=V, trg_vocab=V, nconds=nc, use_cond2lat=True)
+    want, gref = _oracle_step(sd, cfg, batch, eps, beta)
+
+    tr = FusedTrainer(m, mt, pad_id=1, lr=1e-4, warmup=8000)
+    devb = {k: v.to(DEV) for k, v in batch.items()}
+    tr.step(devb, beta, eps_noise=eps.to(DEV))
+    loss, rce, kld = tr.read_losses()
+    bf = next(iter(tr._bufs.values()))
+    tol = 1e-2 if dtype == "bf16" else 1e-4
+    assert rel_err(bf["logits"], want["logits"]) < tol
+    assert rel_err(bf["mu"], want["mu"]) < tol and rel_err(bf["lv"], want["lv"]) < tol and rel_err(bf["z"], want["z"]) < tol
+    assert abs(loss - want["loss"]) < tol * abs(want["loss"]), (loss, want["loss"])
+    assert abs(rce - want["rce"]) < tol * abs(want["rce"]) and abs(kld - want["kld"]) < tol * abs(want["kld"])
+    # gradients: tr.grads still holds this step's (un-averaged, single rank) gradient of the sum-loss
+    names = [n for n, _ in m.named_parameters()]
+    got = dict(zip(names, m.grad_views(tr.grads)))
+    gmax = max(float(g.abs().max()) for g in gref.values())
+    worst_max, worst_fro = ("", 0.0), ("", 0.0)
+    for k, g in gref.items():
+        if k.endswith("k_linear.bias"):        # mathematically zero gradient (softmax shift invariance): rounding noise only
+            continue
+        diff = got[k].double() - g.double()
+        emax = float(diff.abs().max()) / max(float(g.abs().max()), 1e-3 * gmax)
+        efro = float(diff.norm()) / max(float(g.double().norm()), 1e-3 * gmax * g.numel() ** 0.5)
+        if emax > worst_max[1]:
+            worst_max = (k, emax)
+        if efro > worst_fro[1]:
+            worst_fro = (k, efro)
+    print(f"{mt} {dtype}: worst max-abs {worst_max}, worst Frobenius {worst_fro}")
+    # per-tensor Frobenius error is the "1e-2 relative" statement for a gradient TENSOR; single elements of a bf16 run
+    # (41 k-row sums of bf16-rounded products) are held to 3e-2 of the tensor's max
+    assert worst_fro[1] < (1e-2 if dtype == "bf16" else 1e-4), worst_fro
+    assert worst_max[1] < (3e-2 if dtype == "bf16" else 5e-4), worst_max
+
+
+def test_autograd_bridge_at_cfg3_shape_matches_fused_trainer():
+    """The reference-shaped path (forward_propagation -> loss_function -> loss.backward()) and FusedTrainer must produce the
+    same gradients at B = 512 (same kernels, different host plumbing)."""
+    from gct_plus_b200.Model.modules import get_src_mask, get_trg_mask
+    from gct_plus_b200.Train.trainer1 import loss_function
+    B, S, nc, beta = 512, 78, 3, 0.5
+    torch.manual_seed(0)
+    m = Cvaetf(V, V, dropout=0.0, nconds=nc, use_cond2lat=True, compute_dtype="bf16", **ARCH).to(DEV).train()
+    batch = {k: v.to(DEV) for k, v in _train_batch(B, S, nc, 0, seed=51).items()}
+    eps = torch.randn(B, nc + S, ARCH["latent_dim"], generator=torch.Generator().manual_seed(4)).to(DEV)
+    trg_in = batch["trg"][:, :-1]
+    logits, mu, lv, z, _ = m._run(batch["src"], trg_in, get_src_mask(batch["src"], 1, batch["econds"]),
+                                  get_trg_mask(trg_in, 1, False, batch["dconds"]), batch["econds"], batch["dconds"], eps=eps)
+    loss = loss_function(beta, None, logits, None, batch["trg"][:, 1:].reshape(-1), mu, lv, False, 1)[0]
+    loss.backward()
+    auto = {n: p.grad.clone() for n, p in m.named_parameters()}
+    tr = FusedTrainer(m, "pvaetf", pad_id=1)
+    tr.step(batch, beta, eps_noise=eps)
+    for (n, _), g in zip(m.named_parameters(), m.grad_views(tr.grads)):
+        if n.endswith("k_linear.bias"):
+            continue
+        scale = float(auto[n].abs().max()) + 1e-6
+        # split-K weight gradients accumulate with atomics: the summation order differs run to run
+        assert float((g - auto[n]).abs().max()) / scale < 2e-3, n
+
+
+# ------------------------------------------------------------------------------------------ decode attention alone
+@pytest.mark.parametrize("cfg", [0, 831, 1621])
+@pytest.mark.parametrize("n_cached", [0, 1, 49, 67, 68, 99])
+def test_decode_attention_kernel_vs_oracle_attention(n_cached, cfg):
+    """gct_decode_attention (bf16 tier): one query per (row, head) over n_cached cached keys + this step's key, ragged
+    key_valid masks, against O.attention (Model/sublayers.py:29-41) on the same bf16-rounded operands; cfg 0 = the automatic
+    choice (8-key chunks / 3-stage ring below 68 cached keys, 16-key chunks / 2 stages from 68 on), 831 / 1621 force each."""
+    lib = L.lib()
+    B, H, d, Lmax = 777, 8, 512, 128
+    g = torch.Generator().manual_seed(100 + n_cached)
+    kc = torch.randn(B, Lmax, d, generator=g).to(DEV).bfloat16()
+    vc = torch.randn(B, Lmax, d, generator=g).to(DEV).bfloat16()
+    qkv = torch.randn(B, 3 * d, generator=g).to(DEV).bfloat16()
+    valid = (torch.rand(B, Lmax, generator=g) > 0.2).to(torch.uint8)
+    valid[:, n_cached] = 1
+    valid[3] = 0                              # nothing attendable at all: uniform softmax (masked_fill -1e9 semantics)
+    valid[5, :n_cached] = 0                   # only this step's key
+    valid = valid.to(DEV)
+    out = torch.zeros(B, d, device=DEV, dtype=torch.bfloat16)
+    kc0, vc0 = kc.clone(), vc.clone()
+    lib.gct_set_decode_attn_config(cfg)
+    try:
+        L.check(lib.gct_decode_attention(L.ptr(qkv), 3 * d, qkv[:, d:].data_ptr(), qkv[:, 2 * d:].data_ptr(), 3 * d, L.ptr(kc), L.ptr(vc),
+                                         Lmax * d, d, n_cached, L.ptr(valid), Lmax, L.ptr(out), d, B, H, L.DTYPE_BF16, L.stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        lib.gct_set_decode_attn_config(0)
+    n = n_cached + 1
+    K = torch.cat([kc0[:, :n_cached], qkv[:, None, d:2 * d]], dim=1).float().view(B, n, H, 64).transpose(1, 2)
+    Vv = torch.cat([vc0[:, :n_cached], qkv[:, None, 2 * d:]], dim=1).float().view(B, n, H, 64).transpose(1, 2)
+    q = qkv[:, :d].float().view(B, 1, H, 64).transpose(1, 2)
+    want, _ = O.attention(q, K, Vv, 64, valid[:, None, :n].bool())
+    want = want.transpose(1, 2).reshape(B, d)
+    assert rel_err(out, want) < 1e-2
+    # the step's K / V row was appended to the cache, nothing else was touched
+    assert torch.equal(kc[:, n_cached], qkv[:, d:2 * d]) and torch.equal(vc[:, n_cached], qkv[:, 2 * d:])
+    assert torch.equal(kc[:, :n_cached], kc0[:, :n_cached]) and torch.equal(kc[:, n_cached + 1:], kc0[:, n_cached + 1:])
+
+
+# ------------------------------------------------------------------------------------------ 99-step bf16 KV decode
+def _sampler(model, mt, nc, max_strlen, **kw):
+    kwargs = dict(top_k=None, latent_dim=ARCH["latent_dim"], max_strlen=max_strlen, use_cond2dec=False, decode_algo="multinomial",
+                  n_jobs=1, toklen_data=None, cond_dim=nc, scaler=FakeScaler(), device=DEV, SRC=FakeField(), TRG=FakeField(), **kw)
+    return sampling_tool_dict[mt](model, kwargs)
+
+
+DECODE_CASES = [("vaetf", 0, 1, 55, True), ("vaetf", 0, 1, 55, False), ("pvaetf", 3, 1, 55, True), ("scavaetf", 0, 22, 76, True),
+                ("pscavaetf", 3, 22, 76, True)]
+
+
+@pytest.mark.parametrize("mt,nc,t0,Lz,latent_form", DECODE_CASES)
+def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form):
+    """cfg 2 / cfg 5 decode at B = 2048 rows, max_strlen 100 (99 steps), bf16 tier, teacher-forced on random tokens:
+    the logits of EVERY step -- KV cache lengths 1..99 (+ the scaffold prefix), both decode_attn ring configurations,
+    cross-attention in latent space or in K/V form, ragged latent lengths, cond2lat memory rows -- against the oracle's
+    un-cached decoder (Inference/sampling_tool.py:150-160: model.decode on the growing prefix, last position)."""
+    lib = L.lib()
+    B, max_strlen = 2048, 100
+    steps = max_strlen - 1
+    torch.manual_seed(0)
+    cls = Vaetf if mt == "vaetf" else Cvaetf
+    m = cls(V, V, dropout=0.1, nconds=nc, use_cond2lat=nc > 0, compute_dtype="bf16", **ARCH)
+    sd = {k: v.detach().clone().to(DEV) for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    s = _sampler(m, mt, nc, max_strlen, latent_bucket=8)
+    g = torch.Generator().manual_seed(17)
+    zs = torch.randn(B, Lz, ARCH["latent_dim"], generator=g)
+    lens = torch.randint(13 + (t0 - 1), Lz + 1, (B,), generator=g)
+    lens[0], lens[1] = Lz, 1
+    mask = torch.arange(Lz)[None, None, :] < lens[:, None, None]
+    ys = torch.randint(5, V, (B, t0 + steps), generator=g)
+    ys[:, 0] = 2
+    if t0 > 1:
+        ys[:, t0 - 1] = 4
+    ys[7, 40:] = 1                                 # a row that runs into <pad> tokens: key_valid masks them like trg_mask does
+    dconds = torch.randn(B, nc, generator=g).to(DEV) if nc else None
+    lib.gct_set_latent_cross_attention(int(latent_form))
+    try:
+        got = s.teacher_forced_logits(zs, ys, mask, dconds=dconds, t0=t0)        # (steps, B, V)
+    finally:
+        lib.gct_set_latent_cross_attention(1)
+    cfg = O.ModelCfg(model_type=mt, src_vocab=V, trg_vocab=V, nconds=nc, use_cond2lat=nc > 0)
+    trg = ys[:, :-1].to(DEV)
+    with torch.no_grad():
+        want = O.decode_logits(sd, cfg, trg, zs.to(DEV), mask.to(DEV), O.trg_mask(trg, 1), dconds)   # (B, t0+steps-1, V)
+    want = want[:, t0 - 1:, :].transpose(0, 1)     # position t0-1+s is what step s predicts from
+    assert want.shape == got.shape
+    scale = float(want.abs().max())
+    per_step = (got - want).abs().amax(dim=(1, 2)) / scale
+    print(f"{mt} latent_form={latent_form}: worst step {int(per_step.argmax())} rel err {float(per_step.max()):.3e}, "
+          f"mean {float(per_step.mean()):.3e}")
+    assert float(per_step.max()) < 1e-2, (int(per_step.argmax()), float(per_step.max()))
+
+
+def test_fp32_kv_decode_every_step_matches_oracle_at_b2048():
+    """Same teacher-forced comparison in the fp32 tier (the tier whose greedy tokens must be identical): 1e-4."""
+    B, max_strlen, Lz = 2048, 100, 55
+    steps = max_strlen - 1
+    torch.manual_seed(0)
+    m = Vaetf(V, V, dropout=0.1, nconds=0, compute_dtype="fp32", **ARCH)
+    sd = {k: v.detach().clone().to(DEV) for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    s = _sampler(m, "vaetf", 0, max_strlen, latent_bucket=8)
+    g = torch.Generator().manual_seed(18)
+    zs = torch.randn(B, Lz, ARCH["latent_dim"], generator=g)
+    lens = torch.randint(13, Lz + 1, (B,), generator=g)
+    mask = torch.arange(Lz)[None, None, :] < lens[:, None, None]
+    ys = torch.randint(5, V, (B, 1 + steps), generator=g)
+    ys[:, 0] = 2
+    got = s.teacher_forced_logits(zs, ys, mask)
+    cfg = O.ModelCfg(model_type="vaetf", src_vocab=V, trg_vocab=V)
+    trg = ys[:, :-1].to(DEV)
+    with torch.no_grad():
+        want = O.decode_logits(sd, cfg, trg, zs.to(DEV), mask.to(DEV), O.trg_mask(trg, 1)).transpose(0, 1)
+    assert rel_err(got, want) < 1e-4
+    # the greedy choice is reproduced wherever the oracle's top-2 gap exceeds the tolerance (exact ties aside)
+    top2 = want.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 2e-4 * float(want.abs().max())
+    assert torch.equal(got.argmax(-1)[clear], want.argmax(-1)[clear])
+    assert float(clear.float().mean()) > 0.99
