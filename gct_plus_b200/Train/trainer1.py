@@ -15,7 +15,7 @@ import torch.distributed as dist
 from .. import _lib as L
 from ..Model.forward_propagation1 import forward_propagation
 from ..Model.modules import get_src_mask, get_trg_mask
-from .dp import allreduce_sum_, world_info
+from .dp import GradExchange, allreduce_sum_, world_info
 
 
 def KLAnnealer(epoch, KLA_ini_beta, KLA_inc_beta, KLA_beg_epoch):
@@ -175,7 +175,7 @@ class FusedTrainer:
     """
 
     def __init__(self, model, model_type, pad_id=1, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, warmup=8000,
-                 use_cond2dec=False, process_group=None):
+                 use_cond2dec=False, process_group=None, grad_exchange="overlap", force_exchange=False):
         self.model, self.model_type, self.pad_id = model, model_type, pad_id
         self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
         if use_cond2dec or (getattr(model, 'use_cond2dec', False) and int(model.nconds) > 0):
@@ -188,6 +188,12 @@ class FusedTrainer:
         self.variational = model._variational()
         self.pg = process_group
         self.world = world_info(process_group)[1]
+        # gradient exchange across ranks: "overlap" = bucketed NCCL all-reduce on a side stream while the backward still runs
+        # (gct_backward_dp, DDP's behaviour), "nccl" = one all-reduce of the flat buffer after the backward through the
+        # library's communicator, "torch" = the same through torch.distributed (any backend)
+        assert grad_exchange in ("overlap", "nccl", "torch")
+        self.grad_exchange = grad_exchange if (self.world > 1 or force_exchange) else "torch"     # force_exchange: 1-rank communicator (tests)
+        self.xchg = GradExchange(model, process_group) if self.grad_exchange != "torch" else None
         flat = model._flat
         self.grads = torch.zeros_like(flat)
         self.exp_avg = torch.zeros_like(flat)
@@ -256,10 +262,22 @@ class FusedTrainer:
         if not train:
             return self.out4
         self.grads.zero_()
-        L.check(lib.gct_backward(C.byref(cfg), C.byref(w), C.byref(io), L.ptr(bf['dlogits']), L.ptr(bf['dmu']), L.ptr(bf['dlv']),
-                                 None, L.ptr(bf['ws']), bf['ws'].numel(), L.ptr(bf['scratch']), bf['scratch'].numel(), st),
-                "gct_backward")
-        gscale = allreduce_sum_(self.grads, self.pg)       # DDP semantics: mean over ranks of the per-rank sum-loss gradient
+        if self.grad_exchange == "overlap":
+            x = self.xchg
+            L.check(lib.gct_backward_dp(C.byref(cfg), C.byref(w), C.byref(io), L.ptr(bf['dlogits']), L.ptr(bf['dmu']), L.ptr(bf['dlv']),
+                                        None, L.ptr(bf['ws']), bf['ws'].numel(), L.ptr(bf['scratch']), bf['scratch'].numel(), x.comm,
+                                        C.cast(x.buckets, C.c_void_p), x.n_buckets, C.c_void_p(x.stream.cuda_stream), st),
+                    "gct_backward_dp")
+            gscale = 1.0 / self.world
+        else:
+            L.check(lib.gct_backward(C.byref(cfg), C.byref(w), C.byref(io), L.ptr(bf['dlogits']), L.ptr(bf['dmu']), L.ptr(bf['dlv']),
+                                     None, L.ptr(bf['ws']), bf['ws'].numel(), L.ptr(bf['scratch']), bf['scratch'].numel(), st),
+                    "gct_backward")
+            if self.grad_exchange == "nccl":
+                self.xchg.allreduce_(self.grads)
+                gscale = 1.0 / self.world
+            else:
+                gscale = allreduce_sum_(self.grads, self.pg)   # DDP semantics: mean over ranks of the per-rank sum-loss gradient
         self.step_count += 1
         shadow = m._shadow if m.compute_dtype == "bf16" else None
         L.check(lib.gct_adam_step(L.ptr(m._flat), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),

@@ -44,6 +44,10 @@ class GctDecode(C.Structure):
                 ("status", vp), ("forced", vp), ("probs_out", vp), ("logits_out", vp)]
 
 
+class GctBucket(C.Structure):
+    _fields_ = [("stage", i32), ("reserved", i32), ("offset", i64), ("count", i64)]
+
+
 class GctCorpus(C.Structure):
     _fields_ = [("src_ids", vp), ("trg_ids", vp), ("tok_off", vp), ("sca_src_ids", vp), ("sca_trg_ids", vp), ("sca_off", vp),
                 ("econds", vp), ("dconds", vp), ("nconds", i32), ("n_rows", i64)]
@@ -93,11 +97,17 @@ _PROTOS = {
     "gct_collate": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                               vp, vp]),
     "gct_detokenize": (i64, [vp, i64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, i64]),
+    "gct_toklen_draw": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_double, i64, vp]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
     "gct_decode_begin_launches": (C.c_int, [C.POINTER(GctConfig), C.c_int]),
     "gct_decode_attention": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
                                        C.c_int, C.c_int, C.c_int, vp]),
     "gct_allreduce_grads": (C.c_int, [vp, vp, i64, vp]),
+    "gct_nccl_unique_id": (C.c_int, [vp]),
+    "gct_nccl_comm_init": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, vp]),
+    "gct_nccl_comm_destroy": (C.c_int, [vp]),
+    "gct_backward_dp": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctIO), vp, vp, vp, vp, vp, sz, vp, sz, vp, vp,
+                                  C.c_int, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -1,188 +1,278 @@
-// Decode-time cross-attention evaluated in LATENT space (bf16 tier, memories without condition rows).
+// Decode-time cross-attention evaluated in LATENT space (bf16 tier; every sampler: vaetf, pvaetf, scavaetf, pscavaetf).
 //
 // The decoder memory is an affine image of the latent code, mem_j = Wz z_j + bz (Model/vaetf.py:93-95,
 // Model/cvaetf.py:99-101), so for head h
-//     score_hj = q_h . (Wk_h mem_j + bk_h) / 8 = [(Wk_h Wz)^T q_h] . z_j / 8 + const(h)     (the constant cancels in the softmax)
-//     out_h    = sum_j p_hj (Wv_h mem_j + bv_h) = (Wv_h Wz) zbar_h + (Wv_h bz + bv_h),        zbar_h = sum_j p_hj z_j.
-// Instead of streaming per-layer K/V projections of the memory ([keys][512] x 2 per layer and batch row) each step,
-// the step reads the shared latent rows ([keys][LAT], 4x narrower, the same for every layer) and the two projections
-// are folded into the query / output GEMMs once per decode (decode_zprep in model.cuh):
-//     qz   = xn Wqz^T + bqz,   Wqz[h*LAT + a, :] = (1/8) sum_i (Wk Wz)[h*64+i, a] Wq[h*64+i, :]           [B, H*LAT]
-//     zbar = this kernel                                                                                [B, H*LAT]
-//     x   += zbar Woz^T + boz, Woz[:, h*LAT + a] = sum_i Wo[:, h*64+i] (Wv Wz)[h*64+i, a],  boz = Wo (Wv bz + bv) + bo.
-// Algorithmic HBM bytes per batch row and layer: keys*LAT*2 + 2*H*LAT*2  (vs 2*keys*512*2 for the K/V form).
+//     score_hj = q_h . (Wk_h mem_j + bk_h) / 8 = [(Wk_h Wz)^T q_h] . z_j / 8 + C_h,   C_h = q_h . (Wk_h bz + bk_h) / 8
+//     value_j  = Wv_h mem_j + bv_h             = (Wv_h Wz) z_j + (Wv_h bz + bv_h).
+// With use_cond2lat the memory carries `nc` extra rows c_i = embed_cond2lat(dconds)_i in front (Model/cvaetf.py:107-116); they
+// are not images of a latent, but relative to the same constants they are ordinary keys / values of u_i = c_i - bz:
+//     score_hi = q_h . (Wk_h u_i) / 8 + C_h,      value_i = Wv_h u_i + (Wv_h bz + bv_h).
+// C_h cancels in the softmax and the value constant factors out (the probabilities sum to one), so per layer
+//     qz   = xn Wqz^T + bqz          Wqz[h*LAT + a, :] = (1/8) sum_i (Wk Wz)[h*64+i, a] Wq[h*64+i, :]        [B, H*LAT]
+//     q8   = (xn Wq^T + bq) / 8      (only with condition rows)                                          [B, d]
+//     zbar_h = sum_j p_hj z_j ,  ac_h = sum_i p_hi (Wv u_i)_h        <- this kernel, one softmax over latent + condition keys
+//     x   += zbar Woz^T + ac Wo^T + boz,   Woz[:, (h, a)] = sum_i Wo[:, h*64+i] (Wv Wz)[h*64+i, a],  boz = Wo (Wv bz + bv) + bo.
+// The two projections of every layer are folded into the query / output GEMMs once per decode (decode_zprep in model.cuh);
+// the per-layer K/V of the condition rows (nc x 2d per batch row) are computed once per decode as well.
+// Algorithmic HBM bytes per batch row and layer: keys*LAT*2 + 2*H*LAT*2 (+ nc*2d*2 + 2d*2)   vs   2*(nc+keys)*d*2 in K/V form.
 //
-// One warp per batch row, tensor-core math through mma.sync.m16n8k16 (the problem per row is 16 x keys x LAT -- far too
-// small for a tcgen05 tile): S = Qz Z^T with heads as the M dimension, softmax on the accumulator fragments, zbar = P Z
-// with the probabilities re-used as the A fragment (FlashAttention-2 register layout).
+// Kernel: one warp per batch row, no shared memory.  Keys are consumed 16 at a time with an online softmax; both GEMMs are
+// mma.sync.m16n8k16 with the 8 heads as the N dimension (a tcgen05 tile would be > 90 % padding at 16 x 8 x 128 per chunk):
+//     S^T[key][head]    = Z[key][dim] . Q^T[dim][head]          A = latent rows straight from global memory (16-byte loads),
+//     zbar^T[dim][head] = Z^T[dim][key] . P^T[key][head]        A = the SAME registers transposed in place by movmatrix.
+// A lane (g = lane/4, t = lane%4) loads z[key g (and g+8)][32*blk + 8t .. +8): the contraction index of the first GEMM is a
+// free permutation, so those four registers serve as two k-steps as they are (the query fragments are loaded with the same
+// permutation); movmatrix.trans of each register yields the A fragment of the second GEMM with the output dims permuted --
+// which lands every lane on 4-byte pieces of contiguous 32-byte runs of zbar in (dim, head) order.
 #pragma once
 #include "common.cuh"
 
-constexpr int ZA_MAX_KEYS = 64;
 constexpr int ZA_WARPS = 4;
 
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+// 8x8 b16 tile held one register per lane (lane (g,t): row g, columns 2t, 2t+1) -> its transpose in the same layout
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
 }
 
 struct ZAttnParams {
-    const bf16* qz; int ldq;            // [B, ldq], head h at column h*LAT (already scaled by 1/sqrt(dk))
-    const bf16* z; long long z_bstride; // [B][keys][LAT]
-    const uint8_t* key_valid; int kv_stride;
-    int n_keys;                         // keys per row (<= ZA_MAX_KEYS)
-    bf16* out; int ldo;                 // [B, ldo]
+    const bf16* qz; int ldq;            // [B, ldq]: columns [0, H*LAT) latent-space queries, head h at h*LAT (already scaled by 1/8);
+                                        //           with condition rows, columns [H*LAT, H*LAT + 64H) = q / 8
+    const bf16* z; long long z_bstride; // [B][n_keys][LAT] latent rows
+    const uint8_t* key_valid; int kv_stride;   // validity of latent key j of row b at key_valid[b*kv_stride + j]
+    int n_keys;
+    const bf16* kvc; int nc;            // condition rows: [B][nc][2*64H] = (Wk u_i | Wv u_i), or nc = 0
+    bf16* out; int ldo;                 // [B, ldo]: columns [0, LAT*H) zbar in (dim, head) order: a*H + h; then 64H columns ac
     int H; int B;
 };
 
 template <int LAT>
 __global__ void __launch_bounds__(ZA_WARPS * 32)
 decode_zattn_kernel(ZAttnParams p) {
-    constexpr int ROWB = LAT * 2 + 16;          // padded smem row: conflict-free fragment loads and ldmatrix rows
-    constexpr int KS = LAT / 16;                // k-steps of the score GEMM
-    constexpr int NTO = LAT / 8;                // n-tiles of the output GEMM
-    extern __shared__ __align__(16) uint8_t za_smem[];
+    constexpr int NB = LAT / 32;                // 32-dim blocks of a latent row (one 16-byte load per lane and block)
+    constexpr float kL2e = 1.4426950408889634f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.x * ZA_WARPS + warp;
     pdl_wait();
     pdl_launch_dependents();
     if (b >= p.B) return;
-    uint8_t* zs = za_smem + (size_t)warp * ZA_MAX_KEYS * ROWB;
-    const uint32_t zs_u = (uint32_t)__cvta_generic_to_shared(zs);
-    // ---- attendable keys: bit j of (vlo, vhi); keys after the last attendable one are never fetched
+    const int H = p.H, d = 64 * H, nkeys = p.n_keys;
+    const bf16* zg = p.z + (size_t)b * p.z_bstride + t * 8;
     const uint8_t* valid = p.key_valid + (size_t)b * p.kv_stride;
-    const uint32_t vlo = __ballot_sync(0xffffffffu, lane < p.n_keys && valid[lane] != 0);
-    const uint32_t vhi = __ballot_sync(0xffffffffu, lane + 32 < p.n_keys && valid[lane + 32] != 0);
-    int nrow = vhi ? 64 - __clz(vhi) : (vlo ? 32 - __clz(vlo) : 0);
-    const bool none = nrow == 0;                // nothing attendable: uniform softmax over all keys (masked_fill -1e9 semantics)
-    if (none) nrow = p.n_keys;
-    const int nrow16 = (nrow + 15) & ~15;
-    // ---- latent rows -> shared memory (16-byte async copies), zero rows up to the next multiple of 16
-    const bf16* zg = p.z + (size_t)b * p.z_bstride;
-    constexpr int CPR = LAT / 8;                // 16-byte chunks per row
-    for (int i = lane; i < nrow16 * CPR; i += 32) {
-        const int r = i / CPR, c = i % CPR;
-        if (r < nrow) cp_async16(zs_u + r * ROWB + c * 16, zg + (size_t)r * LAT + c * 8);
-        else *reinterpret_cast<uint4*>(zs + r * ROWB + c * 16) = make_uint4(0, 0, 0, 0);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    // ---- query fragments (A operand: row = head): a0/a2 rows g, a1/a3 rows g + 8
-    uint32_t qa[KS][4];
+    const bf16* qrow = p.qz + (size_t)b * p.ldq;
+
+    // first chunk of latent rows: issued before anything depends on it (keys 0 .. 15 exist whenever n_keys > them)
+    uint4 za[NB], zb[NB];
     {
-        const bf16* q0 = p.qz + (size_t)b * p.ldq + (size_t)g * LAT + 2 * t;
-        const bf16* q1 = q0 + (size_t)8 * LAT;
-        const bool h0 = g < p.H, h1 = g + 8 < p.H;
+        const bool ia = g < nkeys, ib = g + 8 < nkeys;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            qa[ks][0] = h0 ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16) : 0u;
-            qa[ks][2] = h0 ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + 8) : 0u;
-            qa[ks][1] = h1 ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16) : 0u;
-            qa[ks][3] = h1 ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8) : 0u;
+        for (int k = 0; k < NB; ++k) {
+            za[k] = ia ? ldg_nc16(zg + (size_t)g * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+            zb[k] = ib ? ldg_nc16(zg + (size_t)(g + 8) * LAT + k * 32) : make_uint4(0, 0, 0, 0);
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    // ---- S = Qz Z^T : n-tile nt covers keys nt*8 .. nt*8+7
-    constexpr int NT = ZA_MAX_KEYS / 8;
-    float s[NT][4];
-    const int ntiles = nrow16 >> 3;
+    // query fragments: lane (g,t) = head g, dims 32*blk + 8t .. +8 (same permutation as the latent rows)
+    uint4 q[NB];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        if (nt < ntiles) {
-            const uint8_t* zr = zs + (nt * 8 + g) * ROWB + 4 * t;
+    for (int k = 0; k < NB; ++k) q[k] = (g < H) ? ldg_nc16(qrow + (size_t)g * LAT + k * 32 + t * 8) : make_uint4(0, 0, 0, 0);
+    // last attendable latent key: later ones are never fetched
+    int nrow = 0;
+    for (int j0 = 0; j0 < nkeys; j0 += 32) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, j0 + lane < nkeys && valid[j0 + lane] != 0);
+        if (bal) nrow = j0 + 32 - __clz(bal);
+    }
+    if (nrow == 0 && p.nc == 0) nrow = nkeys;   // nothing attendable: every score is -1e9 -> uniform softmax over all keys (masked_fill semantics)
+
+    // running softmax state of heads 2t (index 0) and 2t+1 (index 1); l is a per-lane partial, reduced over g at the end
+    float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
+    // ---- condition rows: plain dot products; lane owns 16-byte piece(s) pc = lane + 32 j of the 64H-wide row, head pc / 8
+    constexpr int MAXC = 8;
+    float sc[2][MAXC];                          // log2-scaled score of condition row i for the head of piece j, replicated over its 8 lanes
+    const int npieces = 8 * H;                  // 16-byte pieces per 64H row
+    if (p.nc > 0) {
+        const bf16* kv = p.kvc + (size_t)b * p.nc * 2 * d;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(zr + ks * 32);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(zr + ks * 32 + 16);
-                mma_bf16_16816(s[nt], qa[ks], b0, b1);
+        for (int j = 0; j < 2; ++j) {
+            const int pc = lane + 32 * j;
+            f8 qf;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) qf.v[e] = 0.f;
+            if (pc < npieces) qf = ld8(qrow + (size_t)H * LAT + pc * 8);
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                sc[j][i] = -INFINITY;
+                if (i < p.nc) {
+                    float dsum = 0.f;
+                    if (pc < npieces) {
+                        const f8 kf = ld8(kv + (size_t)i * 2 * d + pc * 8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) dsum = fmaf(qf.v[e], kf.v[e], dsum);
+                    }
+                    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+                    dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+                    dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+                    sc[j][i] = dsum * kL2e;      // condition rows are always attendable (src_mask is extended by ones, cvaetf.py:114-116)
+                }
+            }
+        }
+        // fold them into the running state of this lane's two heads
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int h = 2 * t + e;
+            float mx = -INFINITY, vals[MAXC];
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i) {
+                const float v0 = __shfl_sync(0xffffffffu, sc[0][i], (h & 3) * 8), v1 = __shfl_sync(0xffffffffu, sc[1][i], (h & 3) * 8);
+                vals[i] = (i < p.nc && h < H) ? ((h >> 2) ? v1 : v0) : -INFINITY;
+                mx = fmaxf(mx, vals[i]);
+            }
+            if (h < H) {
+                mrun[e] = mx;
+                if (g == 0) {                   // counted once (l is summed over the eight g lanes later)
+#pragma unroll
+                    for (int i = 0; i < MAXC; ++i) if (i < p.nc) lrun[e] += ex2_approx(vals[i] - mx);
+                }
             }
         }
     }
-    // ---- masked softmax over keys; this thread holds keys nt*8 + 2t, +1 of head rows g (c0,c1) and g+8 (c2,c3)
-    constexpr float kL2e = 1.4426950408889634f;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+
+    float acc[2 * NB][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        if (nt < ntiles) {
+    for (int i = 0; i < 2 * NB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+    for (int c0 = 0; c0 < nrow; c0 += 16) {
+        // prefetch the next chunk while this one is consumed
+        uint4 na[NB], nb[NB];
+        {
+            const int ka = c0 + 16 + g, kb = ka + 8;
+            const bool ia = ka < nrow, ib = kb < nrow;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = nt * 8 + 2 * t + e;
-                const bool ok = (j < 32) ? ((vlo >> j) & 1u) : ((vhi >> (j - 32)) & 1u);
-                float v0 = s[nt][e] * kL2e, v1 = s[nt][2 + e] * kL2e;
-                if (!ok) { v0 = -1e9f * kL2e; v1 = -1e9f * kL2e; }
-                if (j >= nrow) { v0 = -INFINITY; v1 = -INFINITY; }
-                s[nt][e] = v0; s[nt][2 + e] = v1;
-                mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+            for (int k = 0; k < NB; ++k) {
+                na[k] = ia ? ldg_nc16(zg + (size_t)ka * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+                nb[k] = ib ? ldg_nc16(zg + (size_t)kb * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        const int ka = c0 + g, kb = ka + 8;
+        const bool ina = ka < nrow, inb = kb < nrow;
+        const bool oka = ina && valid[ka] != 0, okb = inb && valid[kb] != 0;
+        // ---- S^T = Z Q^T (16 keys x 8 heads), k permuted: two k-steps per 32-dim block
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            mma_bf16_16816(s, za[k].x, zb[k].x, za[k].y, zb[k].y, q[k].x, q[k].y);
+            mma_bf16_16816(s, za[k].z, zb[k].z, za[k].w, zb[k].w, q[k].z, q[k].w);
+        }
+        // s[0], s[1]: key ka, heads 2t, 2t+1 ; s[2], s[3]: key kb
+        float pa[2], pb[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float va = ina ? (oka ? s[e] * kL2e : -1e9f * kL2e) : -INFINITY;
+            const float vb = inb ? (okb ? s[2 + e] * kL2e : -1e9f * kL2e) : -INFINITY;
+            float mx = fmaxf(va, vb);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            const float mn = fmaxf(mrun[e], mx);            // finite: the chunk holds at least one in-range key
+            const float corr = ex2_approx(mrun[e] - mn);    // 0 on the first chunk (mrun = -inf)
+            pa[e] = ex2_approx(va - mn);
+            pb[e] = ex2_approx(vb - mn);
+            lrun[e] = lrun[e] * corr + pa[e] + pb[e];
+            mrun[e] = mn;
+#pragma unroll
+            for (int i = 0; i < 2 * NB; ++i) { acc[i][e] *= corr; acc[i][2 + e] *= corr; }
+        }
+        // ---- zbar^T += Z^T P^T : B = transposed probability tiles, A = transposed latent tiles (two 8-dim groups per m-tile)
+        const uint32_t pb0 = movmatrix_trans(pack_bf16x2(pa[0], pa[1]));
+        const uint32_t pb1 = movmatrix_trans(pack_bf16x2(pb[0], pb[1]));
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            mma_bf16_16816(acc[2 * k], movmatrix_trans(za[k].x), movmatrix_trans(za[k].y), movmatrix_trans(zb[k].x), movmatrix_trans(zb[k].y), pb0, pb1);
+            mma_bf16_16816(acc[2 * k + 1], movmatrix_trans(za[k].z), movmatrix_trans(za[k].w), movmatrix_trans(zb[k].z), movmatrix_trans(zb[k].w), pb0, pb1);
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) { za[k] = na[k]; zb[k] = nb[k]; }
+    }
+    // ---- normalise: l over the eight key slots (g); every lane ends with the totals of its two heads
+    float inv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        float l = lrun[e];
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        inv[e] = 1.f / l;
+    }
+    // acc[2k + m][0..1]: dim 32k + 8(g/2) + 4m + (g&1) (+2 for [2..3]), heads 2t, 2t+1  ->  out[dim*H + head]
+    bf16* orow = p.out + (size_t)b * p.ldo;
+    const int dbase = 8 * (g >> 1) + (g & 1);
+#pragma unroll
+    for (int i = 0; i < 2 * NB; ++i) {
+        const int dim0 = 32 * (i >> 1) + 4 * (i & 1) + dbase;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int dim = dim0 + 2 * r;
+            const float v0 = acc[i][2 * r] * inv[0], v1 = acc[i][2 * r + 1] * inv[1];
+            bf16* o = orow + (size_t)dim * H + 2 * t;
+            if (2 * t + 1 < H && (H & 1) == 0) *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v0, v1);
+            else {
+                if (2 * t < H) o[0] = __float2bfloat16(v0);
+                if (2 * t + 1 < H) o[1] = __float2bfloat16(v1);
             }
         }
     }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float l0 = 0.f, l1 = 0.f;
-    uint32_t pa[NT][2];                          // bf16x2 probabilities: [nt][0] row g, [nt][1] row g+8
+    // ---- condition values: ac[head of the piece][8 dims] = sum_i p_i (Wv u_i)
+    if (p.nc > 0) {
+        const bf16* kv = p.kvc + (size_t)b * p.nc * 2 * d + d;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        pa[nt][0] = pa[nt][1] = 0u;
-        if (nt < ntiles) {
-            const float p00 = ex2_approx(s[nt][0] - mx0), p01 = ex2_approx(s[nt][1] - mx0);
-            const float p10 = ex2_approx(s[nt][2] - mx1), p11 = ex2_approx(s[nt][3] - mx1);
-            l0 += p00 + p01; l1 += p10 + p11;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(p00, p01), h1 = __floats2bfloat162_rn(p10, p11);
-            pa[nt][0] = *reinterpret_cast<uint32_t*>(&h0);
-            pa[nt][1] = *reinterpret_cast<uint32_t*>(&h1);
-        }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    // ---- zbar = P Z : k-step kk covers keys kk*16 .. +15 (A = probability fragments), n-tile = 8 latent dims
-    float o[NTO][4];
+        for (int j = 0; j < 2; ++j) {
+            const int pc = lane + 32 * j;
+            const int h = (pc >> 3) < H ? (pc >> 3) : 0;
+            // final (max, 1/l) of head h live on the lanes with t = h / 2 (any g), component h & 1
+            const float m0 = __shfl_sync(0xffffffffu, mrun[0], h >> 1), m1 = __shfl_sync(0xffffffffu, mrun[1], h >> 1);
+            const float i0 = __shfl_sync(0xffffffffu, inv[0], h >> 1), i1 = __shfl_sync(0xffffffffu, inv[1], h >> 1);
+            const float mh = (h & 1) ? m1 : m0, ih = (h & 1) ? i1 : i0;
+            if (pc < npieces) {
+                f8 o;
 #pragma unroll
-    for (int n = 0; n < NTO; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-    const int ksteps = nrow16 >> 4;
-    // ldmatrix.x4.trans: lanes 0-7 / 8-15 address keys kk*16+0..7 / +8..15 of dims n0..n0+7, lanes 16-31 the same keys of dims n0+8..
-    const uint32_t lm_row = zs_u + (uint32_t)((lane & 15) * ROWB + (lane >> 4) * 16);
+                for (int e = 0; e < 8; ++e) o.v[e] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < ZA_MAX_KEYS / 16; ++kk) {
-        if (kk < ksteps) {
-            const uint32_t a[4] = {pa[2 * kk][0], pa[2 * kk][1], pa[2 * kk + 1][0], pa[2 * kk + 1][1]};
+                for (int i = 0; i < MAXC; ++i) {
+                    if (i < p.nc) {
+                        const float pi = ex2_approx(sc[j][i] - mh) * ih;
+                        const f8 vf = ld8(kv + (size_t)i * 2 * d + pc * 8);
 #pragma unroll
-            for (int n2 = 0; n2 < NTO / 2; ++n2) {
-                uint32_t b0, b1, b2, b3;
-                ldmatrix_x4_trans(lm_row + (uint32_t)(kk * 16 * ROWB + n2 * 32), b0, b1, b2, b3);
-                mma_bf16_16816(o[2 * n2], a, b0, b1);
-                mma_bf16_16816(o[2 * n2 + 1], a, b2, b3);
+                        for (int e = 0; e < 8; ++e) o.v[e] = fmaf(pi, vf.v[e], o.v[e]);
+                    }
+                }
+                st8(orow + (size_t)LAT * H + pc * 8, o);
             }
         }
-    }
-    // ---- normalise and store: rows g / g+8 = heads, columns n*8 + 2t, +1
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
-    bf16* o0 = p.out + (size_t)b * p.ldo + (size_t)g * LAT + 2 * t;
-    bf16* o1 = o0 + (size_t)8 * LAT;
-#pragma unroll
-    for (int n = 0; n < NTO; ++n) {
-        if (g < p.H) *reinterpret_cast<__nv_bfloat162*>(o0 + n * 8) = __floats2bfloat162_rn(o[n][0] * i0, o[n][1] * i0);
-        if (g + 8 < p.H) *reinterpret_cast<__nv_bfloat162*>(o1 + n * 8) = __floats2bfloat162_rn(o[n][2] * i1, o[n][3] * i1);
     }
 }
 
 template <int LAT>
 static int launch_decode_zattn_lat(const ZAttnParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)ZA_WARPS * ZA_MAX_KEYS * (LAT * 2 + 16);
-    GCT_SMEM_LIMIT(decode_zattn_kernel<LAT>, smem);
-    GCT_CUDA(launch_k(decode_zattn_kernel<LAT>, dim3((p.B + ZA_WARPS - 1) / ZA_WARPS), dim3(ZA_WARPS * 32), smem, st, true, p));
+    GCT_CUDA(launch_k(decode_zattn_kernel<LAT>, dim3((p.B + ZA_WARPS - 1) / ZA_WARPS), dim3(ZA_WARPS * 32), 0, st, true, p));
     return GCT_OK;
 }
-static bool zattn_supported(int lat, int H, int n_keys) { return (lat == 128 || lat == 64) && H >= 1 && H <= 16 && n_keys >= 1 && n_keys <= ZA_MAX_KEYS; }
+static bool zattn_supported(int lat, int H, int nc) { return (lat == 128 || lat == 64 || lat == 32) && H >= 1 && H <= 8 && nc >= 0 && nc <= 8; }
 static int launch_decode_zattn(const ZAttnParams& p, int lat, cudaStream_t st) {
-    GCT_REQUIRE(zattn_supported(lat, p.H, p.n_keys), "latent-space cross-attention: lat=%d H=%d keys=%d unsupported", lat, p.H, p.n_keys);
-    return lat == 128 ? launch_decode_zattn_lat<128>(p, st) : launch_decode_zattn_lat<64>(p, st);
+    GCT_REQUIRE(zattn_supported(lat, p.H, p.nc) && p.n_keys >= 1, "latent-space cross-attention: lat=%d H=%d nc=%d keys=%d unsupported", lat, p.H, p.nc, p.n_keys);
+    return lat == 128 ? launch_decode_zattn_lat<128>(p, st) : lat == 64 ? launch_decode_zattn_lat<64>(p, st) : launch_decode_zattn_lat<32>(p, st);
 }

@@ -1,8 +1,6 @@
 // C-ABI entry points of libgct_b200.so (declared in include/gct_b200.h).
 #include "model.cuh"
-#ifdef GCT_WITH_NCCL
-#include <nccl.h>
-#endif
+#include <dlfcn.h>
 
 thread_local char g_gct_err[512] = {0};
 int g_gct_simt_only = 0;
@@ -201,7 +199,7 @@ static int forward_impl(const gct_config_t* cfg, const gct_weights_t* w, const g
 template <typename T>
 static int backward_impl(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, const float* dlogits,
                          const float* dmu, const float* dlv, const float* dz, void* ws, size_t ws_bytes, void* scratch,
-                         size_t scratch_bytes, void* stream) {
+                         size_t scratch_bytes, void* stream, StageHook* hook = nullptr) {
     Model<T> m;
     GCT_TRY(m.init(cfg, w, io->seed, io->train, stream));
     Acts<T> A;
@@ -210,7 +208,9 @@ static int backward_impl(const gct_config_t* cfg, const gct_weights_t* w, const 
     BwdScratch<T> S;
     S.carve(*cfg, A, scratch);
     GCT_REQUIRE(S.bytes <= scratch_bytes, "backward: scratch too small (%zu < %zu)", scratch_bytes, S.bytes);
-    return model_backward<T>(m, *io, A, S, dlogits, dmu, dlv, dz);
+    GCT_TRY(model_backward<T>(m, *io, A, S, dlogits, dmu, dlv, dz, hook));
+    if (hook) GCT_TRY(hook->done(2 * cfg->n_layers));
+    return GCT_OK;
 }
 
 extern "C" {
@@ -286,6 +286,63 @@ int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* voc
     return (int64_t)(o - out);
 }
 
+// Host-side target-length sampler (Inference/toklen_sampling.py:4-16 `run_sampling`, one Python iteration per draw in the
+// reference): per draw one np.random.uniform(0,1) -> first CDF edge >= a, then one np.random.normal() for the half-bin jitter.
+// The draws continue NumPy's GLOBAL legacy generator bit for bit: the caller passes np.random.get_state() (MT19937 key / pos /
+// has_gauss / cached_gaussian), this loop advances it exactly like RandomState.uniform / .normal would (random_sample =
+// 53-bit double from two outputs; legacy polar Gaussian with its cached second value) and hands the state back.
+namespace {
+struct Mt { uint32_t* key; int pos; };
+inline void mt_refill(Mt& m) {
+    uint32_t* k = m.key;
+    int i = 0;
+    for (; i < 624 - 397; ++i) { uint32_t y = (k[i] & 0x80000000u) | (k[i + 1] & 0x7fffffffu); k[i] = k[i + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+    for (; i < 623; ++i) { uint32_t y = (k[i] & 0x80000000u) | (k[i + 1] & 0x7fffffffu); k[i] = k[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+    uint32_t y = (k[623] & 0x80000000u) | (k[0] & 0x7fffffffu);
+    k[623] = k[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    m.pos = 0;
+}
+inline uint32_t mt_next(Mt& m) {
+    if (m.pos >= 624) mt_refill(m);
+    uint32_t y = m.key[m.pos++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+inline double mt_double(Mt& m) {
+    const uint32_t a = mt_next(m) >> 5, b = mt_next(m) >> 6;
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+}  // namespace
+int gct_toklen_draw(uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* cached_gauss, const double* cdf, int n_edges,
+                    const double* centres, double width, int64_t n, double* out) {
+    if (!mt_key || !mt_pos || !has_gauss || !cached_gauss || !cdf || !centres || !out || n_edges < 2 || n < 0) {
+        snprintf(g_gct_err, sizeof(g_gct_err), "toklen_draw: bad arguments");
+        return GCT_ERR_ARG;
+    }
+    Mt m{mt_key, *mt_pos};
+    int hg = *has_gauss;
+    double cg = *cached_gauss;
+    const int nb = n_edges - 1;
+    for (int64_t k = 0; k < n; ++k) {
+        const double a = 0.0 + (1.0 - 0.0) * mt_double(m);          // RandomState.uniform(0, 1)
+        int first = 0;                                              // np.argmax(cdf >= a): 0 when no edge qualifies
+        for (int i = 0; i < n_edges; ++i) if (cdf[i] >= a) { first = i; break; }
+        int idx = first - 1;
+        if (idx < 0) idx += nb;                                     // Python's negative index into the bin centres
+        double g;
+        if (hg) { g = cg; hg = 0; cg = 0.0; }
+        else {
+            double x1, x2, r2;
+            do { x1 = 2.0 * mt_double(m) - 1.0; x2 = 2.0 * mt_double(m) - 1.0; r2 = x1 * x1 + x2 * x2; } while (r2 >= 1.0 || r2 == 0.0);
+            const double f = sqrt(-2.0 * log(r2) / r2);
+            cg = f * x1; hg = 1; g = f * x2;
+        }
+        out[k] = centres[idx] + width * g / 2;
+    }
+    *mt_pos = m.pos; *has_gauss = hg; *cached_gauss = cg;
+    return GCT_OK;
+}
+
 // ---------------- input pipeline ----------------
 int gct_collate(const gct_corpus_t* c, const int64_t* rows, int B, int S, int T, int pad_src, int pad_trg, int sos_id, int eos_id,
                 int sep_src, int sep_trg, int64_t* src, int64_t* trg, float* econds_out, float* dconds_out, void* stream) {
@@ -354,8 +411,9 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
 }
 int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
 int gct_decode_begin_launches(const gct_config_t* cfg, int Lz) {
-    if (cfg->dtype != GCT_DTYPE_F32 && DecodeWs<bf16>::want_zmode(*cfg, Lz)) return 2 + cfg->n_layers * (4 + 3 * cfg->heads);
-    return 3 + 2 * cfg->n_layers + (cfg->nconds > 0 ? 1 : 0);
+    const int nck = (cfg->use_cond2lat && cfg->nconds > 0 && !cfg->use_cond2dec) ? 1 : 0;
+    if (cfg->dtype != GCT_DTYPE_F32 && DecodeWs<bf16>::want_zmode(*cfg, Lz)) return 2 + nck + cfg->n_layers * (5 + 3 * cfg->heads + 4 * nck);
+    return 3 + 2 * cfg->n_layers + nck;
 }
 
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,
@@ -369,15 +427,129 @@ int gct_decode_attention(const void* q, int ldq, const void* knew, const void* v
     return dtype == GCT_DTYPE_F32 ? launch_decode_attn<float>(p, B, ST(stream)) : launch_decode_attn<bf16>(p, B, ST(stream));
 }
 
-int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream) {
-#ifdef GCT_WITH_NCCL
-    ncclResult_t r = ncclAllReduce(grads, grads, (size_t)n, ncclFloat, ncclSum, reinterpret_cast<ncclComm_t>(nccl_comm), ST(stream));
-    if (r != ncclSuccess) GCT_FAIL(GCT_ERR_CUDA, "ncclAllReduce: %s", ncclGetErrorString(r));
+// ---------------- data-parallel gradient exchange (train1.py:111-112 DDP) ----------------
+// NCCL is resolved at run time from the libnccl.so.2 the process already holds (PyTorch's), so the library has no link-time
+// dependency and never brings a second NCCL into the process.
+}  // extern "C"
+namespace {
+typedef struct { char internal[128]; } nccl_uid_t;
+struct Nccl {
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+Nccl& nccl() {
+    static Nccl n;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (n.ok) return n;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return n;
+#define GCT_SYM(name) *(void**)(&n.name) = dlsym(h, "nccl" #name)
+    GCT_SYM(GetUniqueId); GCT_SYM(CommInitRank); GCT_SYM(CommDestroy); GCT_SYM(AllReduce); GCT_SYM(GroupStart); GCT_SYM(GroupEnd);
+    GCT_SYM(GetErrorString);
+#undef GCT_SYM
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.GroupStart && n.GroupEnd && n.GetErrorString;
+    return n;
+}
+#define GCT_NCCL(expr)                                                                                                  \
+    do {                                                                                                                \
+        int r_ = (expr);                                                                                                \
+        if (r_ != 0) GCT_FAIL(GCT_ERR_CUDA, "%s -> %s", #expr, nccl().GetErrorString(r_));                              \
+    } while (0)
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;
+
+// Gradient buckets keyed by the backward stage after which they are final.
+struct DpHook : StageHook {
+    void* comm; cudaStream_t st, cs; float* grads; const gct_bucket_t* buckets; int n_buckets;
+    cudaEvent_t ev[2 * 16 + 2];
+    int done(int stage) override {
+        Nccl& n = nccl();
+        bool any = false;
+        for (int i = 0; i < n_buckets; ++i) any |= buckets[i].stage == stage;
+        if (!any) return GCT_OK;
+        GCT_CUDA(cudaEventRecord(ev[stage], st));
+        GCT_CUDA(cudaStreamWaitEvent(cs, ev[stage], 0));
+        GCT_NCCL(n.GroupStart());
+        for (int i = 0; i < n_buckets; ++i)
+            if (buckets[i].stage == stage && buckets[i].count > 0)
+                GCT_NCCL(n.AllReduce(grads + buckets[i].offset, grads + buckets[i].offset, (size_t)buckets[i].count, NCCL_FLOAT32, NCCL_SUM,
+                                     comm, cs));
+        GCT_NCCL(n.GroupEnd());
+        return GCT_OK;
+    }
+};
+// events are created once per (device) and reused: cudaEventDisableTiming events are cheap to record / wait on
+int dp_events(cudaEvent_t* out, int n) {
+    static cudaEvent_t ev[GCT_MAX_DEVICES][2 * 16 + 2];
+    static bool made[GCT_MAX_DEVICES] = {};
+    const int dev = gct_cur_device();
+    if (!made[dev]) {
+        for (int i = 0; i < 2 * 16 + 2; ++i) GCT_CUDA(cudaEventCreateWithFlags(&ev[dev][i], cudaEventDisableTiming));
+        made[dev] = true;
+    }
+    for (int i = 0; i < n; ++i) out[i] = ev[dev][i];
     return GCT_OK;
-#else
-    (void)nccl_comm; (void)grads; (void)n; (void)stream;
-    GCT_FAIL(GCT_ERR_UNSUPPORTED, "built without NCCL");
-#endif
+}
+}  // namespace
+extern "C" {
+
+int gct_nccl_unique_id(void* out128) {
+    GCT_REQUIRE(out128, "nccl_unique_id: null argument");
+    if (!nccl().ok) GCT_FAIL(GCT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+    GCT_NCCL(nccl().GetUniqueId(reinterpret_cast<nccl_uid_t*>(out128)));
+    return GCT_OK;
+}
+int gct_nccl_comm_init(void** comm, int nranks, int rank, const void* id128) {
+    GCT_REQUIRE(comm && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "nccl_comm_init: bad arguments");
+    if (!nccl().ok) GCT_FAIL(GCT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+    nccl_uid_t id;
+    memcpy(&id, id128, sizeof(id));
+    GCT_NCCL(nccl().CommInitRank(comm, nranks, id, rank));
+    return GCT_OK;
+}
+int gct_nccl_comm_destroy(void* comm) {
+    if (!comm) return GCT_OK;
+    if (!nccl().ok) GCT_FAIL(GCT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+    GCT_NCCL(nccl().CommDestroy(comm));
+    return GCT_OK;
+}
+int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream) {
+    GCT_REQUIRE(nccl_comm && grads && n >= 0, "allreduce_grads: bad arguments");
+    if (!nccl().ok) GCT_FAIL(GCT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+    GCT_NCCL(nccl().AllReduce(grads, grads, (size_t)n, NCCL_FLOAT32, NCCL_SUM, nccl_comm, ST(stream)));
+    return GCT_OK;
+}
+int gct_backward_dp(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, const float* dlogits, const float* dmu,
+                    const float* dlog_var, const float* dz, void* workspace, size_t workspace_bytes, void* scratch,
+                    size_t scratch_bytes, void* nccl_comm, const gct_bucket_t* buckets_host, int n_buckets, void* comm_stream,
+                    void* stream) {
+    GCT_REQUIRE(cfg && w && io && workspace && scratch && nccl_comm && buckets_host && n_buckets > 0 && comm_stream,
+                "backward_dp: null argument");
+    GCT_REQUIRE(w->grads_f32, "backward_dp: gradient buffer missing");
+    if (!nccl().ok) GCT_FAIL(GCT_ERR_UNSUPPORTED, "libnccl.so.2 is not loadable in this process");
+    const int nstages = 2 * cfg->n_layers + 1;
+    for (int i = 0; i < n_buckets; ++i)
+        GCT_REQUIRE(buckets_host[i].stage >= 0 && buckets_host[i].stage < nstages, "backward_dp: bucket %d has stage %d outside [0,%d)", i,
+                    buckets_host[i].stage, nstages);
+    DpHook hook;
+    hook.comm = nccl_comm; hook.st = ST(stream); hook.cs = ST(comm_stream); hook.grads = w->grads_f32; hook.buckets = buckets_host;
+    hook.n_buckets = n_buckets;
+    GCT_TRY(dp_events(hook.ev, nstages + 1));
+    int rc = cfg->dtype == GCT_DTYPE_F32
+                 ? backward_impl<float>(cfg, w, io, dlogits, dmu, dlog_var, dz, workspace, workspace_bytes, scratch, scratch_bytes, stream, &hook)
+                 : backward_impl<bf16>(cfg, w, io, dlogits, dmu, dlog_var, dz, workspace, workspace_bytes, scratch, scratch_bytes, stream, &hook);
+    if (rc != GCT_OK) return rc;
+    // the compute stream continues (optimiser step) only after every bucket has been reduced
+    GCT_CUDA(cudaEventRecord(hook.ev[nstages], hook.cs));
+    GCT_CUDA(cudaStreamWaitEvent(hook.st, hook.ev[nstages], 0));
+    return GCT_OK;
 }
 
 }  // extern "C"

@@ -478,9 +478,17 @@ static int ffn_backward(Model<T>& m, BwdScratch<T>& S, int M, const float* dout,
     return GCT_OK;
 }
 
+// Called by model_backward when a group of gradients is final: stage k < N = decoder layer N-1-k, stage N+k = encoder layer
+// N-1-k, stage 2N = everything (embeddings, heads, final norms).  The data-parallel backward (gct_backward_dp) uses it to
+// start the gradient exchange of that group on the communication stream while the rest of the backward runs.
+struct StageHook {
+    virtual int done(int stage) = 0;
+    virtual ~StageHook() {}
+};
+
 template <typename T>
 static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratch<T>& S, const float* dlogits,
-                          const float* dmu, const float* dlv, const float* dz_ext) {
+                          const float* dmu, const float* dlv, const float* dz_ext, StageHook* hook = nullptr) {
     const int d = m.d, lat = m.lat, nc = m.nc, N = m.N;
     const int B = A.B, Se = A.Se, Sm = A.Sm, Ld = A.Ld, Me = A.Me, Mm = A.Mm, Md = A.Md, V = m.c.trg_vocab, Vpad = A.Vpad;
     cudaStream_t st = m.st;
@@ -560,6 +568,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             else
                 GCT_TRY(m.norm_bwd(yin, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), other, dy, third, Md));
             float* t = dy; dy = third; third = t;
+            if (hook) GCT_TRY(hook->done(N - 1 - l));
         }
         // decoder embedding (+ cond2dec tokens)
         {
@@ -640,6 +649,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                                m.site(S_ENC_BASE + (l - 1) * ES_COUNT + ES_DROP2), m.G(m.enc_slot(l - 1, E_F2_B))));
         else
             GCT_TRY(m.norm_bwd(xin, m.enc_slot(l, E_N1A), m.enc_slot(l, E_N1B), other, nullptr, dx, Me));
+        if (hook) GCT_TRY(hook->done(N + N - 1 - l));
     }
     {
         dim3 grid(cdiv((long long)B * A.S, EMB_BWD_ROWS), cdiv(d, 128));
@@ -661,38 +671,48 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
 template <typename T>
 struct DecodeWs {
     int B, Lz, Sm, Lmax;
-    bool zmode;                     // cross-attention in latent space (decode_zattn.cuh): no per-layer K/V of the memory
-    T* zpad; T* mem; T* kx; T* vx;  // cross-attention keys / values: [N][B*Sm][d] each (K/V form only)
+    bool zmode;                     // cross-attention in latent space (decode_zattn.cuh): no per-layer K/V of the latent rows
+    int nck;                        // condition rows of the memory (use_cond2lat), 0 otherwise
+    int KZ;                         // width of the latent-space query / context vectors: H*lat (+ d with condition rows)
+    T* zpad; T* mem; T* kx; T* vx;  // K/V form: zpad [B][Sm][lat] (cond rows zero), memory, cross keys / values [N][B*Sm][d]
     T* kc; T* vc;                   // [N][B][Lmax][d]
     float* x; T* xn; T* qkv; T* att; T* q2; T* hbuf; float* logits;
     uint8_t* key_valid; uint8_t* cross_mask; uint8_t* done;
-    // latent-space form: folded projections (per layer) and their scratch
-    T* wqz; float* bqz; T* woz; float* boz;      // [N][H*lat][d], [N][H*lat], [N][d][H*lat], [N][d]
-    float* mk; float* mv; float* tvec;           // (Wk Wz) [d][lat], (Wv Wz) [d][lat], Wv bz + bv [d]
-    T* qz; T* zbar;                              // [B][H*lat]
+    // latent-space form: zlat [B][Lz][lat]; folded projections (per layer) and their scratch
+    T* zlat;
+    T* wqz; float* bqz; T* woz; float* boz;      // [N][KZ][d], [N][KZ], [N][d][KZ], [N][d]
+    float* mk; float* mv; float* tvec; T* wtmp;  // (Wk Wz) [d][lat], (Wv Wz) [d][lat], Wv bz + bv [d], Woz in head-major order [d][H*lat]
+    T* ucond; T* kvc;                            // condition rows minus bz [B*nc][d]; their per-layer (K | V) [N][B*nc][2d]
+    T* qz; T* zbar;                              // [B][KZ]
     size_t bytes;
     static bool want_zmode(const gct_config_t& c, int Lz_) {
-        const bool cond_rows = c.use_cond2lat && c.nconds > 0 && !c.use_cond2dec;
-        return sizeof(T) == 2 && g_gct_zattn && !cond_rows && zattn_supported(c.latent_dim, c.heads, Lz_);
+        (void)Lz_;
+        const int nck_ = (c.use_cond2lat && c.nconds > 0 && !c.use_cond2dec) ? c.nconds : 0;
+        return sizeof(T) == 2 && g_gct_zattn && zattn_supported(c.latent_dim, c.heads, nck_);
     }
     void carve(const gct_config_t& c, int B_, int Lz_, int max_len, void* ws) {
         Bump bp(ws);
         B = B_; Lz = Lz_; Lmax = max_len;
         const int d = c.d_model, nc = c.nconds, N = c.n_layers, lat = c.latent_dim, HL = c.heads * c.latent_dim;
-        Sm = Lz + ((c.use_cond2lat && nc > 0 && !(c.use_cond2dec)) ? nc : 0);
+        nck = (c.use_cond2lat && nc > 0 && !(c.use_cond2dec)) ? nc : 0;
+        Sm = Lz + nck;
         zmode = want_zmode(c, Lz_);
-        zpad = bp.arr<T>((size_t)B * Sm * lat);
-        mem = kx = vx = nullptr;
-        wqz = woz = qz = zbar = nullptr; bqz = boz = mk = mv = tvec = nullptr;
+        KZ = HL + (nck ? d : 0);
+        zpad = mem = kx = vx = zlat = nullptr;
+        wqz = woz = qz = zbar = wtmp = ucond = kvc = nullptr; bqz = boz = mk = mv = tvec = nullptr;
         if (!zmode) {
+            zpad = bp.arr<T>((size_t)B * Sm * lat);
             mem = bp.arr<T>((size_t)B * Sm * d);
             kx = bp.arr<T>((size_t)N * B * Sm * d);
             vx = bp.arr<T>((size_t)N * B * Sm * d);
         } else {
-            wqz = bp.arr<T>((size_t)N * HL * d); bqz = bp.arr<float>((size_t)N * HL);
-            woz = bp.arr<T>((size_t)N * d * HL); boz = bp.arr<float>((size_t)N * d);
+            zlat = bp.arr<T>((size_t)B * Lz * lat);
+            wqz = bp.arr<T>((size_t)N * KZ * d); bqz = bp.arr<float>((size_t)N * KZ);
+            woz = bp.arr<T>((size_t)N * d * KZ); boz = bp.arr<float>((size_t)N * d);
             mk = bp.arr<float>((size_t)d * lat); mv = bp.arr<float>((size_t)d * lat); tvec = bp.arr<float>(d);
-            qz = bp.arr<T>((size_t)B * HL); zbar = bp.arr<T>((size_t)B * HL);
+            wtmp = bp.arr<T>((size_t)d * HL);
+            qz = bp.arr<T>((size_t)B * KZ); zbar = bp.arr<T>((size_t)B * KZ);
+            if (nck) { ucond = bp.arr<T>((size_t)B * nck * d); kvc = bp.arr<T>((size_t)N * B * nck * 2 * d); }
         }
         kc = bp.arr<T>((size_t)N * B * Lmax * d);
         vc = bp.arr<T>((size_t)N * B * Lmax * d);
@@ -705,12 +725,44 @@ struct DecodeWs {
     }
 };
 
+// dst[r, c] = T(scale * src[r, c])   (row pitches in elements)
+template <typename T>
+__global__ void scale_copy2d_kernel(const float* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int rows, int cols,
+                                    float scale) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(size_t)r * dst_ld + c] = from_f<T>(scale * src[(size_t)r * src_ld + c]);
+}
+// head-major [rows][H*lat] -> (dim, head) order: dst[r, a*H + h] = src[r, h*lat + a]
+template <typename T>
+__global__ void head_to_dim_major_kernel(const T* __restrict__ src, T* __restrict__ dst, int dst_ld, int rows, int H, int lat) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * H * lat) return;
+    const int r = (int)(i / (H * lat)), c = (int)(i % (H * lat));
+    const int a = c / H, h = c % H;
+    dst[(size_t)r * dst_ld + c] = src[(size_t)r * H * lat + (size_t)h * lat + a];
+}
+// u[b*nc + j, c] = embed_cond2lat(dconds)[b, j, c] - bz[c]   (condition rows of the memory relative to fc_z's bias)
+template <typename T>
+__global__ void cond_u_kernel(const float* __restrict__ conds, const float* __restrict__ W, const float* __restrict__ Bv,
+                              const float* __restrict__ bz, int nc, int d, T* __restrict__ u) {
+    const int b = blockIdx.x / nc, j = blockIdx.x % nc;
+    T* o = u + (size_t)blockIdx.x * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float* w = W + ((size_t)j * d + c) * nc;
+        float v = Bv[(size_t)j * d + c] - bz[c];
+        for (int k = 0; k < nc; ++k) v = fmaf(w[k], conds[(size_t)b * nc + k], v);
+        o[c] = from_f<T>(v);
+    }
+}
+
 // Folds fc_z and the cross-attention k / v / out projections of every decoder layer into the two latent-space
 // operands of decode_zattn.cuh.  fp32 SIMT GEMMs over the master weights (about 0.8 GFLOP, once per decode call);
 // results are rounded once to the operand type.  nn.Linear weights are [out, in] row-major.
 template <typename T>
 static int decode_zprep(Model<T>& m, DecodeWs<T>& W) {
-    const int d = m.d, lat = m.lat, N = m.N, H = m.H, HL = H * lat;
+    const int d = m.d, lat = m.lat, N = m.N, H = m.H, HL = H * lat, KZ = W.KZ;
     cudaStream_t st = m.st;
     const float* Wz = m.P(GCT_SLOT_FCZ_W);      // [d, lat]
     const float* bz = m.P(GCT_SLOT_FCZ_B);
@@ -719,6 +771,8 @@ static int decode_zprep(Model<T>& m, DecodeWs<T>& W) {
         const float* Wk = m.P(m.dec_slot(l, D_KV2_W)); const float* Wv = Wk + (size_t)d * d;
         const float* bv = m.P(m.dec_slot(l, D_KV2_B)) + d;
         const float* Wo = m.P(m.dec_slot(l, D_O2_W)); const float* bo = m.P(m.dec_slot(l, D_O2_B));
+        T* wqz = W.wqz + (size_t)l * KZ * d; float* bqz = W.bqz + (size_t)l * KZ;
+        T* woz = W.woz + (size_t)l * d * KZ;
         {   // mk[c, a] = sum_m Wk[c, m] Wz[m, a] ;  mv likewise
             Epilogue e = Model<T>::epi(nullptr, lat); e.out32 = W.mk;
             GCT_TRY((launch_gemm_simt<float, float, float>(Wk, d, 1, Wz, 1, lat, d, lat, d, 1, e, st)));
@@ -735,16 +789,31 @@ static int decode_zprep(Model<T>& m, DecodeWs<T>& W) {
             const float* mkh = W.mk + (size_t)h * 64 * lat;
             const float* mvh = W.mv + (size_t)h * 64 * lat;
             {   // Wqz[h*lat + a, n] = (1/8) sum_i mk[h*64+i, a] Wq[h*64+i, n]
-                Epilogue e = Model<T>::epi(nullptr, d); e.alpha = 0.125f; e.outT = W.wqz + ((size_t)l * HL + (size_t)h * lat) * d;
+                Epilogue e = Model<T>::epi(nullptr, d); e.alpha = 0.125f; e.outT = wqz + (size_t)h * lat * d;
                 GCT_TRY((launch_gemm_simt<float, float, T>(mkh, 1, lat, Wq + (size_t)h * 64 * d, 1, d, lat, d, 64, 1, e, st)));
                 // bqz[h*lat + a] = (1/8) sum_i mk[h*64+i, a] bq[h*64+i]
-                Epilogue eb = Model<T>::epi(nullptr, 1); eb.alpha = 0.125f; eb.out32 = W.bqz + (size_t)l * HL + (size_t)h * lat;
+                Epilogue eb = Model<T>::epi(nullptr, 1); eb.alpha = 0.125f; eb.out32 = bqz + (size_t)h * lat;
                 GCT_TRY((launch_gemm_simt<float, float, float>(mkh, 1, lat, bq + h * 64, 0, 1, lat, 1, 64, 1, eb, st)));
             }
-            {   // Woz[n, h*lat + a] = sum_i Wo[n, h*64+i] mv[h*64+i, a]
-                Epilogue e = Model<T>::epi(nullptr, HL); e.outT = W.woz + (size_t)l * d * HL + (size_t)h * lat;
+            {   // Woz (head-major scratch)[n, h*lat + a] = sum_i Wo[n, h*64+i] mv[h*64+i, a]
+                Epilogue e = Model<T>::epi(nullptr, HL); e.outT = W.wtmp + (size_t)h * lat;
                 GCT_TRY((launch_gemm_simt<float, float, T>(Wo + h * 64, d, 1, mvh, 1, lat, d, lat, 64, 1, e, st)));
             }
+        }
+        // the kernel writes zbar in (dim, head) order: permute the contraction index of Woz to match
+        head_to_dim_major_kernel<T><<<cdiv((size_t)d * HL, 256), 256, 0, st>>>(W.wtmp, woz, KZ, d, H, lat);
+        GCT_LAUNCH_CHECK();
+        if (W.nck) {
+            // raw queries / 8 as extra output columns of the q GEMM, Wo as extra contraction columns of the out GEMM
+            scale_copy2d_kernel<T><<<cdiv((size_t)d * d, 256), 256, 0, st>>>(Wq, d, wqz + (size_t)HL * d, d, d, d, 0.125f);
+            GCT_LAUNCH_CHECK();
+            scale_copy2d_kernel<float><<<cdiv(d, 256), 256, 0, st>>>(bq, d, bqz + HL, d, 1, d, 0.125f);
+            GCT_LAUNCH_CHECK();
+            scale_copy2d_kernel<T><<<cdiv((size_t)d * d, 256), 256, 0, st>>>(Wo, d, woz + HL, KZ, d, d, 1.f);
+            GCT_LAUNCH_CHECK();
+            // (K | V) of the condition rows: u [B*nc, d] x (Wk ; Wv)^T, no bias (the constants live in boz / cancel in the softmax)
+            Epilogue e = Model<T>::epi(nullptr, 2 * d); e.outT = W.kvc + (size_t)l * W.B * W.nck * 2 * d;
+            GCT_TRY(m.gemm(W.ucond, false, d, m.WT(m.dec_slot(l, D_KV2_W)), false, d, W.B * W.nck, 2 * d, d, e));
         }
     }
     return GCT_OK;
@@ -758,13 +827,20 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
     GCT_REQUIRE(D.zs && D.src_mask && D.ys && D.status, "decode: zs / src_mask / ys / status missing");
     GCT_REQUIRE(D.prefix_len >= 1 && D.prefix_len <= D.max_len, "decode: bad prefix length");
     GCT_REQUIRE(D.max_len <= 200 && Sm <= DEC_MAX_KEYS, "decode: max_len %d > 200 or memory length %d > %d", D.max_len, Sm, DEC_MAX_KEYS);
-    zpad_kernel<T><<<cdiv((size_t)B * Sm * lat, 256), 256, 0, st>>>(D.zs, B, Lz, Sm, lat, W.zpad);
-    GCT_LAUNCH_CHECK();
     cross_mask_kernel<<<cdiv(B * Sm, 256), 256, 0, st>>>(D.src_mask, B, Lz, Sm, W.cross_mask);
     GCT_LAUNCH_CHECK();
     if (W.zmode) {
+        zpad_kernel<T><<<cdiv((size_t)B * Lz * lat, 256), 256, 0, st>>>(D.zs, B, Lz, Lz, lat, W.zlat);      // plain cast: latent rows only
+        GCT_LAUNCH_CHECK();
+        if (W.nck) {
+            GCT_REQUIRE(D.dconds, "decode: dconds missing");
+            cond_u_kernel<T><<<B * nc, 128, 0, st>>>(D.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), m.P(GCT_SLOT_FCZ_B), nc, d, W.ucond);
+            GCT_LAUNCH_CHECK();
+        }
         GCT_TRY(decode_zprep(m, W));
     } else {
+        zpad_kernel<T><<<cdiv((size_t)B * Sm * lat, 256), 256, 0, st>>>(D.zs, B, Lz, Sm, lat, W.zpad);
+        GCT_LAUNCH_CHECK();
         GCT_TRY(m.linear_T(W.zpad, B * Sm, lat, GCT_SLOT_FCZ_W, GCT_SLOT_FCZ_B, d, W.mem));
         if (Sm > Lz) {
             GCT_REQUIRE(D.dconds, "decode: dconds missing");
@@ -812,18 +888,19 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
         if constexpr (sizeof(T) == 2) {
             if (W.zmode) {
                 // cross-attention in latent space (decode_zattn.cuh): q and out projections carry the folded k / v / fc_z
-                const int HL = m.H * m.lat;
+                const int KZ = W.KZ;
                 {
-                    Epilogue e = Model<T>::epi(W.bqz + (size_t)l * HL, HL); e.outT = W.qz;
-                    GCT_TRY(m.gemm(W.xn, false, d, W.wqz + (size_t)l * HL * d, false, d, B, HL, d, e));
+                    Epilogue e = Model<T>::epi(W.bqz + (size_t)l * KZ, KZ); e.outT = W.qz;
+                    GCT_TRY(m.gemm(W.xn, false, d, W.wqz + (size_t)l * KZ * d, false, d, B, KZ, d, e));
                 }
                 ZAttnParams zp;
-                zp.qz = W.qz; zp.ldq = HL; zp.z = W.zpad; zp.z_bstride = (long long)Sm * m.lat; zp.key_valid = W.cross_mask;
-                zp.kv_stride = Sm; zp.n_keys = Sm; zp.out = W.zbar; zp.ldo = HL; zp.H = m.H; zp.B = B;
+                zp.qz = W.qz; zp.ldq = KZ; zp.z = W.zlat; zp.z_bstride = (long long)W.Lz * m.lat; zp.key_valid = W.cross_mask + W.nck;
+                zp.kv_stride = Sm; zp.n_keys = W.Lz; zp.kvc = W.nck ? W.kvc + (size_t)l * B * W.nck * 2 * d : nullptr; zp.nc = W.nck;
+                zp.out = W.zbar; zp.ldo = KZ; zp.H = m.H; zp.B = B;
                 GCT_TRY(launch_decode_zattn(zp, m.lat, st));
                 {
                     Epilogue e = Model<T>::epi(W.boz + (size_t)l * d, d); e.res32 = W.x; e.out32 = W.x;
-                    GCT_TRY(m.gemm(W.zbar, false, HL, W.woz + (size_t)l * d * HL, false, HL, B, d, HL, e));
+                    GCT_TRY(m.gemm(W.zbar, false, KZ, W.woz + (size_t)l * d * KZ, false, KZ, B, d, KZ, e));
                 }
             }
         }

@@ -200,6 +200,12 @@ int gct_decode_begin_launches(const gct_config_t* cfg, int Lz);
  * voff[V+1]) are joined, each row ends with '\n'.  out_bytes >= n*(width*max_token_bytes+1).  Returns bytes written. */
 int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* vocab, const int32_t* voff, int V, int eos_id,
                        int sos_id, char* out, int64_t out_bytes);
+/* Host-side target-length sampler (replaces the per-draw Python loop of Inference/toklen_sampling.py:4-16): n draws from the
+ * histogram CDF (`cdf[n_edges]`, bin `centres[n_edges-1]`, bin `width`) with the reference's half-bin Gaussian jitter, consuming
+ * NumPy's global legacy MT19937 stream exactly like np.random.uniform / np.random.normal would (state passed in and returned:
+ * key[624], pos, has_gauss, cached_gaussian = np.random.get_state()[1:5]).  out[n] doubles. */
+int gct_toklen_draw(uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* cached_gauss, const double* cdf, int n_edges,
+                    const double* centres, double width, int64_t n, double* out);
 /* the step's attention kernel on its own (unit tests, roofline timing): one query per (batch, head) over
  * n_cached cached keys (+ this step's knew/vnew row, which is appended to the cache when non-NULL) */
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,
@@ -226,10 +232,25 @@ int gct_collate(const gct_corpus_t* corpus, const int64_t* rows, int B, int S, i
                 int eos_id, int sep_src, int sep_trg, int64_t* src, int64_t* trg, float* econds_out, float* dconds_out,
                 void* stream);      /* sep_src < 0: no scaffold prefix */
 
-/* ---- data-parallel gradient exchange (train1.py:111-112 DDP) --------------------------------- */
-/* in-place sum over ranks through NCCL; comm is an ncclComm_t created by the host.  Returns
- * GCT_ERR_UNSUPPORTED if the library was built without NCCL (the host then uses torch.distributed). */
+/* ---- data-parallel gradient exchange (train1.py:111-112: DistributedDataParallel over NCCL) ------------------------ */
+/* The host owns the rendezvous (torch.distributed carries the 128-byte id from rank 0 to the others) and the communicator
+ * handle; NCCL itself is resolved at run time from the libnccl.so.2 already loaded in the process (PyTorch's), so the
+ * library has no link-time NCCL dependency.  All return GCT_ERR_UNSUPPORTED when no libnccl.so.2 can be found. */
+int gct_nccl_unique_id(void* out128);                                        /* rank 0: ncclGetUniqueId                  */
+int gct_nccl_comm_init(void** comm, int nranks, int rank, const void* id128); /* every rank: ncclCommInitRank (collective) */
+int gct_nccl_comm_destroy(void* comm);
+/* in-place sum over ranks of a flat fp32 buffer on `stream` */
 int gct_allreduce_grads(void* nccl_comm, float* grads, int64_t n, void* stream);
+/* gct_backward with the gradient exchange overlapped: the flat gradient buffer is cut into buckets, each tagged with the
+ * backward stage after which it is final (stage k < N: decoder layer N-1-k; N+k: encoder layer N-1-k; 2N: the rest --
+ * embeddings, heads, final norms).  After each stage an event is recorded on `stream`, `comm_stream` waits for it and the
+ * stage's buckets are all-reduced (sum) there while the backward continues; on return `stream` has been made to wait for the
+ * last bucket, so the optimiser step can be enqueued directly.  DDP's bucketed overlap (train1.py:111) in one call. */
+typedef struct { int32_t stage; int32_t reserved; int64_t offset; int64_t count; } gct_bucket_t;
+int gct_backward_dp(const gct_config_t* cfg, const gct_weights_t* w, const gct_io_t* io, const float* dlogits, const float* dmu,
+                    const float* dlog_var, const float* dz, void* workspace, size_t workspace_bytes, void* scratch,
+                    size_t scratch_bytes, void* nccl_comm, const gct_bucket_t* buckets_host, int n_buckets, void* comm_stream,
+                    void* stream);
 
 #ifdef __cplusplus
 }

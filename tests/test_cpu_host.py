@@ -190,3 +190,52 @@ def test_fused_trainer_rejects_the_property_head():
     m = Cvaetf(32, 32, nconds=3, use_cond2dec=True, dropout=0.1, **ARCH_SMALL)
     with pytest.raises(GctError):
         FusedTrainer(m, "pvaetf")
+
+
+def test_host_toklen_draw_continues_numpys_global_stream(built):
+    """gct_toklen_draw (C loop in the library) == the reference's per-draw Python loop bit for bit, including a pending
+    cached Gaussian on entry, and leaves np.random in the identical state (the next draws agree)."""
+    from gct_plus_b200.Inference import toklen_sampling as T
+    data = load_golden("misc")["toklen_data"]
+    nb = int(data.max() - data.min())
+    counts, edges = np.histogram(data, bins=nb)
+    width = np.diff(edges)[0]
+    centres = edges[:-1] + 0.5 * width
+    cdf = np.zeros_like(edges)
+    cdf[1:] = np.cumsum(counts / np.sum(counts))
+    for seed, size, pending in ((11, 64, False), (3, 5001, True), (5, 1, True), (9, 0, False)):
+        res = []
+        for fn in (lambda: T.tokenlen_gen_from_data_distribution(data, size, nb), lambda: T._python_loop(cdf, centres, width, size)):
+            np.random.seed(seed)
+            if pending:
+                np.random.normal()              # leaves the second value of the polar pair cached
+            out = fn()
+            res.append((out, np.random.uniform(), np.random.normal(), np.random.randint(1 << 30)))
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:], (seed, size)
+
+
+def test_gradient_buckets_cover_the_flat_buffer_once_and_follow_the_backward_order():
+    """Bucket table of the overlapped DP exchange (gct_backward_dp): every element of the flat gradient buffer belongs to
+    exactly one bucket, a layer's parameters sit in that layer's bucket, and stages run decoder N-1..0, encoder N-1..0, rest."""
+    import gct_plus_b200._lib as L
+    from gct_plus_b200.Model import Cvaetf, Vaetf
+    from gct_plus_b200.Train.dp import gradient_buckets
+    for m in (Cvaetf(32, 32, nconds=3, use_cond2lat=True, dropout=0.1, **ARCH_SMALL), Vaetf(32, 32, nconds=0, dropout=0.1, **ARCH_SMALL)):
+        N, total = len(m.encoder.layers), m._flat.numel()
+        bk = gradient_buckets(m._offsets, N, total, L.NUM_GLOBAL_SLOTS, L.ENC_LAYER_SLOTS, L.DEC_LAYER_SLOTS)
+        cover = np.zeros(total, dtype=np.int32)
+        stage_of = np.full(total, -1)
+        for stage, off, cnt in bk:
+            cover[off:off + cnt] += 1
+            stage_of[off:off + cnt] = stage
+        assert (cover == 1).all()
+        for (name, _), (off, n, _) in zip(m.named_parameters(), m._grad_views):
+            st = set(stage_of[off:off + n].tolist())
+            assert len(st) == 1, name
+            st = st.pop()
+            parts = name.split(".")
+            if parts[1] == "layers":
+                l = int(parts[2])
+                assert st == (N - 1 - l if parts[0] == "decoder" else 2 * N - 1 - l), name
+            else:
+                assert st == 2 * N, name
