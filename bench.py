@@ -4,13 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one synthetic batch:
-  * sampling: one sample_smiles call = one batch of --batch latent draws (default 30000 = cfg 2's 30k draws in one call;
-    the reference driver's -batch_size flag, whose default is 512, is also measured and reported under "batch512")
-    decoded to max_strlen=100 (99 KV-cached multinomial steps), vaetf;
-  * training (reported under "train"): one optimiser step (fwd + loss + bwd [+ allreduce] + Adam),
-    pvaetf B=512 S=78 T=79 at N=1 (cfg 3), pscavaetf B=512/GPU S=98 T=99 data-parallel at N>1 (cfg 4).
-`value` is timed with inputs resident in HBM; `e2e` goes through the public API
-(sampler.sample_smiles with pinned HOST latents in, Python strings out).
+  * sampling (headline, cfg 2): one sample_smiles call = one batch of --batch latent draws (default 30000 = cfg 2's 30k draws
+    in one call; the reference driver's -batch_size default 512 is reported under "batch512") decoded to max_strlen=100
+    (99 KV-cached multinomial steps), vaetf.  `value`: inputs resident in HBM, CUDA events.  `e2e`: the public call with
+    HOST buffers (pinned latents + lengths in, Python strings out).  `e2e_public_call`: sample_smiles(n) with NO inputs
+    (lengths and latents drawn inside the call) for the reference-faithful host draw and for z_on_device=True;
+  * "cfg5": scavaetf scaffold-conditioned sampling (20-token scaffold prefix), --cfg5-draws per rank;
+  * "train": one optimiser step (fwd + loss + bwd [+ overlapped NCCL all-reduce] + Adam) of cfg 3 (pvaetf B=512 S=78, N=1
+    only) and cfg 4 (pscavaetf B=512/GPU S=98 data-parallel, every N including 1; also the authors' batch 64), each with its
+    own tensor roofline; at N>1 "dp_parity" compares the N-rank gradients with a 1-rank run of the same global batch;
+  * "gpu_eager_baseline": the oracle port (= the reference's arithmetic) run eagerly in fp32 on the same GPU, TF32 off / on.
 `--impl reference` times the CPU oracle port of the reference's un-cached sampler on the host cores.
 """
 from __future__ import annotations
@@ -39,6 +42,7 @@ BATCH = 512
 # next to the algorithmic bytes of that same launch
 NCU_TRAFFIC = {"dram_bytes_per_launch": 874883584, "algorithmic_bytes_same_launch": 872415232, "shape": "B=8192, 49 cached keys + 1 new",
                "source": "profiles/r01_decode_attn_b8192_t49_ncu_details.txt"}
+SCAFFOLD20 = "c1ccc(cc1)C(=O)NCCOC"        # 20 tokens under the character tokeniser below (cfg 5)
 ITOS = ["<unk>", "<pad>", "<sos>", "<eos>", "<sep>"] + list("CcNnOoSsFIBrl()[]=#123456+-H@/")[:27]
 
 
@@ -119,15 +123,16 @@ class ClockSampler:
 # =============================================================================================
 # our arm
 # =============================================================================================
-def build_sampler(dev, dtype="bf16"):
-    from gct_plus_b200.Model import Vaetf
-    from gct_plus_b200.Inference.sampling_tool import VaetfSampling
+def build_sampler(dev, dtype="bf16", model_type="vaetf", latent_bucket=64):
+    from gct_plus_b200.Model import Cvaetf, Vaetf
+    from gct_plus_b200.Inference.sampling_tool import sampling_tool_dict
     torch.manual_seed(0)
-    model = Vaetf(VOCAB, VOCAB, dropout=0.1, nconds=0, compute_dtype=dtype, **ARCH).to(dev).eval()
+    cls = Vaetf if model_type == "vaetf" else Cvaetf
+    model = cls(VOCAB, VOCAB, dropout=0.1, nconds=0, compute_dtype=dtype, **ARCH).to(dev).eval()
     kwargs = dict(top_k=None, latent_dim=ARCH["latent_dim"], max_strlen=MAX_STRLEN, use_cond2dec=False, decode_algo="multinomial",
                   n_jobs=1, toklen_data=toklen_data(), cond_dim=0, scaler=None, device=dev, SRC=_Field(), TRG=_Field(),
-                  sync_every=33, latent_bucket=64)
-    return VaetfSampling(model, kwargs)
+                  sync_every=33, latent_bucket=latent_bucket)
+    return sampling_tool_dict[model_type](model, kwargs)
 
 
 def sample_inputs(sampler, n_batches, seed, pinned=True):
@@ -160,7 +165,7 @@ def time_decode_attention(sampler, dev, steps, Sm):
     decode (n_cached = t), caches of all layers in rotation (6 x 2 x 52 MB bf16 > L2).  CUDA events on the launch stream."""
     import gct_plus_b200._lib as L
     lib = L.lib()
-    d, H, N, B = 512, 8, 6, min(BATCH, 8192)        # 8192 rows x 6 layers x 2 x 100 keys = 10 GB of cache: far beyond L2
+    d, H, N, B = 512, 8, 6, BATCH                   # rows per launch == the benched batch; 30000 x 6 layers x 2 x 100 keys = 37 GB of cache
     Lmax = steps + 1
     kc = torch.randn(N, B, Lmax, d, device=dev).bfloat16()
     vc = torch.randn(N, B, Lmax, d, device=dev).bfloat16()
@@ -240,6 +245,29 @@ def run_sampling(args, rank, world, dev):
     torch.cuda.synchronize()
     t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     assert n_out == K * BATCH
+    # ---- the public call with NO inputs: sample_smiles(n) draws the lengths (host, NumPy stream) and the latents itself.
+    # z on the host = the reference's torch.normal on the CPU generator (seed-faithful, sampling_tool.py:93-97);
+    # z_on_device=True (sampler kwarg) draws them with the CUDA generator.
+    public = {}
+    if getattr(args, "public_call", True):
+        for name, on_dev, reps in (("z_on_device", True, max(2, min(K, 4))), ("z_on_host", False, 1)):
+            sampler.z_on_device = on_dev
+            np.random.seed(4242 + rank)
+            torch.manual_seed(4242 + rank)
+            sampler.sample_smiles(BATCH)                                  # warm-up (static buffers of this shape exist already)
+            barrier(world)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got = 0
+            for _ in range(reps):
+                got += len(sampler.sample_smiles(BATCH)[0])
+            torch.cuda.synchronize()
+            dt = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+            assert got == reps * BATCH
+            public[name] = {"value": world * got / (dt / 1e3), "unit": "SMILES/s", "calls": reps, "ms_per_call": dt / reps}
+        sampler.z_on_device = False
+        public["note"] = ("sampler.sample_smiles(n) exactly as the reference drivers call it (uc_sampling.py:16-23): sample_toklen + sample_z "
+                          "inside the timed call; z_on_host draws 30000 x Lz x 128 normals with torch's CPU generator like the reference")
     h2d = int(np.mean([z.numel() * 4 + BATCH * z.size(1) + BATCH * 8 for _, z in inputs[W:]]))
     d2h = BATCH * MAX_STRLEN * 2          # int16 token ids
     cfg = sampler.model._cfg()
@@ -248,7 +276,7 @@ def run_sampling(args, rank, world, dev):
     Sm_mean = float(np.mean([z.size(1) for _, z in inputs[W:]]))
     Sm_true = float(np.mean([np.mean(tl) for tl, _ in inputs[W:]]))       # keys actually attended (rows differ in length)
     return dict(value=value, ms_per_step=ms / K, e2e_value=world * K * BATCH / (t_e2e / 1e3), h2d=h2d, d2h=d2h, clocks=ck,
-                launches=launches, sampler=sampler, Sm_mean=Sm_mean, Sm_true=Sm_true, decode_steps=n_steps_run / K)
+                launches=launches, sampler=sampler, Sm_mean=Sm_mean, Sm_true=Sm_true, decode_steps=n_steps_run / K, public=public)
 
 
 def make_train_batch(B, S, nc, scaffold, seed, dev=None, pinned=False):
@@ -275,19 +303,24 @@ def make_train_batch(B, S, nc, scaffold, seed, dev=None, pinned=False):
     return batch
 
 
-def run_training(args, rank, world, dev):
+TRAIN_CASES = {
+    "cfg3": dict(mt="pvaetf", S=78, sca=0, name="cfg3 pvaetf S=78 T=79"),
+    "cfg4": dict(mt="pscavaetf", S=98, sca=19, name="cfg4 pscavaetf S=98 T=99 data-parallel"),
+}
+
+
+def run_training(args, rank, world, dev, case="cfg3", B=512, steps=None, grad_exchange="overlap"):
+    """One optimiser step = masks + forward + loss + backward [+ NCCL gradient exchange] + fused Adam (FusedTrainer.step).
+    `roofline`: algorithmic FLOPs (SURVEY 8d formula, fwd+bwd = 3x fwd, attention dense) / device time / sustained bf16 peak."""
     from gct_plus_b200.Model import Cvaetf
     from gct_plus_b200.Train.trainer1 import FusedTrainer
     from oracle.gct_oracle import ModelCfg, flops_forward
     torch.manual_seed(0)
-    if world == 1:
-        mt, S, sca, name = "pvaetf", 78, 0, "cfg3 pvaetf B=512 S=78 T=79"
-    else:
-        mt, S, sca, name = "pscavaetf", 98, 19, "cfg4 pscavaetf B=512/GPU S=98 T=99 DP"
-    B, nc = args.train_batch, 3
+    c = TRAIN_CASES[case]
+    mt, S, sca, nc = c["mt"], c["S"], c["sca"], 3
     model = Cvaetf(VOCAB, VOCAB, dropout=0.1, nconds=nc, use_cond2lat=True, compute_dtype="bf16", **ARCH).to(dev).train()
-    tr = FusedTrainer(model, mt, pad_id=1, lr=1e-4, warmup=8000)
-    K, W = min(args.steps, args.train_steps), args.warmup
+    tr = FusedTrainer(model, mt, pad_id=1, lr=1e-4, warmup=8000, grad_exchange=grad_exchange)
+    K, W = steps or min(args.steps, args.train_steps), args.warmup
     host = [make_train_batch(B, S, nc, sca, 50 + rank * 1000 + i, pinned=True) for i in range(4)]
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
     tokens = [int((b["trg"][:, 1:] != 1).sum()) for b in host]
@@ -318,11 +351,176 @@ def run_training(args, rank, world, dev):
     flops = 3.0 * flops_forward(cfg, B, S, S + 1)
     _, tf_peak, src = peaks()
     loss = tr.read_losses()[0]
-    return {"workload": name, "tokens_per_sec": world * ntok / (ms / 1e3), "padded_tokens_per_sec": world * K * B * (S + 1) / (ms / 1e3),
-            "ms_per_step": ms / K, "steps": K, "e2e_tokens_per_sec": world * ntok / (t_e2e / 1e3),
-            "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host[0].values())), "d2h_bytes_per_step": 16,
-            "algorithmic_tflop_per_step": flops / 1e12, "tensor_frac_of_sustained_peak": flops / (ms / K / 1e3) / (tf_peak * 1e12),
-            "peak_source": src, "dtype": "bf16", "loss_finite": bool(np.isfinite(loss))}
+    achieved = flops / (ms / K / 1e3) / 1e12
+    out = {"workload": f"{c['name']}, B={B}/GPU, {world} GPU(s)", "tokens_per_sec": world * ntok / (ms / 1e3),
+           "padded_tokens_per_sec": world * K * B * (S + 1) / (ms / 1e3), "ms_per_step": ms / K, "steps": K,
+           "e2e_tokens_per_sec": world * ntok / (t_e2e / 1e3),
+           "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host[0].values())), "d2h_bytes_per_step": 16,
+           "algorithmic_tflop_per_step": flops / 1e12,
+           "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                        "traffic": None, "peak_source": src, "what": "whole optimiser step (all kernels), per GPU"},
+           "tensor_frac_of_sustained_peak": achieved / tf_peak, "grad_exchange": tr.grad_exchange if world > 1 else None,
+           "dtype": "bf16", "loss_finite": bool(np.isfinite(loss))}
+    if tr.xchg is not None:
+        tr.xchg.close()
+    del tr, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_dp_parity(rank, world, dev, per_rank=64, S=98):
+    """SURVEY 4 'N-GPU vs 1-GPU gradient equality at fixed global batch': every rank takes its shard of one global batch
+    (fp32 tier, dropout off, the same eps rows), the overlapped NCCL exchange sums the shard gradients, and the result / N
+    is compared with rank 0 running the WHOLE global batch alone; also the post-Adam parameters must be identical on all
+    ranks.  train1.py:111-112 semantics (DDP mean of per-rank sum-loss gradients)."""
+    from gct_plus_b200.Model import Cvaetf
+    from gct_plus_b200.Train.trainer1 import FusedTrainer
+    nc = 3
+    glob = make_train_batch(per_rank * world, S, nc, 19, seed=777)
+    eps = torch.randn(per_rank * world, nc + S, ARCH["latent_dim"], generator=torch.Generator().manual_seed(778))
+    lo, hi = rank * per_rank, (rank + 1) * per_rank
+    res = {}
+    for mode in ("overlap", "nccl"):
+        torch.manual_seed(0)
+        m = Cvaetf(VOCAB, VOCAB, dropout=0.0, nconds=nc, use_cond2lat=True, compute_dtype="fp32", **ARCH).to(dev).train()
+        tr = FusedTrainer(m, "pscavaetf", pad_id=1, grad_exchange=mode)
+        # every shard is padded to the global batch's S so that shapes (and the eps rows) line up with the 1-rank run
+        tr.step({k: v[lo:hi].to(dev) for k, v in glob.items()}, 0.5, eps_noise=eps[lo:hi].to(dev))
+        g = tr.grads.clone() / world
+        p = m._flat.clone()
+        ref = p.clone()
+        torch.distributed.broadcast(ref, src=0)
+        res[mode] = dict(g=g, param_diff=float((p - ref).abs().max()))
+        tr.xchg.close()
+        del tr, m
+    torch.manual_seed(0)
+    m = Cvaetf(VOCAB, VOCAB, dropout=0.0, nconds=nc, use_cond2lat=True, compute_dtype="fp32", **ARCH).to(dev).train()
+    out = {"global_batch": per_rank * world, "tier": "fp32, dropout off", "workload": f"pscavaetf S={S}"}
+    if rank == 0:
+        # 1-rank run of the whole global batch (no exchange): gradient of the global sum-loss, then / world like DDP's mean
+        tr = FusedTrainer(m, "pscavaetf", pad_id=1, grad_exchange="none")
+        tr.step({k: v.to(dev) for k, v in glob.items()}, 0.5, eps_noise=eps.to(dev))
+        g1 = tr.grads / world
+        scale = float(g1.abs().max())
+        for mode in ("overlap", "nccl"):
+            out[f"grad_max_rel_diff_vs_1rank_{mode}"] = float((res[mode]["g"] - g1).abs().max()) / scale
+    for mode in ("overlap", "nccl"):
+        t = torch.tensor([res[mode]["param_diff"]], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        out[f"param_max_abs_diff_across_ranks_{mode}"] = float(t.item())
+    torch.distributed.barrier()
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_cfg5(args, rank, world, dev):
+    """BASELINE cfg 5: scavaetf scaffold-conditioned sampling, 20-token scaffold (ys starts at length 22, latent length
+    21 + toklen), multinomial, max_strlen 100, independent draws per rank (rank-offset seeds, no communication)."""
+    from gct_plus_b200.Train.dp import rank_seed
+    sampler = build_sampler(dev, model_type="scavaetf", latent_bucket=16)
+    per_call = min(args.cfg5_draws, 31250)
+    calls = max(1, args.cfg5_draws // per_call)
+    np.random.seed(rank_seed(2024, rank) % (2 ** 31))
+    g = torch.Generator().manual_seed(rank_seed(2024, rank))
+    sca = len(SCAFFOLD20) + 1
+    ins = []
+    for _ in range(2):
+        toklen = sampler.sample_toklen(per_call)
+        zs = torch.randn(per_call, sca + int(max(toklen)), ARCH["latent_dim"], generator=g).pin_memory()
+        ins.append((toklen, zs))
+    sampler.sample_smiles(per_call, SCAFFOLD20, zs=ins[0][1], toklen=list(ins[0][0]))
+    sampler.sample_smiles(per_call, SCAFFOLD20, zs=ins[1][1], toklen=list(ins[1][0]))      # second call captures the CUDA graphs
+    # device-resident decode
+    dev_in = []
+    for toklen, zs in ins:
+        Lz = zs.size(1)
+        mask = torch.arange(Lz).expand(per_call, 1, Lz) < (torch.LongTensor(np.asarray(toklen)).view(per_call, 1, 1) + sca)
+        dev_in.append((zs.to(dev), mask.to(dev)))
+    sca_ids = [sampler.TRG.vocab.stoi[t] for t in sampler.TRG.tokenize(SCAFFOLD20)]
+    ys0 = sampler.init_y(per_call, add_sos=True, sca_ids=sca_ids, add_sep=True).to(dev)
+    sampler.decode(zs=dev_in[0][0], ys=ys0, src_mask=dev_in[0][1])
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(calls):
+        sampler.decode(zs=dev_in[i % 2][0], ys=ys0, src_mask=dev_in[i % 2][1])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    barrier(world)
+    t0 = time.perf_counter()
+    n_out = 0
+    for i in range(calls):
+        n_out += len(sampler.sample_smiles(per_call, SCAFFOLD20, zs=ins[i % 2][1], toklen=list(ins[i % 2][0]))[0])
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    cfg = sampler.model._cfg()
+    import gct_plus_b200._lib as L
+    zmode = bool(L.lib().gct_decode_begin_launches(cfg, 80) != 3 + 2 * cfg.n_layers)
+    out = {"workload": f"cfg5 scavaetf, 20-token scaffold prefix, {per_call * calls} draws per rank in calls of {per_call}, max_strlen 100",
+           "value": world * calls * per_call / (ms / 1e3), "unit": "SMILES/s", "ms_per_call": ms / calls,
+           "e2e": world * n_out / (t_e2e / 1e3), "latent_space_cross_attention": zmode,
+           "projected_s_for_1M_molecules_on_8_gpus": 125000 / (calls * per_call / (t_e2e / 1e3)) if world == 8 else None}
+    del sampler
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu_eager_baseline(dev, budget_rows=512):
+    """BASELINE.md section 3's like-for-like incumbent: the reference's arithmetic (oracle port = plain torch ops over the
+    state_dict, fp32) run eagerly on the SAME B200, TF32 off and on: (a) the un-cached multinomial Sampling.decode loop at the
+    reference driver's batch 512, max_strlen 100; (b) one cfg 3 forward + loss + backward (no optimiser step)."""
+    O, sd, cfg = cpu_sampler_setup()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    out = {"kind": "oracle port of the reference on the GPU (eager torch, fp32)", "batch": budget_rows}
+    rng = np.random.RandomState(3)
+    toklen = np.clip(np.rint(rng.normal(35, 7, size=budget_rows)), 13, 55).astype(int)
+    Lz = int(toklen.max())
+    zs = torch.randn(budget_rows, Lz, ARCH["latent_dim"], generator=torch.Generator().manual_seed(3)).to(dev)
+    mask = (torch.arange(Lz).expand(budget_rows, 1, Lz) < torch.LongTensor(toklen).view(budget_rows, 1, 1)).to(dev)
+    ys0 = torch.full((budget_rows, 1), 2, dtype=torch.long, device=dev)
+    from gct_plus_b200.Model import Cvaetf
+    torch.manual_seed(0)
+    sd3 = {k: v.detach().clone().to(dev) for k, v in Cvaetf(VOCAB, VOCAB, dropout=0.1, nconds=3, use_cond2lat=True, **ARCH).state_dict().items()}
+    cfg3 = O.ModelCfg(model_type="pvaetf", src_vocab=VOCAB, trg_vocab=VOCAB, nconds=3, use_cond2lat=True)
+    batch = make_train_batch(512, 78, 3, 0, 50, dev=dev)
+    ntok = int((batch["trg"][:, 1:] != 1).sum())
+    keep = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    try:
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            tag = "tf32" if tf32 else "fp32"
+            with torch.no_grad():
+                O.sampling_decode(sd, cfg, zs[:64], ys0[:64], mask[:64], max_strlen=12, algo="multinomial")      # warm-up
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ys = O.sampling_decode(sd, cfg, zs, ys0, mask, max_strlen=MAX_STRLEN, algo="multinomial")
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+            out[f"decode_smiles_per_sec_{tag}"] = budget_rows / dt
+            out[f"decode_steps_{tag}"] = int(ys.size(1) - 1)
+            params = {k: v.clone().requires_grad_(not k.endswith("pe.pe")) for k, v in sd3.items()}
+            eps = torch.randn(512, 81, ARCH["latent_dim"], device=dev)
+            for it in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                prop, mol, mu, lv, _ = O.forward_propagation(params, cfg3, batch, 1, eps)
+                loss = O.loss_function(0.5, prop, mol, None, batch["trg"][:, 1:].reshape(-1), mu, lv, False, 1)[0]
+                loss.backward()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                for p_ in params.values():
+                    p_.grad = None
+            out[f"cfg3_fwd_bwd_ms_{tag}"] = dt * 1e3
+            out[f"cfg3_fwd_bwd_tokens_per_sec_{tag}"] = ntok / dt
+            del params
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = keep
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_input_pipeline(dev, batch=512, nrows=20000, iters=50):
@@ -488,6 +686,10 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-batch512", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
+    ap.add_argument("--no-public-call", dest="public_call", action="store_false")
+    ap.add_argument("--cfg5-draws", type=int, default=125000, help="scaffold-conditioned draws per rank (cfg 5: 1M over 8 GPUs)")
     args = ap.parse_args()
     global BATCH
     BATCH = args.batch
@@ -512,7 +714,7 @@ def main():
         big = BATCH
         BATCH = 512
         a2 = argparse.Namespace(**vars(args))
-        a2.steps, a2.warmup = 12, 3
+        a2.steps, a2.warmup, a2.public_call = 12, 3, False
         r = run_sampling(a2, rank, world, dev)
         b512 = {"batch": 512, "value": r["value"], "unit": "SMILES/s", "ms_per_step": r["ms_per_step"], "steps": 12,
                 "e2e": r["e2e_value"], "note": "the reference driver's default -batch_size (uc_sampling.py:16-23)"}
@@ -522,20 +724,32 @@ def main():
     achieved = alg_per_launch / (ms_per_launch / 1e3) / 1e9
     total_alg = decode_alg_bytes(6, BATCH, s["Sm_true"], steps, 2, latent_form=True)
     total_kv_form = decode_alg_bytes(6, BATCH, s["Sm_true"], steps, 2)
-    train = None
+    s.pop("sampler")
+    torch.cuda.empty_cache()
+    cfg5 = None if args.no_cfg5 else run_cfg5(args, rank, world, dev)
+    train, dp_parity, eager = None, None, None
     if not args.no_train:
-        s.pop("sampler")
-        torch.cuda.empty_cache()
-        train = run_training(args, rank, world, dev)
+        train = {}
+        if world == 1:
+            train["cfg3"] = run_training(args, rank, world, dev, "cfg3", args.train_batch)
+        train["cfg4"] = run_training(args, rank, world, dev, "cfg4", args.train_batch)
+        train["cfg4_batch64"] = run_training(args, rank, world, dev, "cfg4", 64, steps=min(args.train_steps, 30))
+        if world > 1:
+            train["cfg4_unoverlapped"] = run_training(args, rank, world, dev, "cfg4", args.train_batch, grad_exchange="nccl")
+            dp_parity = run_dp_parity(rank, world, dev)
         if rank == 0 and not args.no_cpu:
             train["input_pipeline"] = run_input_pipeline(dev)
+    if rank == 0 and not args.no_eager and world == 1:
+        eager = run_gpu_eager_baseline(dev)
     if rank == 0:
         cpu = None if args.no_cpu else cpu_baseline()
         line = {"metric": "sampled_smiles_per_sec", "value": s["value"], "unit": "SMILES/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": base_config(BATCH, world, f"working set (KV cache {0.9 * BATCH / 512:.1f} GB per batch) larger than L2, no flush needed"),
-                "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"]},
+                "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"],
+                        "call": "sampler.sample_smiles(n, zs=<pinned host latents>, toklen=<host list>) -> Python strings"},
+                "e2e_public_call": s["public"],
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -549,7 +763,7 @@ def main():
                                                       "kv_form_* = SURVEY 8(d)'s K/V-projection form of the same decode",
                                               "kv_form_bytes_per_batch": total_kv_form,
                                               "kv_form_equivalent_GBps": total_kv_form / (s["ms_per_step"] / 1e3) / 1e9}},
-                "cpu_baseline": cpu, "batch512": b512, "train": train}
+                "cpu_baseline": cpu, "gpu_eager_baseline": eager, "batch512": b512, "cfg5": cfg5, "train": train, "dp_parity": dp_parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -191,7 +191,9 @@ class FusedTrainer:
         # gradient exchange across ranks: "overlap" = bucketed NCCL all-reduce on a side stream while the backward still runs
         # (gct_backward_dp, DDP's behaviour), "nccl" = one all-reduce of the flat buffer after the backward through the
         # library's communicator, "torch" = the same through torch.distributed (any backend)
-        assert grad_exchange in ("overlap", "nccl", "torch")
+        assert grad_exchange in ("overlap", "nccl", "torch", "none")
+        if grad_exchange == "none":        # single-process semantics even inside an initialised process group (reference runs, parity checks)
+            self.world, grad_exchange = 1, "torch"
         self.grad_exchange = grad_exchange if (self.world > 1 or force_exchange) else "torch"     # force_exchange: 1-rank communicator (tests)
         self.xchg = GradExchange(model, process_group) if self.grad_exchange != "torch" else None
         flat = model._flat
@@ -277,7 +279,8 @@ class FusedTrainer:
                 self.xchg.allreduce_(self.grads)
                 gscale = 1.0 / self.world
             else:
-                gscale = allreduce_sum_(self.grads, self.pg)   # DDP semantics: mean over ranks of the per-rank sum-loss gradient
+                # DDP semantics: mean over ranks of the per-rank sum-loss gradient
+                gscale = allreduce_sum_(self.grads, self.pg) if self.world > 1 else 1.0
         self.step_count += 1
         shadow = m._shadow if m.compute_dtype == "bf16" else None
         L.check(lib.gct_adam_step(L.ptr(m._flat), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
