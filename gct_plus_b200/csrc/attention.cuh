@@ -127,6 +127,9 @@ struct AttnBwdParams {
     const void* dO; int lddo;     // [B, Lq, lddo]
     void* dQ; void* dK; void* dV; // same layouts / pitches as Q, K, V
     int lddq, lddk, lddv;
+    // optional: column sums of dQ / dK / dV over all rows = the bias gradients of the q / k / v projections ([H*64] each,
+    // accumulated with atomics).  Honoured by the tcgen05 kernel only (atc::launch_bwd); other paths ignore them.
+    float* bsum_q = nullptr; float* bsum_k = nullptr; float* bsum_v = nullptr;
 };
 
 template <typename T>

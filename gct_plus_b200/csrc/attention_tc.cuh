@@ -250,14 +250,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 struct BwdLayout {
     // BS = bytes of one [RPq][64] block.  Pd block 0 is written over the V tile (dead once dP = dO V^T has completed),
     // Pd block 1 follows it; LBOP = their distance (the MN-major descriptor's leading-dimension byte offset).
-    int BS, LBOP, pd, ds, dO, q, k, v, bits, red, bars, total;
+    int BS, LBOP, pd, ds, dO, q, k, v, bits, red, bars, csum, total;
     __host__ __device__ BwdLayout(int RPq, int RPk) {
         BS = RPq * 128;
         const int VB = RPk * 128;
         LBOP = VB > BS ? VB : BS;
         v = 0; pd = 0;
         ds = LBOP + BS; dO = ds + 2 * BS; q = dO + BS; k = q + BS; bits = k + VB;
-        red = bits + 2048; bars = red + 1024; total = bars + 64;
+        red = bits + 2048; bars = red + 1024; csum = bars + 64; total = csum + 768;
         // UMMA A operands always span 128 rows: keep the furthest such read (Q as A of S) inside the allocation
         if (total < q + 16384) total = q + 16384;
         total += 1024;
@@ -281,6 +281,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    float* csum = reinterpret_cast<float*>(sm + L.csum);      // [dV | dK | dQ][64] column sums (bias gradients), see below
+    const bool want_bsum = bp.bsum_q != nullptr || bp.bsum_k != nullptr || bp.bsum_v != nullptr;
+    if (t < 192) csum[t] = 0.f;
     if (t == 32) {
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -420,7 +423,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
     tcgen05_fence_after();
     // each thread: 32 of the 64 columns of its dV / dK row (row = key) and of its dQ row (row = query)
-    auto store_chunk = [&](uint32_t col, void* dst, int ld, int Lr) {
+    // `which` 0/1/2 = dV/dK/dQ.  With bias-gradient outputs requested the warp also reduces its 32 rows column-wise (butterfly
+    // with halving: 31 shuffles leave lane j with the sum of column half*32 + j) into the CTA's csum slab.
+    auto store_chunk = [&](uint32_t col, void* dst, int ld, int Lr, int which) {
         float v[32];
         tmem_ld32(trow + col + half * 32, v);
         if (row < Lr) {
@@ -433,14 +438,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 st8(og + g4 * 8, o);
             }
         }
+        if (want_bsum) {
+            if (row >= Lr) {        // rows past the sequence: not part of the tensor (UMMA's M = 128 reads ran into a neighbour tile)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = 0.f;
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                    const float send = up ? v[i] : v[i + off];
+                    const float keep = up ? v[i + off] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            atomicAdd(&csum[which * 64 + half * 32 + lane], v[0]);
+        }
     };
     if (q * 32 < Lk) {
-        store_chunk(0, bp.dV, bp.lddv, Lk);
-        store_chunk(64, bp.dK, bp.lddk, Lk);
+        store_chunk(0, bp.dV, bp.lddv, Lk, 0);
+        store_chunk(64, bp.dK, bp.lddk, Lk, 1);
     }
-    if (q * 32 < Lq) store_chunk(128, bp.dQ, bp.lddq, Lq);
+    if (q * 32 < Lq) store_chunk(128, bp.dQ, bp.lddq, Lq, 2);
     tcgen05_fence_before();
     __syncthreads();
+    if (want_bsum && t < 192) {
+        float* dst = (t < 64) ? bp.bsum_v : (t < 128) ? bp.bsum_k : bp.bsum_q;
+        if (dst) atomicAdd(dst + h * 64 + (t & 63), csum[t]);
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 

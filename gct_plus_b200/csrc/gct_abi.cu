@@ -13,6 +13,7 @@ int g_gct_persist = 1;
 int g_gct_tma_store = 1;
 int g_gct_ew4 = 1;
 int g_gct_pair = 2;
+int g_gct_attn_bias_separate = 0;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -38,6 +39,7 @@ int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_O
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
+int gct_set_attention_bias_grad_fused(int enabled) { g_gct_attn_bias_separate = !enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
                  void* stream) {
@@ -60,10 +62,10 @@ int gct_norm_bwd(const float* x, const float* alpha, const float* dy, const floa
                  float* dbias, int rows, int d, void* stream) {
     GCT_REQUIRE(d % 128 == 0 && d <= 1024, "norm: d=%d must be a multiple of 128, <= 1024", d);
     if (rows <= 0) return GCT_OK;
-    dim3 grid(min(cdiv(rows, 8), 148 * 4));
-    const size_t sm = 3 * d * sizeof(float);
+    dim3 grid(min(cdiv(rows, 8), 148 * 3));
+    const size_t sm = (size_t)8 * 3 * d * sizeof(float);
     DropCtx nodrop; nodrop.seed = 0; nodrop.thresh = 0; nodrop.scale = 1.f;
-#define CASE(NV) case NV: norm_bwd_kernel<float, NV><<<grid, 256, sm, ST(stream)>>>(x, alpha, dy, add, dx, dalpha, dbias, rows, 1e-6f, (float*)nullptr, nodrop, (float*)nullptr); break;
+#define CASE(NV) case NV: if (sm > 48 * 1024) GCT_SMEM_LIMIT((norm_bwd_kernel<float, NV>), sm); norm_bwd_kernel<float, NV><<<grid, 256, sm, ST(stream)>>>(x, alpha, dy, add, dx, dalpha, dbias, rows, 1e-6f, (float*)nullptr, nodrop, (float*)nullptr); break;
     switch (d / 128) { CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) }
 #undef CASE
     GCT_LAUNCH_CHECK();

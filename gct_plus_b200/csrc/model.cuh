@@ -15,6 +15,7 @@ extern int g_gct_simt_only;
 extern int g_gct_simt_attn;
 extern int g_gct_zattn;
 extern int g_gct_ffn_classic;
+extern int g_gct_attn_bias_separate;
 
 template <typename T>
 static int attn_fwd_dispatch(const AttnParams& p, cudaStream_t st) {
@@ -152,9 +153,9 @@ struct Model {
     int norm_bwd(const float* x, int aslot, int bslot, const float* dy, const float* add, float* dx, int rows,
                  T* dropT = nullptr, DropCtx dc = DropCtx{0, 0, 1.f}, float* dropsum = nullptr) {
         const int nv = d / 128;
-        dim3 grid(min(cdiv(rows, 8), 148 * 4));
-        const size_t sm = 3 * d * sizeof(float);
-#define GCT_NORMB_CASE(NV) case NV: norm_bwd_kernel<T, NV><<<grid, 256, sm, st>>>(x, P(aslot), dy, add, dx, G(aslot), G(bslot), rows, 1e-6f, dropT, dc, dropsum); break;
+        dim3 grid(min(cdiv(rows, 8), 148 * 3));
+        const size_t sm = (size_t)8 * 3 * d * sizeof(float);
+#define GCT_NORMB_CASE(NV) case NV: if (sm > 48 * 1024) GCT_SMEM_LIMIT((norm_bwd_kernel<T, NV>), sm); norm_bwd_kernel<T, NV><<<grid, 256, sm, st>>>(x, P(aslot), dy, add, dx, G(aslot), G(bslot), rows, 1e-6f, dropT, dc, dropsum); break;
         switch (nv) { GCT_NORMB_CASE(1) GCT_NORMB_CASE(2) GCT_NORMB_CASE(3) GCT_NORMB_CASE(4) GCT_NORMB_CASE(5) GCT_NORMB_CASE(6)
                       GCT_NORMB_CASE(7) GCT_NORMB_CASE(8) default: GCT_FAIL(GCT_ERR_UNSUPPORTED, "norm width %d", d); }
 #undef GCT_NORMB_CASE
@@ -177,16 +178,35 @@ struct Model {
         p.scale = 0.125f; p.drop = dc;
         return attn_fwd_dispatch<T>(p, st);
     }
+    // gq / gk / gv: bias gradients of the q / k / v projections (column sums of dq / dk / dv), produced inside the tcgen05
+    // kernel's write-out, by separate column-sum launches on the other paths
     int attention_bwd(const T* q, int ldq, const T* k, const T* v, int ldkv, const uint8_t* mask, long long mb, int mr,
                       const float* lse, const T* out, const T* dO, T* dq, int lddq, T* dk, T* dv, int lddkv, int B, int Lq, int Lk,
-                      DropCtx dc) {
+                      DropCtx dc, float* gq = nullptr, float* gk = nullptr, float* gv = nullptr) {
         AttnBwdParams bp;
         AttnParams& p = bp.f;
         p.Q = q; p.K = k; p.V = v; p.ldq = ldq; p.ldk = ldkv; p.ldv = ldkv; p.mask = mask; p.mask_bstride = mb;
         p.mask_rstride = mr; p.O = const_cast<T*>(out); p.ldo = d; p.lse = const_cast<float*>(lse); p.probs = nullptr; p.B = B; p.H = H;
         p.Lq = Lq; p.Lk = Lk; p.scale = 0.125f; p.drop = dc;
         bp.dO = dO; bp.lddo = d; bp.dQ = dq; bp.dK = dk; bp.dV = dv; bp.lddq = lddq; bp.lddk = lddkv; bp.lddv = lddkv;
-        return attn_bwd_dispatch<T>(bp, st);
+        bool fused = false;
+        if constexpr (sizeof(T) == 2) fused = !g_gct_simt_attn && !g_gct_attn_bias_separate && atc::supported(bp.f) && bp.f.O != nullptr;
+        if (fused) { bp.bsum_q = gq; bp.bsum_k = gk; bp.bsum_v = gv; }
+        GCT_TRY(attn_bwd_dispatch<T>(bp, st));
+        if (!fused) {
+            auto cs = [&](const T* g, int rows, int ld, float* dst) -> int {
+                if (!dst) return GCT_OK;
+                const int gy = cdiv(d, 256);
+                dim3 grid(max(1, min(cdiv(rows, 64), 1184 / gy)), gy);
+                colsum_kernel<T><<<grid, 256, 0, st>>>(g, rows, d, ld, dst);
+                GCT_LAUNCH_CHECK();
+                return GCT_OK;
+            };
+            GCT_TRY(cs(dq, B * Lq, lddq, gq));
+            GCT_TRY(cs(dk, B * Lk, lddkv, gk));
+            GCT_TRY(cs(dv, B * Lk, lddkv, gv));
+        }
+        return GCT_OK;
     }
 };
 
@@ -534,9 +554,10 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             }
             T* dq2 = S.dqkvT;                      // [Md, d]
             GCT_TRY(m.attention_bwd(a.q2, d, a.kv2, a.kv2 + d, 2 * d, A.cross_mask, Sm, 0, a.lse2, a.att2, S.dattT, dq2, d, S.dkv2T,
-                                    S.dkv2T + d, 2 * d, B, Ld, Sm, m.site(sb + DS_ATTN2)));
-            GCT_TRY(m.wgrad(dq2, d, a.a2, d, Md, d, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), true));
-            GCT_TRY(m.wgrad(S.dkv2T, 2 * d, A.mem, d, Mm, 2 * d, d, m.dec_slot(l, D_KV2_W), m.dec_slot(l, D_KV2_B), true));
+                                    S.dkv2T + d, 2 * d, B, Ld, Sm, m.site(sb + DS_ATTN2), m.G(m.dec_slot(l, D_Q2_B)),
+                                    m.G(m.dec_slot(l, D_KV2_B)), m.G(m.dec_slot(l, D_KV2_B)) + d));
+            GCT_TRY(m.wgrad(dq2, d, a.a2, d, Md, d, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), false));
+            GCT_TRY(m.wgrad(S.dkv2T, 2 * d, A.mem, d, Mm, 2 * d, d, m.dec_slot(l, D_KV2_W), m.dec_slot(l, D_KV2_B), false));
             {   // dmem += dkv2 Wkv2
                 Epilogue e = Model<T>::epi(nullptr, d); e.res32 = S.dmem; e.out32 = S.dmem;
                 GCT_TRY(m.gemm(S.dkv2T, false, 2 * d, m.WT(m.dec_slot(l, D_KV2_W)), true, d, Mm, d, 2 * d, e));
@@ -555,8 +576,9 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
                 GCT_TRY(m.gemm(S.dyT, false, d, m.WT(m.dec_slot(l, D_O1_W)), true, d, Md, d, d, e));
             }
             GCT_TRY(m.attention_bwd(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.trg_mask, (long long)Ld * Ld, Ld, a.lse1,
-                                    a.att1, S.dattT, S.dqkvT, 3 * d, S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Ld, Ld, m.site(sb + DS_ATTN1)));
-            GCT_TRY(m.wgrad(S.dqkvT, 3 * d, a.a1, d, Md, 3 * d, d, m.dec_slot(l, D_QKV_W), m.dec_slot(l, D_QKV_B), true));
+                                    a.att1, S.dattT, S.dqkvT, 3 * d, S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Ld, Ld, m.site(sb + DS_ATTN1),
+                                    m.G(m.dec_slot(l, D_QKV_B)), m.G(m.dec_slot(l, D_QKV_B)) + d, m.G(m.dec_slot(l, D_QKV_B)) + 2 * d));
+            GCT_TRY(m.wgrad(S.dqkvT, 3 * d, a.a1, d, Md, 3 * d, d, m.dec_slot(l, D_QKV_W), m.dec_slot(l, D_QKV_B), false));
             {
                 Epilogue e = Model<T>::epi(nullptr, d); e.out32 = other;
                 GCT_TRY(m.gemm(S.dqkvT, false, 3 * d, m.WT(m.dec_slot(l, D_QKV_W)), true, d, Md, d, 3 * d, e));
@@ -638,8 +660,9 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             GCT_TRY(m.gemm(S.dyT, false, d, m.WT(m.enc_slot(l, E_O_W)), true, d, Me, d, d, e));
         }
         GCT_TRY(m.attention_bwd(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.src_mask, Se, 0, a.lse, a.att, S.dattT, S.dqkvT, 3 * d,
-                                S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Se, Se, m.site(sb + ES_ATTN)));
-        GCT_TRY(m.wgrad(S.dqkvT, 3 * d, a.a1, d, Me, 3 * d, d, m.enc_slot(l, E_QKV_W), m.enc_slot(l, E_QKV_B), true));
+                                S.dqkvT + d, S.dqkvT + 2 * d, 3 * d, B, Se, Se, m.site(sb + ES_ATTN), m.G(m.enc_slot(l, E_QKV_B)),
+                                m.G(m.enc_slot(l, E_QKV_B)) + d, m.G(m.enc_slot(l, E_QKV_B)) + 2 * d));
+        GCT_TRY(m.wgrad(S.dqkvT, 3 * d, a.a1, d, Me, 3 * d, d, m.enc_slot(l, E_QKV_W), m.enc_slot(l, E_QKV_B), false));
         {   // dA1 = dqkv Wqkv + dX1
             Epilogue e = Model<T>::epi(nullptr, d); e.res32 = third; e.out32 = other;
             GCT_TRY(m.gemm(S.dqkvT, false, 3 * d, m.WT(m.enc_slot(l, E_QKV_W)), true, d, Me, d, 3 * d, e));

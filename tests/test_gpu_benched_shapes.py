@@ -111,7 +111,7 @@ def test_training_step_at_cfg3_cfg4_shape_matches_oracle(mt, S, sca, dtype):
     # cancellation-dominated dS = P o (dP - rowsum(P o dP)), which moves by ~1 % under the bf16 rounding of the 44 M operand
     # weights alone (the fp32 tier below shows 1e-6 on the same tensors, so it is rounding, not arithmetic) -- held to 2e-2.
     tol_t = 1e-2 if dtype == "bf16" else 1e-4
-    assert whole < (5e-3 if dtype == "bf16" else 1e-5), whole
+    assert whole < (1e-2 if dtype == "bf16" else 1e-5), whole
     for efro, emax, k in rows:
         qk = dtype == "bf16" and (".q_linear." in k or ".k_linear." in k)
         assert efro < (2e-2 if qk else tol_t), (k, efro)
@@ -184,18 +184,23 @@ def test_decode_attention_kernel_vs_oracle_attention(n_cached, cfg):
 
 
 # ------------------------------------------------------------------------------------------ 99-step bf16 KV decode
-def _sampler(model, mt, nc, max_strlen, **kw):
-    kwargs = dict(top_k=None, latent_dim=ARCH["latent_dim"], max_strlen=max_strlen, use_cond2dec=False, decode_algo="multinomial",
+def _sampler(model, mt, nc, max_strlen, latent_dim=128, **kw):
+    kwargs = dict(top_k=None, latent_dim=latent_dim, max_strlen=max_strlen, use_cond2dec=False, decode_algo="multinomial",
                   n_jobs=1, toklen_data=None, cond_dim=nc, scaler=FakeScaler(), device=DEV, SRC=FakeField(), TRG=FakeField(), **kw)
     return sampling_tool_dict[mt](model, kwargs)
 
 
-DECODE_CASES = [("vaetf", 0, 1, 55, True), ("vaetf", 0, 1, 55, False), ("pvaetf", 3, 1, 55, True), ("scavaetf", 0, 22, 76, True),
-                ("pscavaetf", 3, 22, 76, True)]
+ARCH_MID = dict(N=2, d_model=256, dff=512, h=4, latent_dim=64)
+ARCH_SMALL = dict(N=2, d_model=128, dff=256, h=2, latent_dim=32)
+DECODE_CASES = [("vaetf", 0, 1, 55, True, ARCH), ("vaetf", 0, 1, 55, False, ARCH), ("pvaetf", 3, 1, 55, True, ARCH),
+                ("pvaetf", 3, 1, 55, False, ARCH), ("scavaetf", 0, 22, 76, True, ARCH), ("pscavaetf", 3, 22, 76, True, ARCH),
+                ("pscavaetf", 3, 22, 76, False, ARCH),
+                # the other instantiations of the latent-space kernel: latent 64 / 4 heads, latent 32 / 2 heads (+ condition rows)
+                ("pvaetf", 3, 1, 40, True, ARCH_MID), ("pscavaetf", 2, 9, 37, True, ARCH_SMALL), ("vaetf", 0, 1, 19, True, ARCH_SMALL)]
 
 
-@pytest.mark.parametrize("mt,nc,t0,Lz,latent_form", DECODE_CASES)
-def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form):
+@pytest.mark.parametrize("mt,nc,t0,Lz,latent_form,arch", DECODE_CASES)
+def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form, arch):
     """cfg 2 / cfg 5 decode at B = 2048 rows, max_strlen 100 (99 steps), bf16 tier, teacher-forced on random tokens:
     the logits of EVERY step -- KV cache lengths 1..99 (+ the scaffold prefix), both decode_attn ring configurations,
     cross-attention in latent space or in K/V form, ragged latent lengths, cond2lat memory rows -- against the oracle's
@@ -205,12 +210,12 @@ def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form):
     steps = max_strlen - 1
     torch.manual_seed(0)
     cls = Vaetf if mt == "vaetf" else Cvaetf
-    m = cls(V, V, dropout=0.1, nconds=nc, use_cond2lat=nc > 0, compute_dtype="bf16", **ARCH)
+    m = cls(V, V, dropout=0.1, nconds=nc, use_cond2lat=nc > 0, compute_dtype="bf16", **arch)
     sd = {k: v.detach().clone().to(DEV) for k, v in m.state_dict().items()}
     m = m.to(DEV).eval()
-    s = _sampler(m, mt, nc, max_strlen, latent_bucket=8)
+    s = _sampler(m, mt, nc, max_strlen, latent_bucket=8, latent_dim=arch["latent_dim"])
     g = torch.Generator().manual_seed(17)
-    zs = torch.randn(B, Lz, ARCH["latent_dim"], generator=g)
+    zs = torch.randn(B, Lz, arch["latent_dim"], generator=g)
     lens = torch.randint(13 + (t0 - 1), Lz + 1, (B,), generator=g)
     lens[0], lens[1] = Lz, 1
     mask = torch.arange(Lz)[None, None, :] < lens[:, None, None]
@@ -225,7 +230,8 @@ def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form):
         got = s.teacher_forced_logits(zs, ys, mask, dconds=dconds, t0=t0)        # (steps, B, V)
     finally:
         lib.gct_set_latent_cross_attention(1)
-    cfg = O.ModelCfg(model_type=mt, src_vocab=V, trg_vocab=V, nconds=nc, use_cond2lat=nc > 0)
+    cfg = O.ModelCfg(model_type=mt, src_vocab=V, trg_vocab=V, nconds=nc, use_cond2lat=nc > 0, N=arch["N"], d_model=arch["d_model"],
+                     dff=arch["dff"], h=arch["h"], latent_dim=arch["latent_dim"])
     trg = ys[:, :-1].to(DEV)
     with torch.no_grad():
         want = O.decode_logits(sd, cfg, trg, zs.to(DEV), mask.to(DEV), O.trg_mask(trg, 1), dconds)   # (B, t0+steps-1, V)
