@@ -61,8 +61,8 @@ struct ZAttnParams {
     int H; int B;
 };
 
-template <int LAT>
-__global__ void __launch_bounds__(ZA_WARPS * 32)
+template <int LAT, int MINB>
+__global__ void __launch_bounds__(ZA_WARPS * 32, MINB)
 decode_zattn_kernel(ZAttnParams p) {
     constexpr int NB = LAT / 32;                // 32-dim blocks of a latent row (one 16-byte load per lane and block)
     constexpr float kL2e = 1.4426950408889634f;
@@ -77,16 +77,21 @@ decode_zattn_kernel(ZAttnParams p) {
     const uint8_t* valid = p.key_valid + (size_t)b * p.kv_stride;
     const bf16* qrow = p.qz + (size_t)b * p.ldq;
 
-    // first chunk of latent rows: issued before anything depends on it (keys 0 .. 15 exist whenever n_keys > them)
-    uint4 za[NB], zb[NB];
-    {
-        const bool ia = g < nkeys, ib = g + 8 < nkeys;
+    // The first TWO 16-key chunks are requested before anything else (their addresses depend on nothing but n_keys): with the
+    // query fragments and the validity bytes that is one round trip to memory for every row of up to 32 keys, two for the rest
+    // (ncu, first version with one chunk in flight: 47 % of the stall samples were long-scoreboard waits, 22 % occupancy).
+    uint4 za[NB], zb[NB], na[NB], nb[NB];
+    auto load_chunk = [&](int chunk, uint4* da, uint4* db, int limit) {
+        const int ka = chunk * 16 + g, kb = ka + 8;
+        const bool ia = ka < limit, ib = kb < limit;
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-            za[k] = ia ? ldg_nc16(zg + (size_t)g * LAT + k * 32) : make_uint4(0, 0, 0, 0);
-            zb[k] = ib ? ldg_nc16(zg + (size_t)(g + 8) * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+            da[k] = ia ? ldg_nc16(zg + (size_t)ka * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+            db[k] = ib ? ldg_nc16(zg + (size_t)kb * LAT + k * 32) : make_uint4(0, 0, 0, 0);
         }
-    }
+    };
+    load_chunk(0, za, zb, nkeys);
+    load_chunk(1, na, nb, nkeys);
     // query fragments: lane (g,t) = head g, dims 32*blk + 8t .. +8 (same permutation as the latent rows)
     uint4 q[NB];
 #pragma unroll
@@ -156,28 +161,20 @@ decode_zattn_kernel(ZAttnParams p) {
 #pragma unroll
     for (int i = 0; i < 2 * NB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-    for (int c0 = 0; c0 < nrow; c0 += 16) {
-        // prefetch the next chunk while this one is consumed
-        uint4 na[NB], nb[NB];
-        {
-            const int ka = c0 + 16 + g, kb = ka + 8;
-            const bool ia = ka < nrow, ib = kb < nrow;
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                na[k] = ia ? ldg_nc16(zg + (size_t)ka * LAT + k * 32) : make_uint4(0, 0, 0, 0);
-                nb[k] = ib ? ldg_nc16(zg + (size_t)kb * LAT + k * 32) : make_uint4(0, 0, 0, 0);
-            }
-        }
+    // one 16-key chunk: scores, online softmax update, context accumulation
+    auto consume = [&](const uint4* ca, const uint4* cb, int c0) {
         const int ka = c0 + g, kb = ka + 8;
         const bool ina = ka < nrow, inb = kb < nrow;
         const bool oka = ina && valid[ka] != 0, okb = inb && valid[kb] != 0;
-        // ---- S^T = Z Q^T (16 keys x 8 heads), k permuted: two k-steps per 32-dim block
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        // ---- S^T = Z Q^T (16 keys x 8 heads), k permuted: two k-steps per 32-dim block, two accumulators to halve the chain
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-            mma_bf16_16816(s, za[k].x, zb[k].x, za[k].y, zb[k].y, q[k].x, q[k].y);
-            mma_bf16_16816(s, za[k].z, zb[k].z, za[k].w, zb[k].w, q[k].z, q[k].w);
+            mma_bf16_16816(s, ca[k].x, cb[k].x, ca[k].y, cb[k].y, q[k].x, q[k].y);
+            mma_bf16_16816(s2, ca[k].z, cb[k].z, ca[k].w, cb[k].w, q[k].z, q[k].w);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[e] += s2[e];
         // s[0], s[1]: key ka, heads 2t, 2t+1 ; s[2], s[3]: key kb
         float pa[2], pb[2];
 #pragma unroll
@@ -202,11 +199,18 @@ decode_zattn_kernel(ZAttnParams p) {
         const uint32_t pb1 = movmatrix_trans(pack_bf16x2(pb[0], pb[1]));
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-            mma_bf16_16816(acc[2 * k], movmatrix_trans(za[k].x), movmatrix_trans(za[k].y), movmatrix_trans(zb[k].x), movmatrix_trans(zb[k].y), pb0, pb1);
-            mma_bf16_16816(acc[2 * k + 1], movmatrix_trans(za[k].z), movmatrix_trans(za[k].w), movmatrix_trans(zb[k].z), movmatrix_trans(zb[k].w), pb0, pb1);
+            mma_bf16_16816(acc[2 * k], movmatrix_trans(ca[k].x), movmatrix_trans(ca[k].y), movmatrix_trans(cb[k].x), movmatrix_trans(cb[k].y), pb0, pb1);
+            mma_bf16_16816(acc[2 * k + 1], movmatrix_trans(ca[k].z), movmatrix_trans(ca[k].w), movmatrix_trans(cb[k].z), movmatrix_trans(cb[k].w), pb0, pb1);
         }
-#pragma unroll
-        for (int k = 0; k < NB; ++k) { za[k] = na[k]; zb[k] = nb[k]; }
+    };
+    // two register buffers, each refilled with the chunk two ahead as soon as it has been consumed
+    for (int c0 = 0; c0 < nrow; c0 += 32) {
+        consume(za, zb, c0);
+        if (c0 + 32 < nrow) load_chunk((c0 >> 4) + 2, za, zb, nrow);
+        if (c0 + 16 < nrow) {
+            consume(na, nb, c0 + 16);
+            if (c0 + 48 < nrow) load_chunk((c0 >> 4) + 3, na, nb, nrow);
+        }
     }
     // ---- normalise: l over the eight key slots (g); every lane ends with the totals of its two heads
     float inv[2];
@@ -266,9 +270,13 @@ decode_zattn_kernel(ZAttnParams p) {
     }
 }
 
+extern int g_za_cfg;      // tuning knob: resident CTAs per SM the kernel is compiled for (3: 160 registers, no spills; 4: 128 registers)
+
 template <int LAT>
 static int launch_decode_zattn_lat(const ZAttnParams& p, cudaStream_t st) {
-    GCT_CUDA(launch_k(decode_zattn_kernel<LAT>, dim3((p.B + ZA_WARPS - 1) / ZA_WARPS), dim3(ZA_WARPS * 32), 0, st, true, p));
+    const dim3 grid((p.B + ZA_WARPS - 1) / ZA_WARPS), block(ZA_WARPS * 32);
+    if (g_za_cfg == 4) GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 4>, grid, block, 0, st, true, p));
+    else GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 3>, grid, block, 0, st, true, p));
     return GCT_OK;
 }
 static bool zattn_supported(int lat, int H, int nc) { return (lat == 128 || lat == 64 || lat == 32) && H >= 1 && H <= 8 && nc >= 0 && nc <= 8; }

@@ -14,6 +14,7 @@ int g_gct_tma_store = 1;
 int g_gct_ew4 = 1;
 int g_gct_pair = 2;
 int g_gct_attn_bias_separate = 0;
+int g_za_cfg = 3;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -39,6 +40,7 @@ int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_O
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
+int gct_set_zattn_config(int ctas_per_sm) { g_za_cfg = ctas_per_sm; return GCT_OK; }
 int gct_set_attention_bias_grad_fused(int enabled) { g_gct_attn_bias_separate = !enabled; return GCT_OK; }
 
 int gct_norm_fwd(const float* x, const float* alpha, const float* bias, void* y, float* y32, int rows, int d, int dtype,
