@@ -23,6 +23,34 @@ from ..Model.modules import get_src_mask, get_trg_mask
 from .toklen_sampling import tokenlen_gen_from_data_distribution
 
 
+_MT_OK = None
+
+
+def _mt_layout_ok() -> bool:
+    """One-off check that torch.get_rng_state() still has the layout gct_mt19937_fill assumes (seed u64, left i32, seeded i32,
+    next u64, 624 x u64 words, ... = 5056 bytes) AND that the engine semantics match: 40 uniforms produced from a copy of the
+    state must equal torch.rand's.  The global generator is left untouched."""
+    global _MT_OK
+    if _MT_OK is None:
+        try:
+            keep = torch.get_rng_state()
+            ok = keep.numel() == 5056
+            if ok:
+                sn = keep.clone().numpy()
+                raw = np.empty(700, dtype=np.uint32)
+                L.check(L.lib().gct_mt19937_fill(sn[24:24 + 4992].view(np.uint64).ctypes.data, sn[8:12].view(np.int32).ctypes.data,
+                                                 sn[16:24].view(np.uint64).ctypes.data, raw.ctypes.data, 700), "gct_mt19937_fill")
+                mine = (raw & 0xFFFFFF).astype(np.float32) * np.float32(2.0 ** -24)
+                theirs = torch.rand(700).numpy()
+                after = torch.get_rng_state().numpy()
+                ok = bool(np.array_equal(mine, theirs)) and bool(np.array_equal(after[:5016], sn[:5016]))
+            torch.set_rng_state(keep)
+            _MT_OK = ok
+        except Exception:
+            _MT_OK = False
+    return _MT_OK
+
+
 class Sampling:
     def __init__(self, model, kwargs, top_k=None):
         self.batch_size = 512
@@ -55,6 +83,7 @@ class Sampling:
         # regex tokeniser in TRG.tokenize (~10 us / row), not with a trivial one ([B200], 30k rows: 40.2k vs 41.6k SMILES/s)
         self.pipeline_rows = kwargs.get('pipeline_rows', None)
         self.z_on_device = kwargs.get('z_on_device', False)
+        self.host_z_exact = kwargs.get('host_z_exact', False)
         self._host_s_per_row = 0.0
         self._side_stream = None
         # static decode buffers / captured CUDA graphs per request shape: small LRUs (each entry pins O(n * Lz * latent)
@@ -144,12 +173,34 @@ class Sampling:
         return p if self.SRC.batch_first else p.T
 
     def sample_z(self, toklen, n):
-        """z ~ N(0, 1), drawn on the HOST like the reference (Inference/sampling_tool.py:93-97) so that a seeded run draws
-        the same latents.  `z_on_device=True` (sampler kwarg, not in the reference) draws them with the CUDA generator
-        instead: for 30 000 x 55 x 128 latents the host draw + copy costs more than the whole decode."""
+        """z ~ N(0, 1) from the HOST generator like the reference (Inference/sampling_tool.py:93-97), so that a seeded run
+        draws the same latents.  torch.normal on the CPU costs ~7 ns per element (2 s for 30 000 x 55 x 128 -- three times
+        the whole decode), so the draw is split: the library advances torch's CPU MT19937 engine in a tight host loop
+        (gct_mt19937_fill, one raw output per element into pinned memory, ~1.5 ns each) and the device applies
+        at::normal_fill's Box-Muller blocks (gct_normal_from_mt).  Same generator state afterwards, same values to the
+        rounding of logf / sincosf (1-2 ulp); returns a CUDA tensor.  `host_z_exact=True` (sampler kwarg) keeps
+        torch.normal itself; `z_on_device=True` draws with the CUDA generator instead (not seed-compatible)."""
         if self.z_on_device:
             return torch.randn((n, toklen, self.latent_dim), device=self.device)
-        return torch.normal(mean=0, std=1, size=(n, toklen, self.latent_dim))
+        numel = int(n) * int(toklen) * int(self.latent_dim)
+        if self.host_z_exact or numel < 16 or not torch.device(self.device).type == 'cuda' or not _mt_layout_ok():
+            return torch.normal(mean=0, std=1, size=(n, toklen, self.latent_dim))
+        lib = L.lib()
+        extra = 16 if numel % 16 else 0
+        raw = getattr(self, '_raw_host', None)
+        if raw is None or raw.numel() < numel + extra:
+            raw = self._raw_host = torch.empty(numel + extra, dtype=torch.int32).pin_memory()
+        state = torch.get_rng_state()
+        sn = state.numpy()
+        words = sn[24:24 + 624 * 8].view(np.uint64)
+        left, nxt = sn[8:12].view(np.int32), sn[16:24].view(np.uint64)
+        L.check(lib.gct_mt19937_fill(words.ctypes.data, left.ctypes.data, nxt.ctypes.data, raw.data_ptr(), numel + extra),
+                "gct_mt19937_fill")
+        torch.set_rng_state(state)
+        raw_dev = raw[:numel + extra].to(self.device, non_blocking=True)
+        z = torch.empty((n, toklen, self.latent_dim), device=self.device, dtype=torch.float32)
+        L.check(lib.gct_normal_from_mt(L.ptr(raw_dev), L.ptr(z), numel, L.stream_ptr()), "gct_normal_from_mt")
+        return z
 
     def transform(self, prop):
         return torch.from_numpy(self.scaler.transform(prop)).float()

@@ -67,6 +67,7 @@ _PROTOS = {
     "gct_set_attention_backend": (C.c_int, [C.c_int]),
     "gct_set_attention_bias_grad_fused": (C.c_int, [C.c_int]),
     "gct_set_zattn_config": (C.c_int, [C.c_int]),
+    "gct_set_sm_budget": (C.c_int, [C.c_int]),
     "gct_set_latent_cross_attention": (C.c_int, [C.c_int]),
     "gct_set_ffn_saved_activation": (C.c_int, [C.c_int]),
     "gct_set_persistent_gemm": (C.c_int, [C.c_int]),
@@ -100,6 +101,8 @@ _PROTOS = {
                               vp, vp]),
     "gct_detokenize": (i64, [vp, i64, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, i64]),
     "gct_toklen_draw": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, vp, C.c_double, i64, vp]),
+    "gct_mt19937_fill": (C.c_int, [vp, vp, vp, vp, i64]),
+    "gct_normal_from_mt": (C.c_int, [vp, vp, i64, vp]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
     "gct_decode_begin_launches": (C.c_int, [C.POINTER(GctConfig), C.c_int]),
     "gct_decode_attention": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,

@@ -15,6 +15,7 @@ int g_gct_ew4 = 1;
 int g_gct_pair = 2;
 int g_gct_attn_bias_separate = 0;
 int g_za_cfg = 3;
+int g_gct_sm_budget = 0;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -40,6 +41,7 @@ int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_O
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
+int gct_set_sm_budget(int sms) { g_gct_sm_budget = sms; return GCT_OK; }
 int gct_set_zattn_config(int ctas_per_sm) { g_za_cfg = ctas_per_sm; return GCT_OK; }
 int gct_set_attention_bias_grad_fused(int enabled) { g_gct_attn_bias_separate = !enabled; return GCT_OK; }
 
@@ -344,6 +346,94 @@ int gct_toklen_draw(uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, doubl
         out[k] = centres[idx] + width * g / 2;
     }
     *mt_pos = m.pos; *has_gauss = hg; *cached_gauss = cg;
+    return GCT_OK;
+}
+
+// Host half of the seed-faithful latent draw (Inference/sampling_tool.py:93-97: torch.normal on the CPU generator): advances
+// PyTorch's CPU MT19937 engine exactly like at::mt19937::operator() (--left == 0 -> regenerate; tempering) and writes the raw
+// 32-bit outputs, one per element -- at::normal_fill draws one uniform per element this way before its Box-Muller pass.
+// `state` is the engine's 624-word array as stored in torch.get_rng_state() (uint64 per word), left / next its counters.
+}  // extern "C"
+namespace {
+// whole 624-word blocks: regenerate, then temper all 624 in one vectorisable pass (AVX2 build of the same code when the CPU has it)
+#define GCT_MT_BLOCK_BODY                                                                                             \
+    for (int64_t b = 0; b < nblocks; ++b) {                                                                           \
+        int i = 0;                                                                                                    \
+        for (; i < 624 - 397; ++i) { const uint32_t y = (k[i] & 0x80000000u) | (k[i + 1] & 0x7fffffffu); k[i] = k[i + 397] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu); } \
+        for (; i < 623; ++i) { const uint32_t y = (k[i] & 0x80000000u) | (k[i + 1] & 0x7fffffffu); k[i] = k[i - 227] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu); }       \
+        { const uint32_t y = (k[623] & 0x80000000u) | (k[0] & 0x7fffffffu); k[623] = k[396] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu); }                              \
+        uint32_t* o = out + b * 624;                                                                                  \
+        for (int j = 0; j < 624; ++j) { uint32_t y = k[j]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18; o[j] = y; }              \
+    }
+void mt_blocks_generic(uint32_t* k, uint32_t* out, int64_t nblocks) { GCT_MT_BLOCK_BODY }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) void mt_blocks_avx2(uint32_t* k, uint32_t* out, int64_t nblocks) { GCT_MT_BLOCK_BODY }
+#endif
+#undef GCT_MT_BLOCK_BODY
+}  // namespace
+extern "C" {
+int gct_mt19937_fill(uint64_t* state, int32_t* left, uint64_t* next, uint32_t* out, int64_t n) {
+    if (!state || !left || !next || (!out && n > 0) || n < 0) {
+        snprintf(g_gct_err, sizeof(g_gct_err), "mt19937_fill: bad arguments");
+        return GCT_ERR_ARG;
+    }
+    uint32_t k[624];
+    for (int i = 0; i < 624; ++i) k[i] = (uint32_t)state[i];
+    Mt m{k, (int)*next};
+    int l = *left;
+    auto one = [&]() {
+        if (--l == 0) { mt_refill(m); l = 624; }
+        uint32_t y = k[m.pos++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    };
+    int64_t i = 0;
+    // drain the current block (left counts the outputs remaining in it, + 1), then whole blocks, then the head of the last one
+    while (i < n && l > 1) out[i++] = one();
+    const int64_t nblocks = (n - i) / 624;
+    if (nblocks > 0) {
+#if defined(__x86_64__) && defined(__GNUC__)
+        if (__builtin_cpu_supports("avx2")) mt_blocks_avx2(k, out + i, nblocks); else
+#endif
+        mt_blocks_generic(k, out + i, nblocks);
+        i += nblocks * 624;
+        l = 1; m.pos = 624;          // the state every full block leaves behind: all 624 outputs consumed
+    }
+    while (i < n) out[i++] = one();
+    for (int j = 0; j < 624; ++j) state[j] = k[j];
+    *left = l; *next = (uint64_t)m.pos;
+    return GCT_OK;
+}
+}  // extern "C"
+// Device half: at::normal_fill's transform (aten/src/ATen/native/cpu/DistributionTemplates.h) on the raw outputs: uniform =
+// (raw & (2^24 - 1)) * 2^-24; per block of 16, (u1 = 1 - x[j], u2 = x[j+8]) -> radius = sqrt(-2 log u1), theta = 2 pi u2,
+// x[j] = radius cos(theta), x[j+8] = radius sin(theta); a tail shorter than 16 is recomputed from 16 fresh draws (raw[n..n+16))
+// over the LAST 16 elements.  Equal to torch.normal(0, 1) on the CPU to the rounding of logf / cosf / sinf (1-2 ulp).
+__global__ void normal_from_mt_kernel(const uint32_t* __restrict__ raw, float* __restrict__ z, long long nblocks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one (j, j+8) pair per thread
+    const long long blk = i >> 3;
+    const int j = (int)(i & 7);
+    if (blk >= nblocks) return;
+    const uint32_t* src = raw + blk * 16;
+    float* dst = z + blk * 16;
+    const float u1 = 1.f - (float)(src[j] & 0xFFFFFFu) * 5.9604644775390625e-08f;
+    const float u2 = (float)(src[j + 8] & 0xFFFFFFu) * 5.9604644775390625e-08f;
+    const float radius = sqrtf(-2.f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    dst[j] = radius * cs;
+    dst[j + 8] = radius * sn;
+}
+extern "C" {
+int gct_normal_from_mt(const uint32_t* raw, float* z, int64_t n, void* stream) {
+    GCT_REQUIRE(raw && z && n >= 16, "normal_from_mt: needs n >= 16 elements (smaller draws take torch's scalar path)");
+    const long long nblocks = n / 16;
+    normal_from_mt_kernel<<<(unsigned)cdiv(nblocks * 8, 256), 256, 0, ST(stream)>>>(raw, z, nblocks);
+    GCT_LAUNCH_CHECK();
+    if (n % 16) {        // the last 16 elements are recomputed from 16 fresh draws (stream order: after the full blocks)
+        normal_from_mt_kernel<<<1, 8, 0, ST(stream)>>>(raw + n, z + n - 16, 1);
+        GCT_LAUNCH_CHECK();
+    }
     return GCT_OK;
 }
 

@@ -20,6 +20,7 @@
 
 extern int g_gct_persist;
 extern int g_gct_tma_store;
+extern int g_gct_sm_budget;
 extern int g_gct_ew4;
 extern int g_gct_pair;
 
@@ -1036,7 +1037,9 @@ static int sm_count() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    // SM budget of the persistent kernels: leaving a few SMs free lets a concurrently running NCCL kernel (overlapped gradient
+    // exchange) get its CTAs without pushing some of a persistent GEMM's CTAs into a second wave
+    return (g_gct_sm_budget > 0 && g_gct_sm_budget < n) ? g_gct_sm_budget : n;
 }
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int EW = 2>

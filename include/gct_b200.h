@@ -92,6 +92,7 @@ int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring s
 int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue (default on) */
 int gct_set_cta_pair_gemm(int level);               /* persistent GEMM over CTA pairs (tcgen05.mma.cta_group::2): 0 off, 1 K-major
                                                        operands only, 2 (default) also dgrad / wgrad operand layouts */
+int gct_set_sm_budget(int sms);                     /* persistent GEMMs use at most this many SMs (0 = all): room for a concurrent NCCL kernel */
 int gct_set_zattn_config(int ctas_per_sm);          /* tuning: latent-space cross-attention compiled for 3 (default) or 4 resident CTAs per SM */
 int gct_set_attention_bias_grad_fused(int enabled); /* bias gradients of the q/k/v projections from the tcgen05 attention backward's
                                                        write-out (default on) instead of separate column-sum launches */
@@ -209,6 +210,13 @@ int64_t gct_detokenize(const int16_t* ids, int64_t n, int width, const char* voc
  * key[624], pos, has_gauss, cached_gaussian = np.random.get_state()[1:5]).  out[n] doubles. */
 int gct_toklen_draw(uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* cached_gauss, const double* cdf, int n_edges,
                     const double* centres, double width, int64_t n, double* out);
+/* Seed-faithful latent draw (Inference/sampling_tool.py:93-97 `sample_z`: torch.normal on the CPU generator, ~7 ns per element
+ * in PyTorch): gct_mt19937_fill advances PyTorch's CPU MT19937 engine (state words / left / next as stored in
+ * torch.get_rng_state()) and writes the raw 32-bit outputs, one per element, into a (pinned) host buffer; gct_normal_from_mt
+ * applies at::normal_fill's uniform conversion and 16-element Box-Muller blocks on the device (raw must hold n + 16 words when
+ * n % 16 != 0).  Same stream, same values to the rounding of logf / sincosf. */
+int gct_mt19937_fill(uint64_t* state624, int32_t* left, uint64_t* next, uint32_t* out_host, int64_t n);
+int gct_normal_from_mt(const uint32_t* raw, float* z, int64_t n, void* stream);
 /* the step's attention kernel on its own (unit tests, roofline timing): one query per (batch, head) over
  * n_cached cached keys (+ this step's knew/vnew row, which is appended to the cache when non-NULL) */
 int gct_decode_attention(const void* q, int ldq, const void* knew, const void* vnew, int ldnew, void* kcache, void* vcache,

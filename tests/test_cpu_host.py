@@ -239,3 +239,23 @@ def test_gradient_buckets_cover_the_flat_buffer_once_and_follow_the_backward_ord
                 assert st == (N - 1 - l if parts[0] == "decoder" else 2 * N - 1 - l), name
             else:
                 assert st == 2 * N, name
+
+
+def test_mt19937_fill_continues_torchs_cpu_generator(built):
+    """gct_mt19937_fill on a copy of torch.get_rng_state(): the raw outputs give exactly torch.rand's uniforms and the engine
+    ends in exactly torch's state, from any position inside a 624-word block and for any count."""
+    lib = built.lib()
+    for pre in (0, 1, 623, 624, 777):
+        torch.manual_seed(5)
+        if pre:
+            torch.rand(pre)
+        for n in (1, 15, 16, 623, 624, 625, 5000, 1248 + 3):
+            keep = torch.get_rng_state().clone()
+            sn = keep.clone().numpy()
+            raw = np.empty(n, dtype=np.uint32)
+            built.check(lib.gct_mt19937_fill(sn[24:24 + 4992].view(np.uint64).ctypes.data, sn[8:12].view(np.int32).ctypes.data,
+                                             sn[16:24].view(np.uint64).ctypes.data, raw.ctypes.data, n))
+            u = torch.rand(n).numpy()
+            assert np.array_equal((raw & 0xFFFFFF).astype(np.float32) * np.float32(2.0 ** -24), u), (pre, n)
+            assert np.array_equal(torch.get_rng_state().numpy()[:5016], sn[:5016]), (pre, n)
+            torch.set_rng_state(keep)
