@@ -10,7 +10,7 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one
     HOST buffers (pinned latents + lengths in, Python strings out).  `e2e_public_call`: sample_smiles(n) with NO inputs
     (lengths and latents drawn inside the call) for the reference-faithful host draw and for z_on_device=True;
   * "cfg5": scavaetf scaffold-conditioned sampling (20-token scaffold prefix), --cfg5-draws per rank;
-  * "train": one optimiser step (fwd + loss + bwd [+ overlapped NCCL all-reduce] + Adam) of cfg 3 (pvaetf B=512 S=78, N=1
+  * "train": one optimiser step (fwd + loss + bwd [+ NCCL all-reduce of the gradients] + Adam) of cfg 3 (pvaetf B=512 S=78, N=1
     only) and cfg 4 (pscavaetf B=512/GPU S=98 data-parallel, every N including 1; also the authors' batch 64), each with its
     own tensor roofline; at N>1 "dp_parity" compares the N-rank gradients with a 1-rank run of the same global batch;
   * "gpu_eager_baseline": the oracle port (= the reference's arithmetic) run eagerly in fp32 on the same GPU, TF32 off / on.
@@ -309,7 +309,7 @@ TRAIN_CASES = {
 }
 
 
-def run_training(args, rank, world, dev, case="cfg3", B=512, steps=None, grad_exchange="overlap"):
+def run_training(args, rank, world, dev, case="cfg3", B=512, steps=None, grad_exchange="nccl"):
     """One optimiser step = masks + forward + loss + backward [+ NCCL gradient exchange] + fused Adam (FusedTrainer.step).
     `roofline`: algorithmic FLOPs (SURVEY 8d formula, fwd+bwd = 3x fwd, attention dense) / device time / sustained bf16 peak."""
     from gct_plus_b200.Model import Cvaetf
@@ -735,7 +735,7 @@ def main():
         train["cfg4"] = run_training(args, rank, world, dev, "cfg4", args.train_batch)
         train["cfg4_batch64"] = run_training(args, rank, world, dev, "cfg4", 64, steps=min(args.train_steps, 30))
         if world > 1:
-            train["cfg4_unoverlapped"] = run_training(args, rank, world, dev, "cfg4", args.train_batch, grad_exchange="nccl")
+            train["cfg4_overlapped_exchange"] = run_training(args, rank, world, dev, "cfg4", args.train_batch, grad_exchange="overlap")
             dp_parity = run_dp_parity(rank, world, dev)
         if rank == 0 and not args.no_cpu:
             train["input_pipeline"] = run_input_pipeline(dev)

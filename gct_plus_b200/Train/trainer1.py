@@ -175,7 +175,7 @@ class FusedTrainer:
     """
 
     def __init__(self, model, model_type, pad_id=1, lr=1e-4, betas=(0.9, 0.98), eps=1e-9, warmup=8000,
-                 use_cond2dec=False, process_group=None, grad_exchange="overlap", force_exchange=False):
+                 use_cond2dec=False, process_group=None, grad_exchange="nccl", force_exchange=False):
         self.model, self.model_type, self.pad_id = model, model_type, pad_id
         self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
         if use_cond2dec or (getattr(model, 'use_cond2dec', False) and int(model.nconds) > 0):
@@ -188,9 +188,13 @@ class FusedTrainer:
         self.variational = model._variational()
         self.pg = process_group
         self.world = world_info(process_group)[1]
-        # gradient exchange across ranks: "overlap" = bucketed NCCL all-reduce on a side stream while the backward still runs
-        # (gct_backward_dp, DDP's behaviour), "nccl" = one all-reduce of the flat buffer after the backward through the
-        # library's communicator, "torch" = the same through torch.distributed (any backend)
+        # gradient exchange across ranks: "nccl" (default) = one all-reduce of the flat buffer after the backward through the
+        # library's communicator; "overlap" = bucketed NCCL all-reduce on a side stream while the backward still runs
+        # (gct_backward_dp, DDP's behaviour); "torch" = one all-reduce through torch.distributed (any backend).
+        # [B200, 2 GPUs, cfg 4, profiles/r02_ab_dp_exchange_2gpu.txt] no exchange 27.92 ms, "nccl" 28.51-28.55, "overlap"
+        # 28.55-28.73: the NCCL kernels do run concurrently with the weight-gradient GEMMs (profiles/r02_dp_overlap_trace_2gpu.json:
+        # 100 % of their 1.0 ms), but every SM they occupy pushes CTAs of a statically scheduled persistent GEMM into a second
+        # wave, which costs what the overlap hides -- so the plain form is the default.
         assert grad_exchange in ("overlap", "nccl", "torch", "none")
         if grad_exchange == "none":        # single-process semantics even inside an initialised process group (reference runs, parity checks)
             self.world, grad_exchange = 1, "torch"
