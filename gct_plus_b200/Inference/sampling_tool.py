@@ -188,8 +188,8 @@ class Sampling:
         lib = L.lib()
         extra = 16 if numel % 16 else 0
         raw = getattr(self, '_raw_host', None)
-        if raw is None or raw.numel() < numel + extra:
-            raw = self._raw_host = torch.empty(numel + extra, dtype=torch.int32).pin_memory()
+        if raw is None or raw.numel() < numel + extra:          # grow-only pinned staging buffer, 25 % headroom: latent lengths vary call to call
+            raw = self._raw_host = torch.empty(int((numel + extra) * 1.25), dtype=torch.int32, pin_memory=True)
         state = torch.get_rng_state()
         sn = state.numpy()
         words = sn[24:24 + 624 * 8].view(np.uint64)
