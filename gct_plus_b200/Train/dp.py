@@ -48,14 +48,12 @@ def gradient_buckets(offsets: np.ndarray, n_layers: int, total: int, num_global_
     N = n_layers
     enc0 = [int(offsets[num_global_slots + l * enc_slots]) for l in range(N)]
     dec0 = [int(offsets[num_global_slots + N * enc_slots + l * dec_slots]) for l in range(N)]
-    placed = sorted(int(o) for o in offsets if o >= 0)
-    after = [o for o in placed if o > dec0[-1] and o not in set(offsets[num_global_slots + N * enc_slots + (N - 1) * dec_slots:
-                                                                num_global_slots + N * enc_slots + N * dec_slots].tolist())]
-    dec_end = min(after) if after else None
-    if dec_end is None:       # nothing placed behind the last decoder layer: its last slot (linear_2.bias, d elements) ends the region
-        last = int(offsets[num_global_slots + N * enc_slots + N * dec_slots - 1])
-        d_model = int(offsets[num_global_slots + 1] - offsets[num_global_slots])      # norm_1.alpha -> norm_1.bias spacing >= d
-        dec_end = min(total, last + d_model)
+    # end of the last decoder layer = end of its last slot (ff.linear_2.bias, d_model elements, padded to the 64-element slot
+    # alignment of engine._flatten); whatever follows (parameters no kernel reads, e.g. vaetf's encoder.fc_mu) is "the rest"
+    last = int(offsets[num_global_slots + N * enc_slots + N * dec_slots - 1])
+    d_model = int(offsets[num_global_slots + 1] - offsets[num_global_slots])      # layer 0: norm_1.alpha -> norm_1.bias
+    dec_end = min(total, last + d_model)
+    assert all(int(o) < dec_end for o in offsets if o >= 0), "a slot is laid out behind the decoder layers"
     starts = enc0 + dec0 + [dec_end]
     assert starts == sorted(starts), "layer slots are not laid out in order"
     out = []
