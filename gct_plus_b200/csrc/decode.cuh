@@ -257,16 +257,19 @@ static int launch_decode_attn(const DecAttnParams& p, int B, cudaStream_t st) {
 // x[b,:] = table[ys[b,pos]]*sqrt(d) + pe[pos + pe_off]; key_valid[b,pos] = tok != pad
 __global__ void decode_embed_kernel(const int64_t* __restrict__ ys, int ys_stride, int pos, const float* __restrict__ table,
                                     int vocab, const float* __restrict__ pe, int pe_off, int d, float scale, int pad_id,
-                                    float* __restrict__ x, uint8_t* __restrict__ key_valid, int kv_stride) {
-    const int b = blockIdx.x;
+                                    float* __restrict__ x, uint8_t* __restrict__ key_valid, int kv_stride, int B) {
+    // one warp per batch row, four rows per CTA (a CTA per row left the 30 000-row launch bound by CTA issue, not by its 61 MB)
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     pdl_wait();
     pdl_launch_dependents();
+    if (b >= B) return;
     long long t = ys[(size_t)b * ys_stride + pos];
-    if (threadIdx.x == 0) key_valid[(size_t)b * kv_stride + pos] = (t != pad_id);
+    if (lane == 0) key_valid[(size_t)b * kv_stride + pos] = (t != pad_id);
     if (t < 0 || t >= vocab) t = 0;
     const float* e = table + (size_t)t * d;
     const float* per = pe + (size_t)(pos + pe_off) * d;
-    for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    for (int c = lane * 4; c < d; c += 128) {
         float4 ev = *reinterpret_cast<const float4*>(e + c);
         float4 pv = *reinterpret_cast<const float4*>(per + c);
         *reinterpret_cast<float4*>(x + (size_t)b * d + c) =
@@ -337,24 +340,30 @@ __global__ void decode_sample_kernel(SampleParams p) {
         if (p.uniforms) u = p.uniforms[b];
         else u = (float)(mix32(p.seed ^ mix32((uint32_t)p.step * 0x9e3779b9U + (uint32_t)b)) >> 8) * (1.0f / 16777216.0f);
         // sequential cumulative sum in index order (same order as a CPU cumsum); threshold u*total
+        // (only the 32-column blocks the vocabulary reaches: V = 27-32 for MOSES is one block)
+        const int nblk = (p.V + 31) >> 5;
         float total = 0.f;
+#pragma unroll
         for (int i = 0; i < 4; ++i)
-            for (int l = 0; l < 32; ++l) {
-                const float pv = __shfl_sync(0xffffffffu, v[i], l);
-                if (i * 32 + l < p.V) total += pv;
-            }
+            if (i < nblk)
+                for (int l = 0; l < 32; ++l) {
+                    const float pv = __shfl_sync(0xffffffffu, v[i], l);
+                    if (i * 32 + l < p.V) total += pv;
+                }
         const float thr = u * total;
         float run = 0.f;
         int pick = -1;
+#pragma unroll
         for (int i = 0; i < 4; ++i)
-            for (int l = 0; l < 32; ++l) {
-                const float pv = __shfl_sync(0xffffffffu, v[i], l);
-                const int c = i * 32 + l;
-                if (c < p.V) {
-                    run += pv;
-                    if (pick < 0 && run > thr) pick = c;
+            if (i < nblk)
+                for (int l = 0; l < 32; ++l) {
+                    const float pv = __shfl_sync(0xffffffffu, v[i], l);
+                    const int c = i * 32 + l;
+                    if (c < p.V) {
+                        run += pv;
+                        if (pick < 0 && run > thr) pick = c;
+                    }
                 }
-            }
         if (pick < 0) pick = p.V - 1;
         tok = pick;
     }

@@ -890,8 +890,8 @@ template <typename T>
 static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int pos, int step, bool sample) {
     const int d = m.d, dff = m.dff, N = m.N, B = W.B, Sm = W.Sm, Lmax = W.Lmax;
     cudaStream_t st = m.st;
-    GCT_CUDA(launch_k(decode_embed_kernel, dim3(B), dim3(128), 0, st, true, (const int64_t*)D.ys, D.max_len, pos, m.P(GCT_SLOT_DEC_EMB),
-                      m.c.trg_vocab, m.P(GCT_SLOT_DEC_PE), 0, d, sqrtf((float)d), m.c.pad_id, W.x, W.key_valid, Lmax));
+    GCT_CUDA(launch_k(decode_embed_kernel, dim3(cdiv(B, 4)), dim3(128), 0, st, true, (const int64_t*)D.ys, D.max_len, pos, m.P(GCT_SLOT_DEC_EMB),
+                      m.c.trg_vocab, m.P(GCT_SLOT_DEC_PE), 0, d, sqrtf((float)d), m.c.pad_id, W.x, W.key_valid, Lmax, B));
     for (int l = 0; l < N; ++l) {
         GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), W.xn, nullptr, B));
         GCT_TRY(m.linear_T(W.xn, B, d, m.dec_slot(l, D_QKV_W), m.dec_slot(l, D_QKV_B), 3 * d, W.qkv));
