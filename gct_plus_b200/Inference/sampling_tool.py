@@ -84,6 +84,8 @@ class Sampling:
         self.pipeline_rows = kwargs.get('pipeline_rows', None)
         self.z_on_device = kwargs.get('z_on_device', False)
         self.host_z_exact = kwargs.get('host_z_exact', False)
+        self.decode_streams = kwargs.get('decode_streams', None)   # row groups decoded on concurrent streams (None = by batch size)
+        self._group_streams = []
         self._host_s_per_row = 0.0
         self._side_stream = None
         # static decode buffers / captured CUDA graphs per request shape: small LRUs (each entry pins O(n * Lz * latent)
@@ -255,6 +257,17 @@ class Sampling:
                     break
         return ys
 
+    def _row_groups(self, n, probe):
+        """How many independent row groups a decode of n rows runs as.  Small batches are launch-latency bound (a step is a
+        chain of 70 dependent kernels of a few microseconds each, whatever the batch): rows are independent, so the batch is
+        cut into groups whose chains run on concurrent streams (one CUDA graph with parallel branches per chunk of steps)."""
+        if probe:
+            return 1
+        g = self.decode_streams
+        if g is None:
+            g = 1 if n > 4096 else max(1, min(4, n // 96))
+        return max(1, min(int(g), n))
+
     def _decode_cached(self, zs, ys, src_mask, dconds=None, uniforms=None, idle_work=None, forced=None, probs_out=None,
                        logits_out=None):
         lib, model, dev = L.lib(), self.model, torch.device(self.device)
@@ -266,17 +279,20 @@ class Sampling:
         Lzp = (Lz + self.latent_bucket - 1) // self.latent_bucket * self.latent_bucket
         greedy = int(self.decode_algo == 'greedy')
         nc = self.cond_dim
+        probe = forced is not None or probs_out is not None or logits_out is not None
+        G = self._row_groups(n, probe)
+        bounds = [(n * g // G, n * (g + 1) // G) for g in range(G)]
 
-        key = (n, Lzp, max_len, t0, greedy, nc, model.compute_dtype)
+        key = (n, Lzp, max_len, t0, greedy, nc, model.compute_dtype, G)
         st = self._static.get(key)
         if st is None:
             st = dict(zs=torch.zeros((n, Lzp, self.latent_dim), device=dev, dtype=torch.float32),
                       mask=torch.zeros((n, Lzp), device=dev, dtype=torch.uint8),
                       ys=torch.zeros((n, max_len), device=dev, dtype=torch.int64),
-                      status=torch.zeros(2, device=dev, dtype=torch.int32),
-                      uni=torch.zeros((steps, n), device=dev, dtype=torch.float32),
+                      status=torch.zeros((G, 2), device=dev, dtype=torch.int32),
+                      uni=[torch.zeros((steps, hi - lo), device=dev, dtype=torch.float32) for lo, hi in bounds],
                       dconds=torch.zeros((n, max(nc, 1)), device=dev, dtype=torch.float32),
-                      status_host=torch.zeros(2, dtype=torch.int32).pin_memory())
+                      status_host=torch.zeros((G, 2), dtype=torch.int32).pin_memory())
             self._static[key] = st
             while len(self._static) > self.cache_shapes:
                 old, _ = self._static.popitem(last=False)
@@ -293,38 +309,56 @@ class Sampling:
         if nc > 0:
             st['dconds'].copy_(dconds.float(), non_blocking=True)
         if not greedy:
-            if uniforms is not None:
-                st['uni'].copy_(uniforms, non_blocking=True)
-            else:
-                st['uni'].uniform_()
-        ws_bytes = lib.gct_decode_workspace_bytes(C.byref(cfg), n, Lzp, max_len)
-        ws = model._ws.get('decode', ws_bytes, dev)
+            for (lo, hi), u in zip(bounds, st['uni']):
+                if uniforms is not None:
+                    u.copy_(uniforms[:, lo:hi], non_blocking=True)
+                else:
+                    u.uniform_()
         w = model._weights()
-        dec = L.GctDecode(B=n, Lz=Lzp, max_len=max_len, prefix_len=t0, greedy=greedy, eos_id=int(self.eos_id), seed=0,
-                          zs=st['zs'].data_ptr(), src_mask=st['mask'].data_ptr(),
-                          dconds=st['dconds'].data_ptr() if nc > 0 else None,
-                          uniforms=None if greedy else st['uni'].data_ptr(), ys=st['ys'].data_ptr(),
-                          status=st['status'].data_ptr(), forced=L._p(forced), probs_out=L._p(probs_out),
-                          logits_out=L._p(logits_out))
-        probe = forced is not None or probs_out is not None or logits_out is not None
         if forced is not None:
             assert forced.is_cuda and forced.dtype == torch.int64 and tuple(forced.shape) == (n, max_len) and forced.is_contiguous()
         for t in (probs_out, logits_out):
             assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
                                  and tuple(t.shape) == (steps, n, cfg.trg_vocab))
+        wss, decs = [], []
+        for g, (lo, hi) in enumerate(bounds):
+            ng = hi - lo
+            ws = model._ws.get(('decode', g), lib.gct_decode_workspace_bytes(C.byref(cfg), ng, Lzp, max_len), dev)
+            wss.append(ws)
+            decs.append(L.GctDecode(B=ng, Lz=Lzp, max_len=max_len, prefix_len=t0, greedy=greedy, eos_id=int(self.eos_id), seed=0,
+                                    zs=st['zs'][lo:].data_ptr(), src_mask=st['mask'][lo:].data_ptr(),
+                                    dconds=st['dconds'][lo:].data_ptr() if nc > 0 else None,
+                                    uniforms=None if greedy else st['uni'][g].data_ptr(), ys=st['ys'][lo:].data_ptr(),
+                                    status=st['status'][g].data_ptr(), forced=L._p(forced), probs_out=L._p(probs_out),
+                                    logits_out=L._p(logits_out)))
+        if G > 1 and len(self._group_streams) < G - 1:
+            self._group_streams += [torch.cuda.Stream(device=dev) for _ in range(G - 1 - len(self._group_streams))]
+
+        def on_groups(fn):
+            """fn(g) for every row group: group 0 on the current stream, the others forked onto side streams and joined back."""
+            cur = torch.cuda.current_stream(dev)
+            fn(0)
+            for g in range(1, G):
+                sg = self._group_streams[g - 1]
+                sg.wait_stream(cur)
+                with torch.cuda.stream(sg):
+                    fn(g)
+            for g in range(1, G):
+                cur.wait_stream(self._group_streams[g - 1])
 
         def begin():
-            L.check(lib.gct_decode_begin(C.byref(cfg), C.byref(w), C.byref(dec), L.ptr(ws), ws.numel(), L.stream_ptr()),
-                    "gct_decode_begin")
+            on_groups(lambda g: L.check(lib.gct_decode_begin(C.byref(cfg), C.byref(w), C.byref(decs[g]), L.ptr(wss[g]), wss[g].numel(),
+                                                             L.stream_ptr()), "gct_decode_begin"))
 
         def run(s0, s1):
-            L.check(lib.gct_decode_steps(C.byref(cfg), C.byref(w), C.byref(dec), s0, s1, L.ptr(ws), ws.numel(),
-                                         L.stream_ptr()), "gct_decode_steps")
+            on_groups(lambda g: L.check(lib.gct_decode_steps(C.byref(cfg), C.byref(w), C.byref(decs[g]), s0, s1, L.ptr(wss[g]),
+                                                             wss[g].numel(), L.stream_ptr()), "gct_decode_steps"))
 
         chunks = [(s, min(steps, s + self.sync_every)) for s in range(0, steps, self.sync_every)]
-        gkey = key + (ws.data_ptr(), w.params_f32, w.params_bf16, self.sync_every)
-        for gk in [gk for gk in self._graphs if gk[len(key)] != ws.data_ptr()]:
-            del self._graphs[gk]                # the grow-only workspace was reallocated: those graphs point at freed memory
+        wptrs = tuple(ws.data_ptr() for ws in wss)
+        gkey = key + (wptrs, w.params_f32, w.params_bf16, self.sync_every)
+        for gk in [gk for gk in self._graphs if gk[:len(key)] == key and gk[len(key)] != wptrs]:
+            del self._graphs[gk]                # a grow-only workspace was reallocated: those graphs point at freed memory
         use_graph = self.use_cuda_graph and not probe      # probe buffers are per call: not baked into a graph
         graphs = self._graphs.get(gkey) if use_graph else None
         if use_graph and graphs is None and st.get('warm'):
@@ -339,6 +373,12 @@ class Sampling:
             # capture does not execute: fall through to replay below
         st['warm'] = True
         steps_run = steps
+
+        def all_done():
+            st['status_host'].copy_(st['status'], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return int(st['status_host'][:, 0].sum()) >= n      # every group counts its own rows that have emitted <eos>
+
         if graphs is not None:
             graphs[0].replay()
         else:
@@ -350,15 +390,10 @@ class Sampling:
                 run(s0, s1)
             if idle_work is not None:
                 idle_work.step()          # bounded slice of host work while the GPU runs this chunk
-            if s1 < steps:
-                st['status_host'].copy_(st['status'], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                if int(st['status_host'][0]) >= n:
-                    break
-        st['status_host'].copy_(st['status'], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        if int(st['status_host'][0]) >= n:
-            steps_run = int(st['status_host'][1]) + 1
+            if s1 < steps and all_done():
+                break
+        if all_done():
+            steps_run = int(st['status_host'][:, 1].max()) + 1      # the step at which the LAST group completed
         self.last_decode_steps = steps_run
         return st['ys'][:, :t0 + steps_run].clone()
 

@@ -14,6 +14,7 @@ dev = torch.device("cuda:0")
 bench.BATCH = int(os.environ.get("GCT_PROFILE_B", "512"))
 s = bench.build_sampler(dev)
 s.use_cuda_graph = False
+s.decode_streams = 1          # one row group: the window below drives the library directly
 inputs = bench.sample_inputs(s, 2, seed=5, pinned=False)
 toklen, zs = inputs[0]
 NB = zs.size(0)
@@ -26,10 +27,10 @@ torch.cuda.synchronize()
 lib, model = L.lib(), s.model
 cfg = model._cfg()
 st = next(iter(s._static.values()))
-ws = model._ws.get('decode', 0, dev)
+ws = model._ws.get(('decode', 0), 0, dev)
 w = model._weights()
 dec = L.GctDecode(B=NB, Lz=st['zs'].size(1), max_len=st['ys'].size(1), prefix_len=1, greedy=0, eos_id=3, seed=0,
-                  zs=st['zs'].data_ptr(), src_mask=st['mask'].data_ptr(), dconds=None, uniforms=st['uni'].data_ptr(),
+                  zs=st['zs'].data_ptr(), src_mask=st['mask'].data_ptr(), dconds=None, uniforms=st['uni'][0].data_ptr(),
                   ys=st['ys'].data_ptr(), status=st['status'].data_ptr())
 L.check(lib.gct_decode_begin(C.byref(cfg), C.byref(w), C.byref(dec), L.ptr(ws), ws.numel(), L.stream_ptr()))
 L.check(lib.gct_decode_steps(C.byref(cfg), C.byref(w), C.byref(dec), 0, 48, L.ptr(ws), ws.numel(), L.stream_ptr()))

@@ -217,3 +217,43 @@ def test_seed_faithful_latent_draw_matches_torch_normal(shape):
     torch.manual_seed(321)
     torch.rand(100)
     assert torch.equal(s.sample_z(L_, n), want)
+
+
+@pytest.mark.parametrize("groups", [1, 2, 3])
+@pytest.mark.parametrize("name", ["vaetf_full", "pscavaetf_small"])
+def test_row_groups_on_concurrent_streams_decode_identically(name, groups):
+    """Small batches decode as independent row groups on concurrent streams (one CUDA graph with parallel branches per chunk of
+    steps): greedy fp32 tokens must equal the reference's recorded decode for any group count (unequal group sizes
+    included), eagerly, while capturing, and on replay; the <eos> early stop must see all groups."""
+    fx = load_golden(name)
+    s, _ = _sampler(fx, "fp32", decode_streams=groups, sync_every=3)
+    d = fx["decode"]
+    kw = dict(zs=d["zs"].to(DEV), ys=d["ys0"].to(DEV), src_mask=d["src_mask"].to(DEV))
+    if "dconds" in d:
+        kw["dconds"] = d["dconds"].to(DEV)
+    for _ in range(3):
+        ys = s.decode(**kw)
+        assert torch.equal(ys.cpu(), d["ys"]), (name, groups)
+    # every row emits <eos> at the first step: the loop stops after it whatever the grouping
+    with torch.no_grad():
+        s.model.out.bias[3] += 50.0
+    for _ in range(3):
+        ys = s.decode(**kw)
+        assert ys.size(1) == d["ys0"].size(1) + 1 and bool((ys[:, -1] == 3).all())
+
+
+def test_row_groups_multinomial_draws_follow_the_supplied_uniforms():
+    """With supplied uniforms the grouped decode draws exactly what the single-group decode draws (each group reads its own
+    columns of the [steps, n] uniforms)."""
+    fx = load_golden("vaetf_full")
+    n, Lz = 37, 12
+    g = torch.Generator().manual_seed(4)
+    zs = torch.randn(n, Lz, 128, generator=g).to(DEV)
+    ys0 = torch.full((n, 1), 2, dtype=torch.long, device=DEV)
+    mask = torch.ones(n, 1, Lz, dtype=torch.bool, device=DEV)
+    u = torch.rand(7, n, generator=g).to(DEV)
+    outs = []
+    for groups in (1, 4):
+        s, _ = _sampler(fx, "fp32", algo="multinomial", max_strlen=8, decode_streams=groups, use_cuda_graph=False)
+        outs.append(s._decode_cached(zs=zs, ys=ys0, src_mask=mask, uniforms=u).cpu())
+    assert torch.equal(outs[0], outs[1])
