@@ -337,11 +337,11 @@ class Sampling:
         def on_groups(fn):
             """fn(g) for every row group: group 0 on the current stream, the others forked onto side streams and joined back."""
             cur = torch.cuda.current_stream(dev)
+            for g in range(1, G):                       # fork BEFORE any group's work is enqueued on the current stream
+                self._group_streams[g - 1].wait_stream(cur)
             fn(0)
             for g in range(1, G):
-                sg = self._group_streams[g - 1]
-                sg.wait_stream(cur)
-                with torch.cuda.stream(sg):
+                with torch.cuda.stream(self._group_streams[g - 1]):
                     fn(g)
             for g in range(1, G):
                 cur.wait_stream(self._group_streams[g - 1])
