@@ -258,15 +258,15 @@ class Sampling:
         return ys
 
     def _row_groups(self, n, probe):
-        """How many independent row groups a decode of n rows runs as.  Small batches are launch-latency bound (a step is a
-        chain of 70 dependent kernels of a few microseconds each, whatever the batch): rows are independent, so the batch is
-        cut into groups whose chains run on concurrent streams (one CUDA graph with parallel branches per chunk of steps)."""
-        if probe:
+        """How many independent row groups a decode of n rows runs as (`decode_streams` sampler kwarg, default 1).  Rows are
+        independent, so a batch can be cut into groups whose kernel chains run on concurrent streams (one CUDA graph with
+        parallel branches per chunk of steps).  [B200] it does not pay at any batch size (profiles/r02_ab_streams.txt: batch 512
+        46.2 ms as one group, 54.6 as two, 55.3 as four; batch 128: 38.9 / 41.6 / 52.5): a step costs ~37 ms / 99 of fixed
+        per-kernel latency whatever the rows, but the small-tile GEMMs already occupy every SM's CTA slots (shared memory),
+        so the branches serialise instead of overlapping.  Kept as an option for other shapes; the default is one group."""
+        if probe or not self.decode_streams:
             return 1
-        g = self.decode_streams
-        if g is None:
-            g = 1 if n > 4096 else max(1, min(4, n // 96))
-        return max(1, min(int(g), n))
+        return max(1, min(int(self.decode_streams), n))
 
     def _decode_cached(self, zs, ys, src_mask, dconds=None, uniforms=None, idle_work=None, forced=None, probs_out=None,
                        logits_out=None):
