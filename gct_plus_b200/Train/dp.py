@@ -105,6 +105,9 @@ class GradExchange:
             self.comm = C.c_void_p()
 
     def __del__(self):
+        import sys
+        if sys.is_finalizing():      # the CUDA context / NCCL may already be gone at interpreter shutdown: leave the handle to the OS
+            return
         try:
             self.close()
         except Exception:
