@@ -178,13 +178,13 @@ class FusedTrainer:
                  use_cond2dec=False, process_group=None, grad_exchange="nccl", force_exchange=False):
         self.model, self.model_type, self.pad_id = model, model_type, pad_id
         self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
-        if use_cond2dec or (getattr(model, 'use_cond2dec', False) and int(model.nconds) > 0):
-            # the reference loss adds MSE(prop_fc(logits[:, :nconds])) and pairs targets with logits[:, nconds:]
-            # (trainer1.py:24-26, cvaetf.py:184-186); the fused step has no property head -> refuse instead of
-            # training on a wrong loss.  run_epoch / loss_function (autograd path) cover use_cond2dec.
-            raise L.GctError("FusedTrainer does not implement the use_cond2dec property head (prop_fc + MSE); "
-                             "train use_cond2dec models through run_epoch / loss_function")
-        self.use_cond2dec = False
+        # use_cond2dec (cvaetf.py:103-105,184-186; trainer1.py:24-26): nconds property rows precede the target rows of the
+        # decoder; they carry no cross-entropy term, the prop_fc head on them adds MSE(sum) to the loss (gct_prop_head_fwd_bwd)
+        self.use_cond2dec = bool(getattr(model, 'use_cond2dec', False) and int(model.nconds) > 0)
+        if use_cond2dec and not self.use_cond2dec:
+            raise L.GctError("use_cond2dec=True but the model was not built with use_cond2dec / nconds > 0")
+        if self.use_cond2dec and model_type not in ('pvaetf', 'pscavaetf'):
+            raise L.GctError("use_cond2dec needs a property-conditioned model type (pvaetf / pscavaetf)")
         self.variational = model._variational()
         self.pg = process_group
         self.world = world_info(process_group)[1]
@@ -216,14 +216,17 @@ class FusedTrainer:
         dev = m._flat.device
         src, trg = batch['src'].contiguous(), batch['trg']
         trg_in = trg[:, :-1].contiguous()
-        ys_mol = trg[:, 1:].contiguous().view(-1)
         B, S = src.shape
         T = trg_in.size(1)
         nc = cfg.nconds if self.has_conds else 0
         econds = batch['econds'].float().contiguous() if nc else None
         dconds = batch['dconds'].float().contiguous() if nc else None
         Se, lat = nc + S, cfg.latent_dim
-        Ld = T + (nc if cfg.use_cond2dec else 0)
+        Ld = T + (nc if self.use_cond2dec else 0)
+        if self.use_cond2dec:       # property rows get the ignore index: no cross-entropy term, zero dlogits from the CE kernel
+            ys_mol = torch.cat([torch.full((B, nc), int(self.pad_id), dtype=trg.dtype, device=trg.device), trg[:, 1:]], dim=1).contiguous().view(-1)
+        else:
+            ys_mol = trg[:, 1:].contiguous().view(-1)
         key = (B, S, T)
         bf = self._bufs.get(key)
         if bf is None:
@@ -265,9 +268,17 @@ class FusedTrainer:
                                      B * Se * lat, float(beta), 1.0, L.ptr(self.out4), L.ptr(bf['dlogits']) if train else None,
                                      L.ptr(bf['dmu']) if train else None, L.ptr(bf['dlv']) if train else None, L.ptr(bf['lscr']), st),
                 "gct_loss_fwd_bwd")
+        if train:
+            self.grads.zero_()
+        if self.use_cond2dec:
+            off = m._offsets
+            gw, gb = int(off[18]), int(off[19])          # GCT_SLOT_PROP_W / GCT_SLOT_PROP_B
+            L.check(lib.gct_prop_head_fwd_bwd(L.ptr(bf['logits']), B, Ld, nc, V, m._flat[gw:].data_ptr(), m._flat[gb:].data_ptr(),
+                                              L.ptr(dconds), 1.0, None, L.ptr(self.out4), L.ptr(bf['dlogits']) if train else None,
+                                              self.grads[gw:].data_ptr() if train else None, self.grads[gb:].data_ptr() if train else None, st),
+                    "gct_prop_head_fwd_bwd")
         if not train:
             return self.out4
-        self.grads.zero_()
         if self.grad_exchange == "overlap":
             x = self.xchg
             L.check(lib.gct_backward_dp(C.byref(cfg), C.byref(w), C.byref(io), L.ptr(bf['dlogits']), L.ptr(bf['dmu']), L.ptr(bf['dlv']),
@@ -294,9 +305,10 @@ class FusedTrainer:
         self.lr = noam_lr(self.step_count, cfg.d_model, self.warmup)       # takes effect on the next step
         return self.out4
 
-    def read_losses(self):
-        loss, rce, _, kld = self.out4.tolist()
-        return loss, rce, kld
+    def read_losses(self, with_prop=False):
+        """(loss, RCE_mol, KLD) of the last step -- one host read; with_prop=True: (loss, RCE_mol, RCE_prop, KLD) like loss_function."""
+        loss, rce, rprop, kld = self.out4.tolist()
+        return (loss, rce, rprop, kld) if with_prop else (loss, rce, kld)
 
     # ------------------------------------------------------------------ checkpoint compatibility (SURVEY 8f rank 2)
     def state_dict(self):

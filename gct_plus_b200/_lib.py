@@ -86,6 +86,7 @@ _PROTOS = {
     "gct_cast_bf16_to_f32": (C.c_int, [vp, vp, i64, vp]),
     "gct_loss_scratch_bytes": (sz, [i64, i64]),
     "gct_loss_fwd_bwd": (C.c_int, [vp, C.c_int, C.c_int, vp, i64, C.c_int, vp, vp, i64, f32, f32, vp, vp, vp, vp, vp, vp]),
+    "gct_prop_head_fwd_bwd": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
     "gct_forward_workspace_bytes": (sz, [C.POINTER(GctConfig), C.c_int, C.c_int, C.c_int]),
     "gct_forward": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctIO), vp, sz, vp]),
     "gct_backward_scratch_bytes": (sz, [C.POINTER(GctConfig), C.c_int, C.c_int, C.c_int]),

@@ -394,6 +394,45 @@ __global__ void final_sum_kernel(const float* __restrict__ in, size_t n, float* 
     }
 }
 
+// Property head of use_cond2dec models (Model/cvaetf.py:184-186, Train/trainer1.py:24-26): prop[b,i] = logits[b,i,:] . w + b0 on the
+// first nc rows of every sample, RCE_prop = sum (prop - y)^2, and its backward: dlogits[b,i,:] = 2 g (prop - y) w (those rows carry
+// no cross-entropy term), dw += 2 g (prop - y) logits[b,i,:], db += 2 g (prop - y).  One warp per (b, i) row, V <= 128.
+__global__ void prop_head_kernel(const float* __restrict__ logits, int B, int Ld, int nc, int V, const float* __restrict__ w,
+                                 const float* __restrict__ b0, const float* __restrict__ target, float gscale, float* __restrict__ prop_out,
+                                 float* __restrict__ out4, float* __restrict__ dlogits, float* __restrict__ dw, float* __restrict__ db) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= B * nc) return;
+    const int b = r / nc, i = r % nc;
+    const float* lr = logits + ((size_t)b * Ld + i) * V;
+    float v[4], wv[4], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = k * 32 + lane;
+        v[k] = (c < V) ? lr[c] : 0.f;
+        wv[k] = (c < V) ? w[c] : 0.f;
+        dot = fmaf(v[k], wv[k], dot);
+    }
+    const float p = warp_sum(dot) + b0[0];
+    const float diff = p - target[r];
+    if (lane == 0) {
+        if (prop_out) prop_out[r] = p;
+        if (out4) { atomicAdd(out4 + 0, diff * diff); atomicAdd(out4 + 2, diff * diff); }
+    }
+    if (!dlogits) return;
+    const float g = 2.f * gscale * diff;
+    float* dr = dlogits + ((size_t)b * Ld + i) * V;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = k * 32 + lane;
+        if (c < V) {
+            dr[c] = g * wv[k];
+            atomicAdd(dw + c, g * v[k]);
+        }
+    }
+    if (lane == 0) atomicAdd(db, g);
+}
+
 // d(KL)/dmu = beta*mu ; d(KL)/dlv = beta*0.5*(exp(lv)-1)   (scaled by upstream gscale)
 __global__ void kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, size_t n, float g,
                               float* __restrict__ dmu, float* __restrict__ dlv) {

@@ -190,6 +190,16 @@ int gct_loss_fwd_bwd(const float* logits, int ld, int V, const int64_t* target, 
     return GCT_OK;
 }
 
+int gct_prop_head_fwd_bwd(const float* logits, int B, int Ld, int nc, int V, const float* w, const float* b0, const float* target,
+                          float gscale, float* prop_out, float* out4, float* dlogits, float* dw, float* db, void* stream) {
+    GCT_REQUIRE(logits && w && b0 && target && B >= 0 && nc >= 1 && nc <= Ld && V >= 1 && V <= 128, "prop_head: bad arguments");
+    GCT_REQUIRE(!dlogits || (dw && db), "prop_head: gradient outputs missing");
+    if (B == 0) return GCT_OK;
+    prop_head_kernel<<<cdiv((long long)B * nc, 8), 256, 0, ST(stream)>>>(logits, B, Ld, nc, V, w, b0, target, gscale, prop_out, out4, dlogits, dw, db);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
+}
+
 // ---------------- model ----------------
 }  // extern "C"
 template <typename T>

@@ -135,6 +135,13 @@ int gct_loss_fwd_bwd(const float* logits, int ld, int V, const int64_t* target, 
                      const float* mu, const float* log_var, int64_t n_latent, float beta, float gscale, float* out4,
                      float* dlogits, float* dmu, float* dlv, void* scratch, void* stream);
 
+/* Property head of use_cond2dec models (Model/cvaetf.py:184-186 `prop_fc` on the first nconds logit rows; Train/trainer1.py:24-26
+ * RCE_prop = mse_loss(sum)): prop_out[B,nc] (optional), out4[0] += RCE_prop, out4[2] += RCE_prop (after gct_loss_fwd_bwd filled
+ * out4), and with dlogits != NULL the backward: rows [0,nc) of every sample of dlogits [B,Ld,V] are SET to 2 g (prop - y) w,
+ * dw[V] / db[1] accumulate the head's parameter gradients. */
+int gct_prop_head_fwd_bwd(const float* logits, int B, int Ld, int nc, int V, const float* w, const float* b0, const float* target,
+                          float gscale, float* prop_out, float* out4, float* dlogits, float* dw, float* db, void* stream);
+
 /* ---- whole-model forward / backward: Vaetf.forward / Cvaetf.forward (+ .encode/.decode) ------ */
 typedef struct {
     const int64_t* src;        /* [B,S]                                  */

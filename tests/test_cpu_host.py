@@ -181,15 +181,20 @@ def test_flat_storage_survives_deepcopy_pickle_and_data_reassignment(tmp_path):
     assert torch.equal(b._flat, a._flat)
 
 
-def test_fused_trainer_rejects_the_property_head():
-    """use_cond2dec adds prop_fc + an MSE term and shifts the target rows (trainer1.py:24-26); the fused step does not
-    implement it and must refuse rather than train on a wrong loss."""
+def test_fused_trainer_property_head_configuration():
+    """use_cond2dec adds prop_fc + an MSE term and shifts the target rows (trainer1.py:24-26): FusedTrainer takes it from the
+    model and refuses an inconsistent request instead of training on a wrong loss."""
     from gct_plus_b200._lib import GctError
     from gct_plus_b200.Model import Cvaetf
     from gct_plus_b200.Train.trainer1 import FusedTrainer
     m = Cvaetf(32, 32, nconds=3, use_cond2dec=True, dropout=0.1, **ARCH_SMALL)
+    assert FusedTrainer(m, "pvaetf").use_cond2dec
     with pytest.raises(GctError):
-        FusedTrainer(m, "pvaetf")
+        FusedTrainer(m, "scavaetf")                      # property rows without a property-conditioned model type
+    m2 = Cvaetf(32, 32, nconds=3, use_cond2lat=True, dropout=0.1, **ARCH_SMALL)
+    assert not FusedTrainer(m2, "pvaetf").use_cond2dec
+    with pytest.raises(GctError):
+        FusedTrainer(m2, "pvaetf", use_cond2dec=True)    # the model has no property head
 
 
 def test_host_toklen_draw_continues_numpys_global_stream(built):

@@ -255,3 +255,40 @@ def test_fused_trainer_checkpoint_round_trip(tmp_path):
         if k.endswith("k_linear.bias"):
             continue          # mathematically zero gradient: rounding noise normalised by Adam (see test_fused_trainer...)
         assert rel_err(x, y) < 1e-4, k
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_fused_trainer_property_head_matches_reference(dtype):
+    """use_cond2dec through FusedTrainer (property rows in front of the target rows, prop_fc + MSE(sum) from
+    gct_prop_head_fwd_bwd): loss terms against the reference's recorded values, every gradient -- prop_fc's included --
+    against the oracle's autograd.  cvaetf.py:103-105,184-186; trainer1.py:24-26."""
+    fx = load_golden("pvaetf_c2d_small")
+    m, sd = build_model(fx, dtype, dropout=0.0)
+    m.train()
+    tr = FusedTrainer(m, "pvaetf", pad_id=1)
+    assert tr.use_cond2dec
+    eps = eps_for(fx)
+    tol = TOL[dtype]
+    # validation pass first (train=False: loss terms only, parameters untouched), then the optimiser step
+    tr.step(_to_dev(fx["batch"]), fx["beta"], eps_noise=eps.to(DEV), train=False)
+    l0 = tr.read_losses(with_prop=True)
+    assert abs(l0[0] - fx["loss"]) < tol * abs(fx["loss"]) and abs(l0[2] - fx["rprop"]) < tol * abs(fx["rprop"])
+    tr.step(_to_dev(fx["batch"]), fx["beta"], eps_noise=eps.to(DEV))
+    loss, rce, rprop, kld = tr.read_losses(with_prop=True)
+    assert abs(loss - fx["loss"]) < tol * abs(fx["loss"]) and abs(rce - fx["rce"]) < tol * abs(fx["rce"])
+    assert abs(rprop - fx["rprop"]) < tol * abs(fx["rprop"]) and abs(kld - fx["kld"]) < tol * abs(fx["kld"])
+    cfg = cfg_from_fixture(fx)
+    nc = fx["nconds"]
+    params = {k: v.clone().requires_grad_(not k.endswith("pe.pe")) for k, v in sd.items()}
+    po, mo, muo, lvo, _ = O.forward_propagation(params, cfg, fx["batch"], 1, eps)
+    ys_c = fx["batch"]["dconds"].unsqueeze(2).view(-1, nc, 1)
+    O.loss_function(fx["beta"], po, mo, ys_c, fx["batch"]["trg"][:, 1:].reshape(-1), muo, lvo, True, 1)[0].backward()
+    gmax = max(float(p.grad.abs().max()) for p in params.values() if p.grad is not None)
+    got = dict(zip([n for n, _ in m.named_parameters()], m.grad_views(tr.grads)))
+    for k, p in params.items():
+        if p.grad is None or k.endswith("k_linear.bias"):
+            continue
+        scale = max(float(p.grad.abs().max()), 1e-3 * gmax)
+        err = float((got[k].cpu() - p.grad).abs().max()) / scale
+        assert err < (5e-4 if dtype == "fp32" else 6e-2), (k, err)
+    assert float(got["prop_fc.weight"].abs().max()) > 0
