@@ -271,7 +271,7 @@ def run_sampling(args, rank, world, dev):
     h2d = int(np.mean([z.numel() * 4 + BATCH * z.size(1) + BATCH * 8 for _, z in inputs[W:]]))
     d2h = BATCH * MAX_STRLEN * 2          # int16 token ids
     cfg = sampler.model._cfg()
-    per_step = L.lib().gct_decode_launches_per_step(cfg)
+    per_step = L.lib().gct_decode_launches_per_step_at(cfg, BATCH)
     launches = K * (L.lib().gct_decode_begin_launches(cfg, int(inputs[W][1].size(1))) + (n_steps_run // max(K, 1)) * per_step)
     Sm_mean = float(np.mean([z.size(1) for _, z in inputs[W:]]))
     Sm_true = float(np.mean([np.mean(tl) for tl, _ in inputs[W:]]))       # keys actually attended (rows differ in length)

@@ -105,6 +105,9 @@ _PROTOS = {
     "gct_mt19937_fill": (C.c_int, [vp, vp, vp, vp, i64]),
     "gct_normal_from_mt": (C.c_int, [vp, vp, i64, vp]),
     "gct_decode_launches_per_step": (C.c_int, [C.POINTER(GctConfig)]),
+    "gct_decode_launches_per_step_at": (C.c_int, [C.POINTER(GctConfig), C.c_int]),
+    "gct_gemm_rownorm": (C.c_int, [vp, i64, vp, i64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, f32, vp]),
+    "gct_set_rownorm_fusion": (C.c_int, [C.c_int]),
     "gct_decode_begin_launches": (C.c_int, [C.POINTER(GctConfig), C.c_int]),
     "gct_decode_attention": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int,
                                        C.c_int, C.c_int, C.c_int, vp]),

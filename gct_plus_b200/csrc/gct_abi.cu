@@ -16,6 +16,7 @@ int g_gct_pair = 2;
 int g_gct_attn_bias_separate = 0;
 int g_za_cfg = 3;
 int g_gct_sm_budget = 0;
+int g_gct_rownorm = 1;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -41,6 +42,7 @@ int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_O
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
+int gct_set_rownorm_fusion(int mode) { g_gct_rownorm = mode; return GCT_OK; }
 int gct_set_sm_budget(int sms) { g_gct_sm_budget = sms; return GCT_OK; }
 int gct_set_zattn_config(int ctas_per_sm) { g_za_cfg = ctas_per_sm; return GCT_OK; }
 int gct_set_attention_bias_grad_fused(int enabled) { g_gct_attn_bias_separate = !enabled; return GCT_OK; }
@@ -93,6 +95,15 @@ int gct_gemm(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int6
                                                   b_mn ? ldb : 1, M, N, K, split_k, e, ST(stream));
     return tc::launch_gemm_tc((const bf16*)A, a_mn != 0, lda, (const bf16*)B, b_mn != 0, ldb, M, N, K, split_k, bn_hint, e,
                               ST(stream));
+}
+
+int gct_gemm_rownorm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const float* bias, const float* res32,
+                     float* out32, const float* alpha, const float* beta, void* normT, float* norm32, float eps, void* stream) {
+    GCT_REQUIRE(A && W && alpha && beta && normT, "gemm_rownorm: null argument");
+    tc::RowNormParams rp;
+    rp.bias = bias; rp.res32 = res32; rp.out32 = out32; rp.alpha = alpha; rp.beta = beta; rp.norm32 = norm32;
+    rp.drop.seed = 0; rp.drop.thresh = 0; rp.drop.scale = 1.f; rp.eps = eps; rp.M = M; rp.K = K;
+    return tc::launch_gemm_rownorm((const bf16*)A, lda, (const bf16*)W, ldw, (bf16*)normT, rp, ST(stream));
 }
 
 static AttnParams make_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
@@ -514,6 +525,12 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
                                        : decode_steps_impl<bf16>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream);
 }
 int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
+int gct_decode_launches_per_step_at(const gct_config_t* cfg, int B) {
+    // the two residual projections of a layer absorb the Norm that follows them (gemm_rownorm.cuh) at large batch
+    const bool fused = cfg->dtype != GCT_DTYPE_F32 && cfg->d_model == tc::RN_N && !g_gct_simt_only &&
+                       (g_gct_rownorm == 2 || (g_gct_rownorm == 1 && cdiv(B, 128) >= 96));
+    return 1 + cfg->n_layers * (fused ? 9 : 11) + 3;
+}
 int gct_decode_begin_launches(const gct_config_t* cfg, int Lz) {
     const int nck = (cfg->use_cond2lat && cfg->nconds > 0 && !cfg->use_cond2dec) ? 1 : 0;
     if (cfg->dtype != GCT_DTYPE_F32 && DecodeWs<bf16>::want_zmode(*cfg, Lz)) return 2 + nck + cfg->n_layers * (5 + 3 * cfg->heads + 4 * nck);

@@ -10,7 +10,9 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_rownorm.cuh"
 
+extern int g_gct_rownorm;
 extern int g_gct_simt_only;
 extern int g_gct_simt_attn;
 extern int g_gct_zattn;
@@ -148,6 +150,27 @@ struct Model {
 #undef GCT_NORM_CASE
         GCT_LAUNCH_CHECK();
         return GCT_OK;
+    }
+    // x_out = res + dropout(A W^T + bias) followed by (normT [, norm32]) = Norm(x_out): one kernel (gemm_rownorm.cuh) when the
+    // bf16 tier runs at d_model = 512 with enough row tiles to fill the machine, otherwise the residual GEMM + norm_fwd pair
+    bool rownorm_ok(int M) const {
+        if (sizeof(T) != 2 || d != tc::RN_N || g_gct_simt_only || g_gct_rownorm == 0) return false;
+        return g_gct_rownorm == 2 || cdiv(M, 128) >= 96;
+    }
+    int linear_res_norm(const T* A, int M, int K, const T* Wp, const float* bias, const float* res32, float* out32, DropCtx drop,
+                        int aslot, int bslot, T* normT, float* norm32) {
+        if constexpr (sizeof(T) == 2) {
+            if (rownorm_ok(M)) {
+                tc::RowNormParams rp;
+                rp.bias = bias; rp.res32 = res32; rp.out32 = out32; rp.alpha = P(aslot); rp.beta = P(bslot); rp.norm32 = norm32;
+                rp.drop = drop; rp.eps = 1e-6f; rp.M = M; rp.K = K;
+                return tc::launch_gemm_rownorm(A, K, Wp, K, normT, rp, st);
+            }
+        }
+        Epilogue e = epi(bias, d);
+        e.res32 = res32; e.out32 = out32; e.drop = drop;
+        GCT_TRY(gemm(A, false, K, Wp, false, K, M, d, K, e));
+        return norm_fwd(out32, aslot, bslot, normT, norm32, M);
     }
     // dropT / dc / dropsum: fused prologue of the consumer (see norm_bwd_kernel); null = plain Norm backward
     int norm_bwd(const float* x, int aslot, int bslot, const float* dy, const float* add, float* dx, int rows,
@@ -339,12 +362,9 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
             float* probs = io.enc_attn ? io.enc_attn + (size_t)l * B * m.H * Se * Se : nullptr;
             GCT_TRY(m.attention(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.src_mask, Se, 0, a.att, a.lse, probs, B, Se,
                                 Se, m.site(sb + ES_ATTN)));
-            {   // x1 = a1 + drop(att Wo^T + bo)     (residual on the normalised stream, layers.py:23-28)
-                Epilogue e = Model<T>::epi(m.P(m.enc_slot(l, E_O_B)), d);
-                e.res32 = a.a1_32; e.out32 = a.x1; e.drop = m.site(sb + ES_DROP1);
-                GCT_TRY(m.gemm(a.att, false, d, m.WT(m.enc_slot(l, E_O_W)), false, d, Me, d, d, e));
-            }
-            GCT_TRY(m.norm_fwd(a.x1, m.enc_slot(l, E_N2A), m.enc_slot(l, E_N2B), a.a2, a.a2_32, Me));
+            // x1 = a1 + drop(att Wo^T + bo) (residual on the normalised stream, layers.py:23-28) ; a2 = Norm2(x1)
+            GCT_TRY(m.linear_res_norm(a.att, Me, d, m.WT(m.enc_slot(l, E_O_W)), m.P(m.enc_slot(l, E_O_B)), a.a1_32, a.x1,
+                                      m.site(sb + ES_DROP1), m.enc_slot(l, E_N2A), m.enc_slot(l, E_N2B), a.a2, a.a2_32));
             {   // g = drop(gelu(a2 W1^T + b1))
                 Epilogue e = Model<T>::epi(m.P(m.enc_slot(l, E_F1_B)), dff);
                 e.flags = g_gct_ffn_classic ? EPI_GELU : (EPI_GELU | EPI_GELU_GRAD); e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + ES_FF);
@@ -408,23 +428,15 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
         float* pr1 = io.dec_attn1 ? io.dec_attn1 + (size_t)l * B * m.H * Ld * Ld : nullptr;
         GCT_TRY(m.attention(a.qkv, 3 * d, a.qkv + d, a.qkv + 2 * d, 3 * d, io.trg_mask, (long long)Ld * Ld, Ld, a.att1, a.lse1,
                             pr1, B, Ld, Ld, m.site(sb + DS_ATTN1)));
-        {
-            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O1_B)), d);
-            e.res32 = yin; e.out32 = a.y1; e.drop = m.site(sb + DS_DROP1);
-            GCT_TRY(m.gemm(a.att1, false, d, m.WT(m.dec_slot(l, D_O1_W)), false, d, Md, d, d, e));
-        }
-        GCT_TRY(m.norm_fwd(a.y1, m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), a.a2, nullptr, Md));
+        GCT_TRY(m.linear_res_norm(a.att1, Md, d, m.WT(m.dec_slot(l, D_O1_W)), m.P(m.dec_slot(l, D_O1_B)), yin, a.y1,
+                                  m.site(sb + DS_DROP1), m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), a.a2, nullptr));
         GCT_TRY(m.linear_T(a.a2, Md, d, m.dec_slot(l, D_Q2_W), m.dec_slot(l, D_Q2_B), d, a.q2));
         GCT_TRY(m.linear_T(A.mem, Mm, d, m.dec_slot(l, D_KV2_W), m.dec_slot(l, D_KV2_B), 2 * d, a.kv2));
         float* pr2 = io.dec_attn2 ? io.dec_attn2 + (size_t)l * B * m.H * Ld * Sm : nullptr;
         GCT_TRY(m.attention(a.q2, d, a.kv2, a.kv2 + d, 2 * d, A.cross_mask, Sm, 0, a.att2, a.lse2, pr2, B, Ld, Sm,
                             m.site(sb + DS_ATTN2)));
-        {
-            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O2_B)), d);
-            e.res32 = a.y1; e.out32 = a.y2; e.drop = m.site(sb + DS_DROP2);
-            GCT_TRY(m.gemm(a.att2, false, d, m.WT(m.dec_slot(l, D_O2_W)), false, d, Md, d, d, e));
-        }
-        GCT_TRY(m.norm_fwd(a.y2, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), a.a3, nullptr, Md));
+        GCT_TRY(m.linear_res_norm(a.att2, Md, d, m.WT(m.dec_slot(l, D_O2_W)), m.P(m.dec_slot(l, D_O2_B)), a.y1, a.y2,
+                                  m.site(sb + DS_DROP2), m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), a.a3, nullptr));
         {
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff);
             e.flags = g_gct_ffn_classic ? EPI_GELU : (EPI_GELU | EPI_GELU_GRAD); e.aux_out = a.hpre; e.outT = a.g; e.drop = m.site(sb + DS_FF);
@@ -903,11 +915,8 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
             GCT_TRY(launch_decode_attn<T>(p, B, st));
         }
-        {
-            Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O1_B)), d); e.res32 = W.x; e.out32 = W.x;
-            GCT_TRY(m.gemm(W.att, false, d, m.WT(m.dec_slot(l, D_O1_W)), false, d, B, d, d, e));
-        }
-        GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), W.xn, nullptr, B));
+        GCT_TRY(m.linear_res_norm(W.att, B, d, m.WT(m.dec_slot(l, D_O1_W)), m.P(m.dec_slot(l, D_O1_B)), W.x, W.x, m.site(0),
+                                  m.dec_slot(l, D_N2A), m.dec_slot(l, D_N2B), W.xn, nullptr));
         if constexpr (sizeof(T) == 2) {
             if (W.zmode) {
                 // cross-attention in latent space (decode_zattn.cuh): q and out projections carry the folded k / v / fc_z
@@ -921,10 +930,8 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
                 zp.kv_stride = Sm; zp.n_keys = W.Lz; zp.kvc = W.nck ? W.kvc + (size_t)l * B * W.nck * 2 * d : nullptr; zp.nc = W.nck;
                 zp.out = W.zbar; zp.ldo = KZ; zp.H = m.H; zp.B = B;
                 GCT_TRY(launch_decode_zattn(zp, m.lat, st));
-                {
-                    Epilogue e = Model<T>::epi(W.boz + (size_t)l * d, d); e.res32 = W.x; e.out32 = W.x;
-                    GCT_TRY(m.gemm(W.zbar, false, KZ, W.woz + (size_t)l * d * KZ, false, KZ, B, d, KZ, e));
-                }
+                GCT_TRY(m.linear_res_norm(W.zbar, B, KZ, W.woz + (size_t)l * d * KZ, W.boz + (size_t)l * d, W.x, W.x, m.site(0),
+                                          m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), W.xn, nullptr));
             }
         }
         if (!W.zmode) {
@@ -937,12 +944,9 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
                 p.key_valid = W.cross_mask; p.kv_stride = Sm; p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
                 GCT_TRY(launch_decode_attn<T>(p, B, st));
             }
-            {
-                Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_O2_B)), d); e.res32 = W.x; e.out32 = W.x;
-                GCT_TRY(m.gemm(W.att, false, d, m.WT(m.dec_slot(l, D_O2_W)), false, d, B, d, d, e));
-            }
+            GCT_TRY(m.linear_res_norm(W.att, B, d, m.WT(m.dec_slot(l, D_O2_W)), m.P(m.dec_slot(l, D_O2_B)), W.x, W.x, m.site(0),
+                                      m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), W.xn, nullptr));
         }
-        GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), W.xn, nullptr, B));
         {
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff); e.flags = EPI_GELU; e.outT = W.hbuf;
             GCT_TRY(m.gemm(W.xn, false, d, m.WT(m.dec_slot(l, D_F1_W)), false, d, B, dff, d, e));

@@ -112,6 +112,12 @@ int gct_norm_bwd(const float* x, const float* alpha, const float* dy, const floa
 int gct_gemm(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int64_t ldb, int M, int N, int K,
              const float* bias, const float* res32, const void* aux_in, void* aux_out, float* out32, void* outT,
              int ldc, int flags, int split_k, int bn_hint, int dtype, void* stream);
+/* Residual projection + the Norm after it in one kernel (Model/layers.py:26-29,62-72 + Model/modules.py:80-95), d_model = 512, bf16:
+ * out32 [M,512] = A[M,K] W[512,K]^T + bias + res32 ; normT (bf16) [, norm32] = alpha (out32 - mean) / (std_unbiased + eps) + beta.
+ * out32 may alias res32.  gct_set_rownorm_fusion: 0 = never use it inside the model, 1 (default) = when >= 96 row tiles, 2 = always. */
+int gct_gemm_rownorm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const float* bias, const float* res32,
+                     float* out32, const float* alpha, const float* beta, void* normT, float* norm32, float eps, void* stream);
+int gct_set_rownorm_fusion(int mode);
 /* attention: Model/sublayers.py:29-41.  q/k/v [B,L,ld] with head h at column 64*h; mask bytes. */
 int gct_attention_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const uint8_t* mask,
                       int64_t mask_bstride, int mask_rstride, void* out, int ldo, float* lse, float* probs, int B,
@@ -205,6 +211,7 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
                      int step_end, void* workspace, size_t workspace_bytes, void* stream);
 /* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
 int gct_decode_launches_per_step(const gct_config_t* cfg);
+int gct_decode_launches_per_step_at(const gct_config_t* cfg, int B);   /* at batch B (large batches fuse two Norms per layer away) */
 int gct_decode_begin_launches(const gct_config_t* cfg, int Lz);
 /* Host-side batch detokeniser (replaces the per-row Python loop of Inference/sampling_tool.py:54-61 `id_to_smi`): rows of
  * int16 ids [n, width] are cut at the first eos_id, sos_id is dropped, token strings (UTF-8 blob `vocab`, offsets

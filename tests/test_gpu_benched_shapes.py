@@ -196,7 +196,9 @@ DECODE_CASES = [("vaetf", 0, 1, 55, True, ARCH), ("vaetf", 0, 1, 55, False, ARCH
                 ("pvaetf", 3, 1, 55, False, ARCH), ("scavaetf", 0, 22, 76, True, ARCH), ("pscavaetf", 3, 22, 76, True, ARCH),
                 ("pscavaetf", 3, 22, 76, False, ARCH),
                 # the other instantiations of the latent-space kernel: latent 64 / 4 heads, latent 32 / 2 heads (+ condition rows)
-                ("pvaetf", 3, 1, 40, True, ARCH_MID), ("pscavaetf", 2, 9, 37, True, ARCH_SMALL), ("vaetf", 0, 1, 19, True, ARCH_SMALL)]
+                ("pvaetf", 3, 1, 40, True, ARCH_MID), ("pscavaetf", 2, 9, 37, True, ARCH_SMALL), ("vaetf", 0, 1, 19, True, ARCH_SMALL),
+                # residual projections fused with the following Norm (gemm_rownorm.cuh), forced on at this 16-row-tile batch
+                ("vaetf", 0, 1, 55, True, "rownorm"), ("pvaetf", 3, 1, 55, True, "rownorm"), ("pscavaetf", 3, 22, 76, False, "rownorm")]
 
 
 @pytest.mark.parametrize("mt,nc,t0,Lz,latent_form,arch", DECODE_CASES)
@@ -206,6 +208,9 @@ def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form, a
     cross-attention in latent space or in K/V form, ragged latent lengths, cond2lat memory rows -- against the oracle's
     un-cached decoder (Inference/sampling_tool.py:150-160: model.decode on the growing prefix, last position)."""
     lib = L.lib()
+    force_rownorm = arch == "rownorm"
+    if force_rownorm:
+        arch = ARCH
     B, max_strlen = 2048, 100
     steps = max_strlen - 1
     torch.manual_seed(0)
@@ -226,10 +231,12 @@ def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form, a
     ys[7, 40:] = 1                                 # a row that runs into <pad> tokens: key_valid masks them like trg_mask does
     dconds = torch.randn(B, nc, generator=g).to(DEV) if nc else None
     lib.gct_set_latent_cross_attention(int(latent_form))
+    lib.gct_set_rownorm_fusion(2 if force_rownorm else 1)
     try:
         got = s.teacher_forced_logits(zs, ys, mask, dconds=dconds, t0=t0)        # (steps, B, V)
     finally:
         lib.gct_set_latent_cross_attention(1)
+        lib.gct_set_rownorm_fusion(1)
     cfg = O.ModelCfg(model_type=mt, src_vocab=V, trg_vocab=V, nconds=nc, use_cond2lat=nc > 0, N=arch["N"], d_model=arch["d_model"],
                      dff=arch["dff"], h=arch["h"], latent_dim=arch["latent_dim"])
     trg = ys[:, :-1].to(DEV)

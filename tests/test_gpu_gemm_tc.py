@@ -184,3 +184,34 @@ def test_cta_pair_dgrad_and_split_k_wgrad(_pair_switch, pair, M, N, K, a_mn, b_m
         out = torch.ones(M, N, device=DEV)
         gemm(As, Bs, M, N, K, a_mn=a_mn, b_mn=b_mn, flags=4, split_k=split, out32=out)
         _close(out, ref + 1.0)
+
+
+@pytest.mark.parametrize("M,K", [(300, 512), (128 * 150 + 17, 512), (4096, 1024), (1000, 1536), (2500, 2048)])
+@pytest.mark.parametrize("variant", ["full", "inplace", "no_bias_res", "norm32"])
+def test_residual_projection_fused_with_norm(M, K, variant):
+    """gct_gemm_rownorm (128 x 512 tiles, whole rows per CTA, Norm in the epilogue) against torch: x = A W^T + b + res and
+    y = alpha (x - mean) / (std_unbiased + eps) + beta (Model/modules.py:80-95), ragged last tile, in-place residual stream."""
+    import gct_plus_b200._lib as L
+    lib = L.lib()
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    W = (torch.randn(512, K, generator=g) / K ** 0.5).to(DEV).bfloat16()
+    bias = torch.randn(512, generator=g).to(DEV) if variant != "no_bias_res" else None
+    res = (2 * torch.randn(M, 512, generator=g) + 0.5).to(DEV) if variant != "no_bias_res" else None
+    alpha = (1 + 0.1 * torch.randn(512, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(512, generator=g)).to(DEV)
+    x_ref = A.float() @ W.float().t()
+    if bias is not None:
+        x_ref = x_ref + bias + res
+    y_ref = alpha * (x_ref - x_ref.mean(-1, keepdim=True)) / (x_ref.std(-1, keepdim=True) + 1e-6) + beta
+    out32 = res.clone() if variant == "inplace" else torch.full((M, 512), 7.0, device=DEV)
+    res_in = out32 if variant == "inplace" else res
+    normT = torch.zeros(M, 512, device=DEV, dtype=torch.bfloat16)
+    norm32 = torch.zeros(M, 512, device=DEV) if variant == "norm32" else None
+    L.check(lib.gct_gemm_rownorm(L.ptr(A), K, L.ptr(W), K, M, K, L.ptr(bias), L.ptr(res_in), L.ptr(out32), L.ptr(alpha), L.ptr(beta),
+                                 L.ptr(normT), L.ptr(norm32), 1e-6, L.stream_ptr()), "gct_gemm_rownorm")
+    torch.cuda.synchronize()
+    _close(out32, x_ref, 2e-3)
+    _close(normT, y_ref, 1e-2)
+    if norm32 is not None:
+        _close(norm32, y_ref, 2e-3)

@@ -292,3 +292,31 @@ def test_fused_trainer_property_head_matches_reference(dtype):
         err = float((got[k].cpu() - p.grad).abs().max()) / scale
         assert err < (5e-4 if dtype == "fp32" else 6e-2), (k, err)
     assert float(got["prop_fc.weight"].abs().max()) > 0
+
+
+@pytest.mark.parametrize("fusion", [0, 2])
+@pytest.mark.parametrize("name", ["vaetf_full", "pvaetf_full"])
+def test_forward_backward_with_and_without_the_fused_residual_norm(name, fusion):
+    """The bf16 forward at d_model = 512 with the residual projections fused with their Norm forced on (2) and off (0): both
+    against the reference's recorded outputs; gradients of the two settings against each other (the backward reads the saved
+    x / normalised activations whichever kernel wrote them)."""
+    import gct_plus_b200._lib as L
+    fx = load_golden(name)
+    lib = L.lib()
+    lib.gct_set_rownorm_fusion(fusion)
+    try:
+        m, _ = build_model(fx, "bf16", dropout=0.0)
+        m.train()
+        batch = _to_dev(fx["batch"])
+        logits, mu, lv, z, _ = _run_with_eps(m, fx, batch, eps_for(fx))
+        assert rel_err(logits, fx["output_mol"]) < 1e-2 and rel_err(mu, fx["mu"]) < 1e-2 and rel_err(z, fx["z"]) < 1e-2
+        loss = loss_function(fx["beta"], None, logits, None, batch["trg"][:, 1:].reshape(-1), mu, lv, False, 1)[0]
+        assert abs(float(loss) - fx["loss"]) < 1e-2 * abs(fx["loss"])
+        loss.backward()
+        for k, sg in fx["grads"].items():
+            if k.endswith("k_linear.bias"):
+                continue
+            got = float(dict(m.named_parameters())[k].grad.double().abs().sum())
+            assert abs(got - sg["abssum"]) <= 5e-2 * sg["abssum"] + 1e-5 * sg["numel"] + 1e-3, (k, fusion)
+    finally:
+        lib.gct_set_rownorm_fusion(1)
