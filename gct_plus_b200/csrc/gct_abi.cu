@@ -16,8 +16,7 @@ int g_gct_pair = 2;
 int g_gct_attn_bias_separate = 0;
 int g_za_cfg = 3;
 int g_gct_sm_budget = 0;
-int g_gct_rownorm = 1;
-int g_gct_rownorm_staged = 0;
+int g_gct_rownorm = 0;
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -43,7 +42,7 @@ int gct_set_persistent_gemm(int enabled) { g_gct_persist = enabled; return GCT_O
 int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
-int gct_set_rownorm_fusion(int mode) { g_gct_rownorm = mode & 3; g_gct_rownorm_staged = (mode >> 2) & 1; return GCT_OK; }
+int gct_set_rownorm_fusion(int mode) { g_gct_rownorm = mode; return GCT_OK; }
 int gct_set_sm_budget(int sms) { g_gct_sm_budget = sms; return GCT_OK; }
 int gct_set_zattn_config(int ctas_per_sm) { g_za_cfg = ctas_per_sm; return GCT_OK; }
 int gct_set_attention_bias_grad_fused(int enabled) { g_gct_attn_bias_separate = !enabled; return GCT_OK; }
@@ -103,7 +102,7 @@ int gct_gemm_rownorm(const void* A, int64_t lda, const void* W, int64_t ldw, int
     GCT_REQUIRE(A && W && alpha && beta && normT, "gemm_rownorm: null argument");
     tc::RowNormParams rp;
     rp.bias = bias; rp.res32 = res32; rp.out32 = out32; rp.alpha = alpha; rp.beta = beta; rp.norm32 = norm32;
-    rp.drop.seed = 0; rp.drop.thresh = 0; rp.drop.scale = 1.f; rp.eps = eps; rp.M = M; rp.K = K; rp.normT = nullptr;
+    rp.drop.seed = 0; rp.drop.thresh = 0; rp.drop.scale = 1.f; rp.eps = eps; rp.M = M; rp.K = K;
     return tc::launch_gemm_rownorm((const bf16*)A, lda, (const bf16*)W, ldw, (bf16*)normT, rp, ST(stream));
 }
 

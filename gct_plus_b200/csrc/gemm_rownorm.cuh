@@ -7,12 +7,16 @@
 // centred sum of squares; normalise), exactly the two-pass mean / unbiased-std arithmetic of norm_fwd_kernel.  This removes the
 // separate norm_fwd launch and its fp32 re-read of x, and a 128 x 512 tile has 1.6x the arithmetic intensity per operand byte
 // of the 128 x 128 tiles these short-K projections otherwise use.
+// [B200] measured (scripts/one_rownorm.py, profiles/r02_rownorm_fusion_ab.txt): correct, but NOT faster than the residual GEMM +
+// norm_fwd pair -- M = 41472, K = 512: 96.8 vs 84.6 us; M = 30000: 67.1 vs 64.9 us (K = 512), 82.5 vs 72.4 us (K = 1024).  With
+// all 512 TMEM columns holding one accumulator the epilogue (~27 us per tile: per-row residual loads, 96 staged TMA stores, three
+// TMEM passes) cannot overlap the next tile's main loop, while the unfused kernel double-buffers 128-column accumulators; writing
+// x / y straight from registers instead of through the staging tiles was slower still (134 us).  Kept as a tested option
+// (gct_set_rownorm_fusion), off by default.
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..17 epilogue (TMEM lane quarter = warp % 4,
 // column slice = (warp - 2) / 4 of 128 columns).  2-stage ring of (A 128 x 64, B 512 x 64) bf16 tiles, SWIZZLE_128B.
 #pragma once
 #include "gemm_tc.cuh"
-
-extern int g_gct_rownorm_staged;
 
 namespace tc {
 
@@ -23,7 +27,6 @@ struct RowNormParams {
     const float* alpha;       // Norm parameters [512]
     const float* beta;
     float* norm32;            // optional [M, 512] fp32 Norm(x)
-    bf16* normT;              // [M, 512] bf16 Norm(x)
     DropCtx drop;
     float eps;
     int M, K;
@@ -53,7 +56,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // named barrier over the 16 epilogue warps
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(4 * RN_EW * 32) : "memory"); }
 
-template <bool STAGED>
 __global__ void __launch_bounds__(RN_THREADS, 1)
 gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, RowNormParams p) {
@@ -192,16 +194,10 @@ gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 tmem_st16(trow + ch * 16, v);
                 if (p.out32) {
-                    if constexpr (STAGED) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            *reinterpret_cast<float4*>(stg + stage_off(lane, (ch & 1) * 4 + i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        if (ch & 1) stage_tma_store(&tmX, stg_s, c0 + (ch - 1) * 16, m0 + q * 32, lane);      // 32 fp32 columns x 32 rows
-                    } else if (rok) {           // fire-and-forget: 64 contiguous bytes of the lane's own row
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            *(reinterpret_cast<float4*>(p.out32 + roff + ch * 16) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(stg + stage_off(lane, (ch & 1) * 4 + i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    if (ch & 1) stage_tma_store(&tmX, stg_s, c0 + (ch - 1) * 16, m0 + q * 32, lane);      // 32 fp32 columns x 32 rows
                 }
             }
             tmem_st_wait();
@@ -245,15 +241,9 @@ gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int i = 0; i < 4; ++i)
                         *(reinterpret_cast<float4*>(p.norm32 + roff + ch * 16) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
-                if constexpr (STAGED) {
-                    *reinterpret_cast<uint4*>(stg + stage_off(lane, (ch & 3) * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4*>(stg + stage_off(lane, (ch & 3) * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    if ((ch & 3) == 3) stage_tma_store(&tmY, stg_s, c0 + (ch - 3) * 16, m0 + q * 32, lane);   // 64 bf16 columns x 32 rows
-                } else if (rok) {
-                    uint4* yo = reinterpret_cast<uint4*>(p.normT + roff + ch * 16);
-                    yo[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    yo[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                }
+                *reinterpret_cast<uint4*>(stg + stage_off(lane, (ch & 3) * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(stg + stage_off(lane, (ch & 3) * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if ((ch & 3) == 3) stage_tma_store(&tmY, stg_s, c0 + (ch - 3) * 16, m0 + q * 32, lane);   // 64 bf16 columns x 32 rows
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -276,17 +266,10 @@ static int launch_gemm_rownorm(const bf16* A, long long lda, const bf16* W, long
     tx = ta;
     if (p.out32) GCT_TRY(get_tensor_map(p.out32, (uint64_t)RN_N, (uint64_t)p.M, (uint64_t)RN_N * 4, 32, 32, &tx, 4));
     GCT_TRY(get_tensor_map(normT, (uint64_t)RN_N, (uint64_t)p.M, (uint64_t)RN_N * 2, 64, 32, &ty, 2));
+    GCT_SMEM_LIMIT(gemm_rownorm_kernel, RnSmem::REQUEST);
     const int m_tiles = (p.M + BM - 1) / BM;
     const int grid = m_tiles < sm_count() ? m_tiles : sm_count();
-    RowNormParams q = p;
-    q.normT = normT;
-    if (g_gct_rownorm_staged) {
-        GCT_SMEM_LIMIT(gemm_rownorm_kernel<true>, RnSmem::REQUEST);
-        GCT_CUDA(launch_k(gemm_rownorm_kernel<true>, dim3(grid), dim3(RN_THREADS), (size_t)RnSmem::REQUEST, st, true, ta, tb, tx, ty, q));
-    } else {
-        GCT_SMEM_LIMIT(gemm_rownorm_kernel<false>, RnSmem::REQUEST);
-        GCT_CUDA(launch_k(gemm_rownorm_kernel<false>, dim3(grid), dim3(RN_THREADS), (size_t)RnSmem::REQUEST, st, true, ta, tb, tx, ty, q));
-    }
+    GCT_CUDA(launch_k(gemm_rownorm_kernel, dim3(grid), dim3(RN_THREADS), (size_t)RnSmem::REQUEST, st, true, ta, tb, tx, ty, p));
     return GCT_OK;
 }
 

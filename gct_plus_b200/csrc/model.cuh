@@ -163,7 +163,7 @@ struct Model {
             if (rownorm_ok(M)) {
                 tc::RowNormParams rp;
                 rp.bias = bias; rp.res32 = res32; rp.out32 = out32; rp.alpha = P(aslot); rp.beta = P(bslot); rp.norm32 = norm32;
-                rp.drop = drop; rp.eps = 1e-6f; rp.M = M; rp.K = K; rp.normT = nullptr;
+                rp.drop = drop; rp.eps = 1e-6f; rp.M = M; rp.K = K;
                 return tc::launch_gemm_rownorm(A, K, Wp, K, normT, rp, st);
             }
         }

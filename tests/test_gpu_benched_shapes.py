@@ -63,12 +63,22 @@ def _oracle_step(sd, cfg, batch, eps, beta):
                 kld=float(kld)), grads
 
 
-@pytest.mark.parametrize("mt,S,sca,dtype", [("pvaetf", 78, 0, "bf16"), ("pscavaetf", 98, 19, "bf16"), ("pvaetf", 78, 0, "fp32")])
-def test_training_step_at_cfg3_cfg4_shape_matches_oracle(mt, S, sca, dtype):
+@pytest.fixture
+def _rownorm_switch():
+    yield L.lib().gct_set_rownorm_fusion
+    L.lib().gct_set_rownorm_fusion(0)
+
+
+@pytest.mark.parametrize("mt,S,sca,dtype", [("pvaetf", 78, 0, "bf16"), ("pscavaetf", 98, 19, "bf16"), ("pvaetf", 78, 0, "fp32"),
+                                            ("pvaetf", 78, 0, "bf16+rownorm")])
+def test_training_step_at_cfg3_cfg4_shape_matches_oracle(mt, S, sca, dtype, _rownorm_switch):
     """cfg 3 (pvaetf B=512 S=78 T=79 -> 41 472 encoder rows) and cfg 4's per-GPU shape (pscavaetf B=512 S=98 T=99 ->
     51 712 rows) through FusedTrainer.step -- the call bench.py times -- with dropout off and a supplied eps, against the
     oracle's logits, mu / log_var / z, loss terms and the gradient of every parameter."""
     B, nc, beta = 512, 3, 0.5
+    if dtype.endswith("+rownorm"):          # the optional fused residual-projection + Norm kernel (gemm_rownorm.cuh) at 324 row tiles
+        dtype = "bf16"
+        _rownorm_switch(1)
     torch.manual_seed(0)
     m = Cvaetf(V, V, dropout=0.0, nconds=nc, use_cond2lat=True, compute_dtype=dtype, **ARCH)
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
@@ -231,12 +241,12 @@ def test_bf16_kv_decode_every_step_matches_oracle(mt, nc, t0, Lz, latent_form, a
     ys[7, 40:] = 1                                 # a row that runs into <pad> tokens: key_valid masks them like trg_mask does
     dconds = torch.randn(B, nc, generator=g).to(DEV) if nc else None
     lib.gct_set_latent_cross_attention(int(latent_form))
-    lib.gct_set_rownorm_fusion(2 if force_rownorm else 1)
+    lib.gct_set_rownorm_fusion(2 if force_rownorm else 0)
     try:
         got = s.teacher_forced_logits(zs, ys, mask, dconds=dconds, t0=t0)        # (steps, B, V)
     finally:
         lib.gct_set_latent_cross_attention(1)
-        lib.gct_set_rownorm_fusion(1)
+        lib.gct_set_rownorm_fusion(0)
     cfg = O.ModelCfg(model_type=mt, src_vocab=V, trg_vocab=V, nconds=nc, use_cond2lat=nc > 0, N=arch["N"], d_model=arch["d_model"],
                      dff=arch["dff"], h=arch["h"], latent_dim=arch["latent_dim"])
     trg = ys[:, :-1].to(DEV)

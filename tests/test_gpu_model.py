@@ -319,4 +319,4 @@ def test_forward_backward_with_and_without_the_fused_residual_norm(name, fusion)
             got = float(dict(m.named_parameters())[k].grad.double().abs().sum())
             assert abs(got - sg["abssum"]) <= 5e-2 * sg["abssum"] + 1e-5 * sg["numel"] + 1e-3, (k, fusion)
     finally:
-        lib.gct_set_rownorm_fusion(1)
+        lib.gct_set_rownorm_fusion(0)
