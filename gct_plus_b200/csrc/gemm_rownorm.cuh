@@ -18,6 +18,8 @@
 #pragma once
 #include "gemm_tc.cuh"
 
+extern int g_gct_rownorm_res_tma;
+
 namespace tc {
 
 struct RowNormParams {
@@ -38,7 +40,7 @@ struct RnSmem {
     static constexpr int STAGING_OFF = RN_STAGES * STAGE_BYTES;              // 16 epilogue warps x 4 KB
     static constexpr int RED_OFF = STAGING_OFF + 4 * RN_EW * 4096;           // [4 slices][128 rows] floats
     static constexpr int BAR_OFF = RED_OFF + RN_EW * 128 * 4;
-    static constexpr int TOTAL = BAR_OFF + 64;
+    static constexpr int TOTAL = BAR_OFF + 64 + 16 * 8;                      // pipeline barriers + one residual barrier per epilogue warp
     static constexpr int REQUEST = 232448;                                   // the whole 227 KB: up to 960 B of alignment slack
 };
 static_assert(RnSmem::TOTAL <= RnSmem::REQUEST, "row-norm GEMM does not fit in shared memory");
@@ -56,9 +58,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // named barrier over the 16 epilogue warps
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(4 * RN_EW * 32) : "memory"); }
 
+// RES_TMA: the residual arrives as 32-row x 32-column boxes in the warp's staging tile (coalesced, no per-row loads) instead of
+// through per-lane loads of the lane's own row.
+template <bool RES_TMA>
 __global__ void __launch_bounds__(RN_THREADS, 1)
 gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, RowNormParams p) {
+                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                    const __grid_constant__ CUtensorMap tmR, RowNormParams p) {
     using L = RnSmem;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -82,6 +88,7 @@ gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < RN_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int w = 0; w < 4 * RN_EW; ++w) mbar_init(bars + 64u + 8u * w, 1);
         mbar_init(tfull_bar, 1);
         mbar_init(tempty_bar, 4 * RN_EW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -145,13 +152,67 @@ gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* stg = sm + L::STAGING_OFF + (warp - 2) * 4096;
         const uint32_t stg_s = smem_u32(stg);
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, res_phase = 0;
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
             const int m0 = tile * BM;
             const int row = m0 + q * 32 + lane;
             const bool rok = row < p.M;
             const size_t roff = (size_t)row * RN_N + c0;
             // ---- pass 1: x = dropout(acc + bias) + res, written back to TMEM in place and out through the staging tile
+            float sum = 0.f;
+            if constexpr (RES_TMA) {
+                const uint32_t rbar = bars + 64u + 8u * (uint32_t)(warp - 2);
+                const bool has_res = p.res32 != nullptr;
+                if (has_res && lane == 0) {                 // first residual box: in flight before the accumulator is ready
+                    mbar_expect_tx(rbar, 4096);
+                    tma_load_2d(stg_s, &tmR, c0, m0 + q * 32, rbar);
+                }
+                mbar_wait(tfull_bar, acc_phase);
+                tcgen05_fence_after();
+                epi_bar_sync();                    // every warp is past the previous tile's reads of `red`
+#pragma unroll 1
+                for (int sg = 0; sg < 4; ++sg) {
+                    float v[2][16];
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int ch = sg * 2 + c2;
+                        tmem_ld16(trow + ch * 16, v[c2]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + ch * 16) + i);
+                                v[c2][4 * i] += b.x; v[c2][4 * i + 1] += b.y; v[c2][4 * i + 2] += b.z; v[c2][4 * i + 3] += b.w;
+                            }
+                        }
+                        if (p.drop.thresh) {
+                            const uint32_t pair0 = (uint32_t)((roff + ch * 16) >> 1);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) drop_pair(p.drop, pair0 + i, v[c2][2 * i], v[c2][2 * i + 1]);
+                        }
+                    }
+                    if (has_res) mbar_wait(rbar, res_phase);           // the segment's residual box has landed
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4* slot = reinterpret_cast<float4*>(stg + stage_off(lane, c2 * 4 + i));
+                            float4 x4 = make_float4(v[c2][4 * i], v[c2][4 * i + 1], v[c2][4 * i + 2], v[c2][4 * i + 3]);
+                            if (has_res) { const float4 r4 = *slot; x4.x += r4.x; x4.y += r4.y; x4.z += r4.z; x4.w += r4.w; }
+                            *slot = x4;
+                            v[c2][4 * i] = x4.x; v[c2][4 * i + 1] = x4.y; v[c2][4 * i + 2] = x4.z; v[c2][4 * i + 3] = x4.w;
+                            sum += (x4.x + x4.y) + (x4.z + x4.w);
+                        }
+                        tmem_st16(trow + (sg * 2 + c2) * 16, v[c2]);
+                    }
+                    if (has_res) res_phase ^= 1u;
+                    if (p.out32) stage_tma_store(&tmX, stg_s, c0 + sg * 32, m0 + q * 32, lane);      // also frees the tile for the next box
+                    else __syncwarp();
+                    if (has_res && sg + 1 < 4 && lane == 0) {
+                        mbar_expect_tx(rbar, 4096);
+                        tma_load_2d(stg_s, &tmR, c0 + (sg + 1) * 32, m0 + q * 32, rbar);
+                    }
+                }
+            } else {
             float4 rnext[4];
             if (p.res32 && rok) {
 #pragma unroll
@@ -163,7 +224,6 @@ gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(tfull_bar, acc_phase);
             tcgen05_fence_after();
             epi_bar_sync();                    // every warp is past the previous tile's reads of `red`
-            float sum = 0.f;
 #pragma unroll 1
             for (int ch = 0; ch < 8; ++ch) {
                 float4 rc[4];
@@ -199,6 +259,7 @@ gemm_rownorm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         *reinterpret_cast<float4*>(stg + stage_off(lane, (ch & 1) * 4 + i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     if (ch & 1) stage_tma_store(&tmX, stg_s, c0 + (ch - 1) * 16, m0 + q * 32, lane);      // 32 fp32 columns x 32 rows
                 }
+            }
             }
             tmem_st_wait();
             red[cs * 128 + q * 32 + lane] = sum;
@@ -266,10 +327,18 @@ static int launch_gemm_rownorm(const bf16* A, long long lda, const bf16* W, long
     tx = ta;
     if (p.out32) GCT_TRY(get_tensor_map(p.out32, (uint64_t)RN_N, (uint64_t)p.M, (uint64_t)RN_N * 4, 32, 32, &tx, 4));
     GCT_TRY(get_tensor_map(normT, (uint64_t)RN_N, (uint64_t)p.M, (uint64_t)RN_N * 2, 64, 32, &ty, 2));
-    GCT_SMEM_LIMIT(gemm_rownorm_kernel, RnSmem::REQUEST);
+    CUtensorMap tr = tx;
+    if (p.res32 && p.res32 != p.out32) GCT_TRY(get_tensor_map(p.res32, (uint64_t)RN_N, (uint64_t)p.M, (uint64_t)RN_N * 4, 32, 32, &tr, 4));
     const int m_tiles = (p.M + BM - 1) / BM;
     const int grid = m_tiles < sm_count() ? m_tiles : sm_count();
-    GCT_CUDA(launch_k(gemm_rownorm_kernel, dim3(grid), dim3(RN_THREADS), (size_t)RnSmem::REQUEST, st, true, ta, tb, tx, ty, p));
+    // the boxed residual needs the fp32 output's staging geometry (always present in the model's uses)
+    if (g_gct_rownorm_res_tma && p.out32) {
+        GCT_SMEM_LIMIT(gemm_rownorm_kernel<true>, RnSmem::REQUEST);
+        GCT_CUDA(launch_k(gemm_rownorm_kernel<true>, dim3(grid), dim3(RN_THREADS), (size_t)RnSmem::REQUEST, st, true, ta, tb, tx, ty, tr, p));
+    } else {
+        GCT_SMEM_LIMIT(gemm_rownorm_kernel<false>, RnSmem::REQUEST);
+        GCT_CUDA(launch_k(gemm_rownorm_kernel<false>, dim3(grid), dim3(RN_THREADS), (size_t)RnSmem::REQUEST, st, true, ta, tb, tx, ty, tr, p));
+    }
     return GCT_OK;
 }
 

@@ -29,7 +29,8 @@ def pair():
     L.check(lib.gct_norm_fwd(L.ptr(x), L.ptr(alpha), L.ptr(beta), L.ptr(xn), None, M, 512, 1, st))
 
 
-for name, fn in (("fused", fused), ("gemm + norm_fwd", pair), ("fused", fused), ("gemm + norm_fwd", pair)):
+for name, fn in (("fused, boxed residual", fused), ("gemm + norm_fwd", pair), ("fused, per-row residual", fused), ("fused, boxed residual", fused), ("gemm + norm_fwd", pair)):
+    lib.gct_set_rownorm_fusion(1 | (4 if "per-row" in name else 0))
     for _ in range(3):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,4 +40,4 @@ for name, fn in (("fused", fused), ("gemm + norm_fwd", pair), ("fused", fused), 
         fn()
     e1.record()
     torch.cuda.synchronize()
-    print(f"M={M} K={K} {name:16s}: {e0.elapsed_time(e1) * 100:.1f} us", flush=True)
+    print(f"M={M} K={K} {name:24s}: {e0.elapsed_time(e1) * 100:.1f} us", flush=True)
