@@ -18,6 +18,8 @@ dev = torch.device("cuda:0")
 lib = L.lib()
 if os.environ.get("GCT_PAIR") is not None:
     lib.gct_set_cta_pair_gemm(int(os.environ["GCT_PAIR"]))
+if os.environ.get("GCT_RES_BOX") is not None:
+    lib.gct_set_residual_box(int(os.environ["GCT_RES_BOX"]))
 if os.environ.get("GCT_EW4") is not None:
     lib.gct_set_epilogue_warps16(int(os.environ["GCT_EW4"]))
 A = torch.randn(M, K, device=dev).bfloat16()
