@@ -825,7 +825,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const bool res_box = (use_tma_store & 2) && (mode == 2 || mode == 8) && !(e.flags & (32 | 64)) && (SLICE % 32) == 0;
                 const uint32_t rbar = base + L::RBAR_OFF + 8u * (uint32_t)(warp - 2);
                 uint8_t* stg_r = smem_raw + (base - smem_u32(smem_raw)) + L::STAGING_OFF + (warp - 2) * 4096;
-                if (res_box && lane == 0) {                     // first box: in flight before the accumulator is ready
+                const bool aux_box = (use_tma_store & 4) && mode == 10 && !(e.flags & (32 | 64)) && (SLICE % 64) == 0;
+                if ((res_box || aux_box) && lane == 0) {        // first box: in flight before the accumulator is ready
                     mbar_expect_tx(rbar, 4096);
                     tma_load_2d(smem_u32(stg_r), &tmR, n0 + cs * SLICE, m0 + q * 32, rbar);
                 }
@@ -873,6 +874,47 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         if (sg + 1 < NSEG && lane == 0) {
                             mbar_expect_tx(rbar, 4096);
                             tma_load_2d(stg_s, &tmR, colb + (sg + 1) * 32, m0 + q * 32, rbar);
+                        }
+                    }
+                } else if (aux_box) {
+                    // multiply-by-aux (backward of the FFN's first projection): the saved keep * gelu'(pre) factor arrives as 32-row x
+                    // 64-column bf16 boxes in the staging tile, the product leaves from the same tile
+                    const int colb = n0 + cs * SLICE;
+                    const size_t off0 = (size_t)row * e.ldc + colb;
+                    const uint32_t stg_s = smem_u32(stg_r);
+                    constexpr int NSEG = SLICE / 64;
+#pragma unroll 1
+                    for (int sg = 0; sg < NSEG; ++sg) {
+                        mbar_wait(rbar, res_phase);
+                        res_phase ^= 1u;
+#pragma unroll 1
+                        for (int ci = 0; ci < 4; ++ci) {
+                            float v[16];
+                            tmem_ld16(tslice + sg * 64 + ci * 16, v);
+                            if (e.drop.thresh) {
+                                const uint32_t pair0 = (uint32_t)((off0 + sg * 64 + ci * 16) >> 1);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) drop_pair(e.drop, pair0 + i, v[2 * i], v[2 * i + 1]);
+                            }
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                uint4* slot = reinterpret_cast<uint4*>(stg_r + stage_off(lane, ci * 2 + g));
+                                const uint4 h = *slot;
+                                const uint32_t* hw = reinterpret_cast<const uint32_t*>(&h);
+                                uint4 o;
+                                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 hf = make_float2(__uint_as_float(hw[i] << 16), __uint_as_float(hw[i] & 0xffff0000u));
+                                    ow[i] = pack_bf16x2(v[8 * g + 2 * i] * hf.x, v[8 * g + 2 * i + 1] * hf.y);
+                                }
+                                *slot = o;
+                            }
+                        }
+                        stage_tma_store(&tmC, stg_s, colb + sg * 64, m0 + q * 32, lane);
+                        if (sg + 1 < NSEG && lane == 0) {
+                            mbar_expect_tx(rbar, 4096);
+                            tma_load_2d(stg_s, &tmR, colb + (sg + 1) * 64, m0 + q * 32, rbar);
                         }
                     }
                 } else {
@@ -1091,10 +1133,16 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 // bit 1 of use_tma when the launch qualifies (fp32 output through TMA stores, 16-byte aligned residual with the output's pitch).
 static int residual_box_map(const Epilogue& epi, int M, int N, int& use_tma, CUtensorMap* out) {
     const int mode = epi_mode(epi);
-    if (!g_gct_res_box || !(use_tma & 1) || !(mode == 2 || mode == 8) || !epi.res32 || !epi.out32) return GCT_OK;
-    if ((reinterpret_cast<uintptr_t>(epi.res32) & 15) || ((size_t)epi.ldc * 4) % 16) return GCT_OK;
-    GCT_TRY(get_tensor_map(epi.res32, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 4, 32, 32, out, 4));
-    use_tma |= 2;
+    if (!g_gct_res_box || !(use_tma & 1)) return GCT_OK;
+    if ((mode == 2 || mode == 8) && epi.res32 && epi.out32) {
+        if ((reinterpret_cast<uintptr_t>(epi.res32) & 15) || ((size_t)epi.ldc * 4) % 16) return GCT_OK;
+        GCT_TRY(get_tensor_map(epi.res32, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 4, 32, 32, out, 4));
+        use_tma |= 2;
+    } else if (mode == 10 && epi.aux_in && epi.outT) {      // multiply-by-aux: the bf16 factor as 64-column boxes
+        if ((reinterpret_cast<uintptr_t>(epi.aux_in) & 15) || ((size_t)epi.ldc * 2) % 16) return GCT_OK;
+        GCT_TRY(get_tensor_map(epi.aux_in, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 2, 64, 32, out, 2));
+        use_tma |= 4;
+    }
     return GCT_OK;
 }
 
