@@ -22,6 +22,8 @@
 #include "gemm_tc.cuh"
 #include <math_constants.h>
 
+extern int g_gct_attn_box;
+
 namespace atc {
 using namespace tc;
 
@@ -89,7 +91,7 @@ struct FwdLayout {
 
 __global__ void __launch_bounds__(256, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, AttnParams p) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int box_store, AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -231,7 +233,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // O is 64 columns: each half stores 32 of them
         float o32[32];
         tmem_ld32(trow + half * 32, o32);
-        if (row < Lq) {
+        if (box_store) {
+            // the output tile leaves as ONE TMA box (rows past Lq are outside the rank-3 map): a lane writing its own row to
+            // global memory makes every 16-byte store of the warp hit a different line
+            if (row < RPq) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(o32[g * 8 + 2 * e] * inv, o32[g * 8 + 2 * e + 1] * inv);
+                    *reinterpret_cast<uint4*>(sm + L.q + swz16(row, half * 4 + g)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);    // Q / P are dead
+                }
+            }
+        } else if (row < Lq) {
             bf16* og = reinterpret_cast<bf16*>(p.O) + ((size_t)b * Lq + row) * p.ldo + h * 64 + half * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -242,8 +256,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     }
+    if (box_store) fence_async_smem();
     tcgen05_fence_before();
     __syncthreads();
+    if (box_store && t == 0) {
+        tma_store_3d(&tmO, base + L.q, h * 64, 0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
@@ -266,7 +286,9 @@ struct BwdLayout {
 
 __global__ void __launch_bounds__(256, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, AttnBwdParams bp) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
+                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, int box_io, AttnBwdParams bp) {
     const AttnParams& p = bp.f;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -287,11 +309,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (t == 32) {
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bars, (uint32_t)(2 * RPq + 2 * NS) * 128u);
+        mbar_expect_tx(bars, (uint32_t)((box_io ? 3 : 2) * RPq + 2 * NS) * 128u);
         tma_load_2d(base + L.q, &tmQ, h * 64, b * Lq, bars);
         tma_load_2d(base + L.k, &tmK, h * 64, b * Lk, bars);
         tma_load_2d(base + L.v, &tmV, h * 64, b * Lk, bars);
         tma_load_2d(base + L.dO, &tmDO, h * 64, b * Lq, bars);
+        if (box_io) tma_load_2d(base + L.ds, &tmO, h * 64, b * Lq, bars);      // forward output tile: parked where dS goes later
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
@@ -308,7 +331,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool qok = row < Lq;
     // forward output row (32 of its 64 columns) for D = rowsum(dO * O): requested before the TMA wait
     uint4 ov[4];
-    if (qok) {
+    if (qok && !box_io) {
         const uint4* og = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.O) + ((size_t)b * Lq + row) * p.ldo + h * 64 + half * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) ov[i] = og[i];
@@ -334,6 +357,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint4 dv = *reinterpret_cast<const uint4*>(sm + L.dO + swz16(row, half * 4 + i));
+            if (box_io) ov[i] = *reinterpret_cast<const uint4*>(sm + L.ds + swz16(row, half * 4 + i));
             const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&dv);
             const __nv_bfloat162* o = reinterpret_cast<const __nv_bfloat162*>(&ov[i]);
 #pragma unroll
@@ -428,7 +452,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto store_chunk = [&](uint32_t col, void* dst, int ld, int Lr, int which) {
         float v[32];
         tmem_ld32(trow + col + half * 32, v);
-        if (row < Lr) {
+        if (box_io) {
+            // park the tile in shared memory (dV over K, dK over V / Pd, dQ over Q: all dead once the last MMAs have completed);
+            // it leaves as one TMA box per tensor below
+            const int RPr = (Lr + 15) & ~15;
+            uint8_t* tile = sm + (which == 0 ? L.k : (which == 1 ? L.v : L.q));
+            if (row < RPr) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(v[g4 * 8 + 2 * e], v[g4 * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(tile + swz16(row, half * 4 + g4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+        } else if (row < Lr) {
             bf16* og = reinterpret_cast<bf16*>(dst) + ((size_t)b * Lr + row) * ld + h * 64 + half * 32;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
@@ -461,8 +499,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         store_chunk(64, bp.dK, bp.lddk, Lk, 1);
     }
     if (q * 32 < Lq) store_chunk(128, bp.dQ, bp.lddq, Lq, 2);
+    if (box_io) fence_async_smem();
     tcgen05_fence_before();
     __syncthreads();
+    if (box_io && t == 0) {
+        tma_store_3d(&tmDV, base + L.k, h * 64, 0, b);
+        tma_store_3d(&tmDK, base + L.v, h * 64, 0, b);
+        tma_store_3d(&tmDQ, base + L.q, h * 64, 0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     if (want_bsum && t < 192) {
         float* dst = (t < 64) ? bp.bsum_v : (t < 128) ? bp.bsum_k : bp.bsum_q;
         if (dst) atomicAdd(dst + h * 64 + (t & 63), csum[t]);
@@ -493,7 +539,13 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
             done_.cur() = 1;
         }
     }
-    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, p);
+    CUtensorMap to = tq;
+    int box_store = 0;
+    if (g_gct_attn_box && (reinterpret_cast<uintptr_t>(p.O) & 15) == 0 && (p.ldo % 8) == 0) {
+        GCT_TRY(get_tensor_map3(p.O, (uint64_t)p.H * 64, (uint64_t)p.Lq, (uint64_t)p.B, (uint64_t)p.ldo * 2, 64, (uint32_t)RPq, &to));
+        box_store = 1;
+    }
+    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, to, box_store, p);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
@@ -515,7 +567,17 @@ static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
             done_.cur() = 1;
         }
     }
-    attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, bp);
+    CUtensorMap to = tq, tdq = tq, tdk = tq, tdv = tq;
+    int box_io = 0;
+    auto ok16 = [](const void* ptr, int ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld % 8) == 0; };
+    if (g_gct_attn_box && ok16(p.O, p.ldo) && ok16(bp.dQ, bp.lddq) && ok16(bp.dK, bp.lddk) && ok16(bp.dV, bp.lddv)) {
+        GCT_TRY(operand_map(p.O, p.ldo, p.B * p.Lq, p.H, RPq, &to));
+        GCT_TRY(get_tensor_map3(bp.dQ, (uint64_t)p.H * 64, (uint64_t)p.Lq, (uint64_t)p.B, (uint64_t)bp.lddq * 2, 64, (uint32_t)RPq, &tdq));
+        GCT_TRY(get_tensor_map3(bp.dK, (uint64_t)p.H * 64, (uint64_t)p.Lk, (uint64_t)p.B, (uint64_t)bp.lddk * 2, 64, (uint32_t)RPk, &tdk));
+        GCT_TRY(get_tensor_map3(bp.dV, (uint64_t)p.H * 64, (uint64_t)p.Lk, (uint64_t)p.B, (uint64_t)bp.lddv * 2, 64, (uint32_t)RPk, &tdv));
+        box_io = 1;
+    }
+    attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, to, tdq, tdk, tdv, box_io, bp);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }

@@ -17,6 +17,7 @@ int g_gct_attn_bias_separate = 0;
 int g_za_cfg = 3;
 int g_gct_sm_budget = 0;
 int g_gct_res_box = 1;
+int g_gct_attn_box = 1;
 int g_gct_rownorm = 0;
 int g_gct_rownorm_res_tma = 1;
 
@@ -45,7 +46,7 @@ int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
 int gct_set_rownorm_fusion(int mode) { g_gct_rownorm = mode & 3; g_gct_rownorm_res_tma = (mode & 4) ? 0 : 1; return GCT_OK; }
-int gct_set_residual_box(int enabled) { g_gct_res_box = enabled; return GCT_OK; }
+int gct_set_residual_box(int enabled) { g_gct_res_box = enabled & 1; g_gct_attn_box = (enabled & 2) ? 0 : 1; return GCT_OK; }
 int gct_set_sm_budget(int sms) { g_gct_sm_budget = sms; return GCT_OK; }
 int gct_set_zattn_config(int ctas_per_sm) { g_za_cfg = ctas_per_sm; return GCT_OK; }
 int gct_set_attention_bias_grad_fused(int enabled) { g_gct_attn_bias_separate = !enabled; return GCT_OK; }

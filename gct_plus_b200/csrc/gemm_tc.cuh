@@ -1115,6 +1115,52 @@ static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint6
     return GCT_OK;
 }
 
+// Rank-3 map over a [batch][rows][inner] bf16 tensor (row pitch `row_pitch_bytes`, batch pitch rows * row pitch): boxes of
+// box_inner x box_rows x 1, SWIZZLE_128B.  Rows past `rows` of a batch element are out of bounds for the map, so a store of a
+// padded tile never touches the next element (the rank-2 operand maps treat [batch * rows] as one dimension).
+static int get_tensor_map3(const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_pitch_bytes, uint32_t box_inner,
+                           uint32_t box_rows, CUtensorMap* out) {
+    struct Key3 {
+        const void* p; uint64_t inner, rows, batch, pitch; uint32_t b0, b1;
+        bool operator==(const Key3& o) const { return p == o.p && inner == o.inner && rows == o.rows && batch == o.batch && pitch == o.pitch && b0 == o.b0 && b1 == o.b1; }
+    };
+    struct Hash3 { size_t operator()(const Key3& k) const { size_t h = (size_t)k.p; h = h * 1000003u ^ k.inner; h = h * 1000003u ^ k.rows; h = h * 1000003u ^ k.batch; h = h * 1000003u ^ k.pitch; h = h * 1000003u ^ k.b1; return h; } };
+    static std::mutex mu;
+    static std::unordered_map<Key3, CUtensorMap, Hash3> cache;
+    static PFN_encodeTiled encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GCT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) GCT_FAIL(GCT_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    Key3 key{ptr, inner, rows, batch, row_pitch_bytes, box_inner, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return GCT_OK; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_pitch_bytes & 15))
+        GCT_FAIL(GCT_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch (ptr=%p pitch=%llu)", ptr,
+                 (unsigned long long)row_pitch_bytes);
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {row_pitch_bytes, rows * row_pitch_bytes};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) GCT_FAIL(GCT_ERR_CUDA, "cuTensorMapEncodeTiled (rank 3) failed: %d", (int)r);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return GCT_OK;
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(src_smem)
+                 : "memory");
+}
+
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int split_k, const Epilogue& epi,
                       cudaStream_t st) {

@@ -92,7 +92,9 @@ int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring s
 int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue (default on) */
 int gct_set_cta_pair_gemm(int level);               /* persistent GEMM over CTA pairs (tcgen05.mma.cta_group::2): 0 off, 1 K-major
                                                        operands only, 2 (default) also dgrad / wgrad operand layouts */
-int gct_set_residual_box(int enabled);             /* persistent GEMM: fp32 residual fetched as TMA boxes into the staging tile (default on) */
+int gct_set_residual_box(int mode);                /* bit 0 (default 1): persistent GEMM epilogues fetch the fp32 residual / the multiply-by-aux factor as
+                                                       TMA boxes into the staging tile; bit 1 set: the tcgen05 attention kernels store O / dQ / dK / dV (and
+                                                       load the saved O) per lane instead of as TMA boxes */
 int gct_set_sm_budget(int sms);                     /* persistent GEMMs use at most this many SMs (0 = all): room for a concurrent NCCL kernel */
 int gct_set_zattn_config(int ctas_per_sm);          /* tuning: latent-space cross-attention compiled for 3 (default) or 4 resident CTAs per SM */
 int gct_set_attention_bias_grad_fused(int enabled); /* bias gradients of the q/k/v projections from the tcgen05 attention backward's
