@@ -17,7 +17,10 @@ lib = L.lib()
 model = Cvaetf(32, 32, dropout=0.1, nconds=3, use_cond2lat=True, compute_dtype="bf16", **bench.ARCH).to(dev).train()
 tr = FusedTrainer(model, "pvaetf")
 batch = bench.make_train_batch(512, 78, 3, 0, 1, dev=dev)
-settings = [("pair=0 ew4=1", 0, 1), ("pair=1 ew4=1", 1, 1), ("pair=2 ew4=1", 2, 1), ("pair=2 ew4=0", 2, 0)]
+# gct_set_residual_box: bit 0 = GEMM epilogue operands (fp32 residual, multiply-by-aux factor) as TMA boxes; bit 1 set = attention
+# kernels store / load per lane instead of as TMA boxes
+settings = [("gemm boxes off, attention boxes off", 2), ("gemm boxes on, attention boxes off", 3), ("gemm boxes on, attention boxes on", 1),
+            ("gemm boxes off, attention boxes on", 0)]
 
 
 def run(n):
@@ -33,8 +36,7 @@ def run(n):
 for _ in range(3):
     tr.step(batch, 0.5)
 for rep in range(2):
-    for name, pair, ew4 in settings:
-        lib.gct_set_cta_pair_gemm(pair)
-        lib.gct_set_epilogue_warps16(ew4)
+    for name, mode in settings:
+        lib.gct_set_residual_box(mode)
         run(2)
         print(f"rep {rep} {name}: {run(10):.3f} ms/step", flush=True)
