@@ -8,11 +8,12 @@
 // separate norm_fwd launch and its fp32 re-read of x, and a 128 x 512 tile has 1.6x the arithmetic intensity per operand byte
 // of the 128 x 128 tiles these short-K projections otherwise use.
 // [B200] measured (scripts/one_rownorm.py, profiles/r02_rownorm_fusion_ab.txt): correct, but NOT faster than the residual GEMM +
-// norm_fwd pair -- M = 41472, K = 512: 96.8 vs 84.6 us; M = 30000: 67.1 vs 64.9 us (K = 512), 82.5 vs 72.4 us (K = 1024).  With
-// all 512 TMEM columns holding one accumulator the epilogue (~27 us per tile: per-row residual loads, 96 staged TMA stores, three
-// TMEM passes) cannot overlap the next tile's main loop, while the unfused kernel double-buffers 128-column accumulators; writing
-// x / y straight from registers instead of through the staging tiles was slower still (134 us).  Kept as a tested option
-// (gct_set_rownorm_fusion), off by default.
+// norm_fwd pair.  With the residual read per lane (RES_TMA = false): M = 41472, K = 512: 96.8 us; with the residual fetched as
+// TMA boxes into the staging tiles (RES_TMA = true, the default): 79 us -- against 84.6 us for the pair at that time and 71 us
+// (47.4 + 23.5) once the same boxed fetch went into the persistent GEMM's own epilogue.  With all 512 TMEM columns holding one
+// accumulator the epilogue (three TMEM passes, 96 staged TMA stores per tile) cannot overlap the next tile's main loop, while the
+// unfused kernel double-buffers 128-column accumulators; writing x / y straight from registers instead of through the staging
+// tiles was slower still (134 us).  Kept as a tested option (gct_set_rownorm_fusion), off by default.
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2..17 epilogue (TMEM lane quarter = warp % 4,
 // column slice = (warp - 2) / 4 of 128 columns).  2-stage ring of (A 128 x 64, B 512 x 64) bf16 tiles, SWIZZLE_128B.
 #pragma once

@@ -117,10 +117,11 @@ int gct_gemm(const void* A, int a_mn, int64_t lda, const void* B, int b_mn, int6
              int ldc, int flags, int split_k, int bn_hint, int dtype, void* stream);
 /* Residual projection + the Norm after it in one kernel (Model/layers.py:26-29,62-72 + Model/modules.py:80-95), d_model = 512, bf16:
  * out32 [M,512] = A[M,K] W[512,K]^T + bias + res32 ; normT (bf16) [, norm32] = alpha (out32 - mean) / (std_unbiased + eps) + beta.
- * out32 may alias res32.  gct_set_rownorm_fusion: 0 (default) = the model keeps the residual GEMM + norm_fwd pair, 1 = fused when >= 96 row tiles, 2 = always.
- * [B200] correct (unit + model + decode tests with it forced on) but not faster than the pair it replaces: M=41472 K=512 96.8 vs
- * 84.6 us, M=30000 K=512 67.1 vs 64.9 us, K=1024 82.5 vs 72.4 us (single-buffered 512-column accumulator: the three-pass epilogue
- * cannot overlap the next tile's main loop), so it is off by default. */
+ * out32 may alias res32.  gct_set_rownorm_fusion: bits 0-1: 0 (default) = the model keeps the residual GEMM + norm_fwd pair, 1 = fused
+ * when >= 96 row tiles, 2 = always; bit 2 set = the fused kernel reads the residual per lane instead of as TMA boxes.
+ * [B200] correct (unit + model + decode tests with it forced on) but not faster than the pair it replaces: M=41472 K=512 79 us
+ * (96.8 with the per-lane residual) vs 71 us for the pair (single-buffered 512-column accumulator: the three-pass epilogue cannot
+ * overlap the next tile's main loop), so it is off by default. */
 int gct_gemm_rownorm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, const float* bias, const float* res32,
                      float* out32, const float* alpha, const float* beta, void* normT, float* norm32, float eps, void* stream);
 int gct_set_rownorm_fusion(int mode);
