@@ -68,6 +68,8 @@ _PROTOS = {
     "gct_set_attention_bias_grad_fused": (C.c_int, [C.c_int]),
     "gct_set_zattn_config": (C.c_int, [C.c_int]),
     "gct_set_sm_budget": (C.c_int, [C.c_int]),
+    "gct_set_attention_trace": (C.c_int, [C.c_void_p]),
+    "gct_set_attention_persistent": (C.c_int, [C.c_int]),
     "gct_set_residual_box": (C.c_int, [C.c_int]),
     "gct_set_latent_cross_attention": (C.c_int, [C.c_int]),
     "gct_set_ffn_saved_activation": (C.c_int, [C.c_int]),

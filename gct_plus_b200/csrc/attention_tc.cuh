@@ -23,6 +23,8 @@
 #include <math_constants.h>
 
 extern int g_gct_attn_box;
+extern int g_gct_attn_persist;                    // persistent, operand-prefetching kernels for L <= 96 (gct_set_attention_persistent)
+extern unsigned long long* g_gct_attn_trace;      // debugging hook (gct_set_attention_trace): per-CTA phase timestamps
 
 namespace atc {
 using namespace tc;
@@ -31,6 +33,22 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kFill2 = -1.4426950408889634e9f;     // the reference's -1e9 fill, in log2 units
 
+// phase i of tile `slot` (default: this CTA's index): [16*slot + i] = globaltimer (ns), [16*blockIdx + 8 + i] = SM clock; slot 7 of the first group = %smid
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int i, int slot = -1) {
+    if (trace != nullptr && threadIdx.x == 0) {
+        if (slot < 0) slot = blockIdx.x;
+        unsigned long long g, c;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g));
+        asm volatile("mov.u64 %0, %clock64;" : "=l"(c));
+        trace[(size_t)slot * 16 + i] = g;
+        trace[(size_t)slot * 16 + 8 + i] = c;
+        if (i == 0) {
+            uint32_t sm;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+            trace[(size_t)slot * 16 + 7] = sm;
+        }
+    }
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `chunk` (8 bf16 columns) of row `row` inside one [rows][64] bf16 block, 128B swizzle
@@ -91,7 +109,8 @@ struct FwdLayout {
 
 __global__ void __launch_bounds__(256, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int box_store, AttnParams p) {
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int box_store, AttnParams p,
+                   unsigned long long* trace) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -105,6 +124,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    trace_mark(trace, 0);
     if (t == 32) {
         // the thread that initialises the barriers also starts the loads: they are in flight before the TMEM allocation
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
@@ -123,10 +143,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
+    trace_mark(trace, 1);
     const bool dense = p.mask_rstride != 0;
     if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
     __syncthreads();
     mbar_wait(bars, 0);
+    trace_mark(trace, 2);
     if (t == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(128, NS, false, false);
@@ -146,6 +168,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bars + 8, 0);
     __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge after the elected-thread branch / spin loop
     tcgen05_fence_after();
+    trace_mark(trace, 3);
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float mx = -CUDART_INF_F;
     if (wactive) {
@@ -217,6 +240,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_async_smem();
     tcgen05_fence_before();
     __syncthreads();
+    trace_mark(trace, 4);
     if (t == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(128, 64, false, true);
@@ -229,6 +253,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bars + 16, 0);
     __syncwarp();
     tcgen05_fence_after();
+    trace_mark(trace, 5);
     if (wactive) {
         // O is 64 columns: each half stores 32 of them
         float o32[32];
@@ -264,6 +289,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    trace_mark(trace, 6);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
@@ -288,7 +314,8 @@ __global__ void __launch_bounds__(256, 2)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
-                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, int box_io, AttnBwdParams bp) {
+                   const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, int box_io, AttnBwdParams bp,
+                   unsigned long long* trace) {
     const AttnParams& p = bp.f;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -306,6 +333,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* csum = reinterpret_cast<float*>(sm + L.csum);      // [dV | dK | dQ][64] column sums (bias gradients), see below
     const bool want_bsum = bp.bsum_q != nullptr || bp.bsum_k != nullptr || bp.bsum_v != nullptr;
     if (t < 192) csum[t] = 0.f;
+    trace_mark(trace, 0);
     if (t == 32) {
         for (int i = 0; i < 3; ++i) mbar_init(bars + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -337,8 +365,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 0; i < 4; ++i) ov[i] = og[i];
     }
     const float lse2 = qok ? p.lse[((size_t)b * p.H + h) * Lq + row] * kLog2e : 0.f;
+    trace_mark(trace, 1);
     __syncthreads();
     mbar_wait(bars, 0);
+    trace_mark(trace, 2);
     if (t == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc(128, NS, false, false);
@@ -381,6 +411,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bars + 8, 0);
     __syncwarp();
     tcgen05_fence_after();
+    trace_mark(trace, 3);
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     if (wlive) {
 #pragma unroll
@@ -424,6 +455,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_async_smem();
     tcgen05_fence_before();
     __syncthreads();
+    trace_mark(trace, 4);
     if (t == 0) {
         tcgen05_fence_after();
         const int nq = RPq >> 4, nk = NS >> 4;
@@ -446,6 +478,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(bars + 16, 0);
     __syncwarp();
     tcgen05_fence_after();
+    trace_mark(trace, 5);
     // each thread: 32 of the 64 columns of its dV / dK row (row = key) and of its dQ row (row = query)
     // `which` 0/1/2 = dV/dK/dQ.  With bias-gradient outputs requested the warp also reduces its 32 rows column-wise (butterfly
     // with halving: 31 shuffles leave lane j with the sum of column half*32 + j) into the CTA's csum slab.
@@ -509,11 +542,517 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    trace_mark(trace, 6);
     if (want_bsum && t < 192) {
         float* dst = (t < 64) ? bp.bsum_v : (t < 128) ? bp.bsum_k : bp.bsum_q;
         if (dst) atomicAdd(dst + h * 64 + (t & 63), csum[t]);
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Persistent variants for L <= 96 (both sequence lengths), the shapes the training step runs (src 81, trg 80).
+// [B200] per-CTA phase timestamps of the one-tile-per-CTA kernels above (scripts/trace_attention.py,
+// profiles/r02_attention_trace.txt) show ~2.7 us of each CTA's ~10 us (backward) / ~6.7 us (forward) life spent before its
+// operand tiles have landed, plus ~1 us between one CTA's exit and its successor's start.  Here a CTA keeps its TMEM
+// allocation and walks a contiguous range of (batch, head) tiles; the next tile's operands are requested while the current
+// tile is still computing, into shared-memory units whose contents are dead by then:
+//   backward (2 CTAs / SM, nine units of U = 128 * ceil16(L) bytes): Q and K alternate between two pairs of units (the pair of
+//   tile i+1 is loaded during tile i); V, dO and the saved O of tile i+1 are requested as soon as tile i's last MMAs have
+//   completed (into the dS / dO units) and land while tile i's results are being staged and stored;
+//   forward (3 CTAs / SM, five units): Q / K pairs as above, V of tile i+1 requested when tile i's P V has completed.
+// Results leave as TMA boxes from dead units exactly as above; a unit is re-used only after `cp.async.bulk.wait_group.read`.
+struct FwdPersistLayout {
+    int U, q0, k0, ps, v, bits, red, bars, total;       // pair x: Q at q0 + x*ps, K at k0 + x*ps; P block 0 / 1 of a tile are written over its own Q / K units
+    __host__ __device__ FwdPersistLayout(int RP) {
+        U = RP * 128;
+        q0 = 0; k0 = U; ps = 2 * U; v = 4 * U;
+        bits = 5 * U; red = bits + 2048; bars = red + 2048; total = bars + 128;
+        if (total < k0 + ps + 16384) total = k0 + ps + 16384;          // UMMA A operands span 128 rows from their base
+        total += 1024;
+    }
+};
+
+__global__ void __launch_bounds__(256, 3)
+attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnParams p, int ntiles,
+                           unsigned long long* trace) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const int Lq = p.Lq, Lk = p.Lk;
+    const int RPq = (Lq + 15) & ~15, NS = (Lk + 15) & ~15;
+    const FwdPersistLayout L(RPq > NS ? RPq : NS);
+    const uint32_t bars = base + L.bars;
+    const uint32_t bar_qk0 = bars, bar_v = bars + 16, bar_m1 = bars + 24, bar_m2 = bars + 32;     // bar_qk1 = bars + 8
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bars + 64);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(sm + L.bits);
+    float* red = reinterpret_cast<float*>(sm + L.red);       // [2 kinds][2 halves][128 rows]
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    const int first = (int)((long long)blockIdx.x * ntiles / gridDim.x), last = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+    const int n = last - first;
+    const uint32_t qk_bytes = (uint32_t)(RPq + NS) * 128u, v_bytes = (uint32_t)NS * 128u;
+    if (t == 0 && n > 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int b0 = first / p.H, h0 = first % p.H;
+        mbar_expect_tx(bar_qk0, qk_bytes);
+        tma_load_2d(base + L.q0, &tmQ, h0 * 64, b0 * Lq, bar_qk0);
+        tma_load_2d(base + L.k0, &tmK, h0 * 64, b0 * Lk, bar_qk0);
+        mbar_expect_tx(bar_v, v_bytes);
+        tma_load_2d(base + L.v, &tmV, h0 * 64, b0 * Lk, bar_v);
+        if (n > 1) {
+            const int b1 = (first + 1) / p.H, h1 = (first + 1) % p.H;
+            mbar_expect_tx(bar_qk0 + 8, qk_bytes);
+            tma_load_2d(base + (L.q0 + L.ps), &tmQ, h1 * 64, b1 * Lq, bar_qk0 + 8);
+            tma_load_2d(base + (L.k0 + L.ps), &tmK, h1 * 64, b1 * Lk, bar_qk0 + 8);
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const bool dense = p.mask_rstride != 0;
+    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
+    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const bool wactive = q * 32 < Lq;                 // warp-uniform: the warp owns at least one real query row
+    const float cs = p.scale * kLog2e;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    int b_prev = -1;
+    for (int i = 0; i < n; ++i) {
+        const int tile = first + i, b = tile / p.H, h = tile - b * p.H, pr = i & 1;
+        const uint32_t ph = (uint32_t)(i & 1), phqk = (uint32_t)((i >> 1) & 1);
+        const uint32_t uq = (uint32_t)(L.q0 + pr * L.ps), uk = (uint32_t)(L.k0 + pr * L.ps);
+        trace_mark(trace, 0, tile);
+        const bool newmask = p.mask != nullptr && b != b_prev;      // CTA-uniform
+        b_prev = b;
+        if (newmask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
+        if (t == 0) {
+            mbar_wait(bar_qk0 + 8 * pr, phqk);
+            tcgen05_fence_after();
+            trace_mark(trace, 2, tile);
+            const uint32_t idesc = make_idesc(128, NS, false, false);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem, make_smem_desc(base + uq + k * 32, 16, 1024), make_smem_desc(base + uk + k * 32, 16, 1024), idesc,
+                          k > 0 ? 1u : 0u);
+            umma_commit(bar_m1);
+            // tile i-1's output box has left its unit (the other pair's Q unit): that pair is free for tile i+1's Q / K
+            if (i > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (i > 0 && i + 1 < n) {
+                const int b1 = (tile + 1) / p.H, h1 = (tile + 1) % p.H;
+                const uint32_t bq = bar_qk0 + 8 * (pr ^ 1);
+                mbar_expect_tx(bq, qk_bytes);
+                tma_load_2d(base + (L.q0 + (pr ^ 1) * L.ps), &tmQ, h1 * 64, b1 * Lq, bq);
+                tma_load_2d(base + (L.k0 + (pr ^ 1) * L.ps), &tmK, h1 * 64, b1 * Lk, bq);
+            }
+        }
+        if (newmask) __syncthreads();
+        uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (p.mask) mb = *reinterpret_cast<const uint4*>(bits + (dense ? min(row, Lq - 1) : 0) * 4);
+        mbar_wait(bar_m1, ph);
+        __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge after the elected-thread branch / spin loop
+        tcgen05_fence_after();
+        trace_mark(trace, 3, tile);
+        float mx = -CUDART_INF_F;
+        if (wactive) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const int c16 = cbeg + ci;
+                if (c16 < cend) {
+                    float v[16];
+                    tmem_ld16(trow + c16 * 16, v);
+                    const int nvalid = Lk - c16 * 16;
+                    if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
+                    else score16<true>(v, mask16(mb, c16), cs, nvalid);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) mx = fmaxf(mx, v[e]);
+                }
+            }
+        }
+        red[half * 128 + row] = mx;
+        __syncthreads();
+        mx = fmaxf(red[row], red[128 + row]);
+        float sum = 0.f;
+        const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
+        if (wactive) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const int c16 = cbeg + ci;
+                if (c16 < cend) {
+                    float v[16];
+                    tmem_ld16(trow + c16 * 16, v);
+                    const int nvalid = Lk - c16 * 16;
+                    if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
+                    else score16<true>(v, mask16(mb, c16), cs, nvalid);
+                    uint32_t pk[8];
+                    const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;      // drow32 is even
+#pragma unroll
+                    for (int e2 = 0; e2 < 8; ++e2) {
+                        const float2 d = __fadd2_rn(make_float2(v[2 * e2], v[2 * e2 + 1]), make_float2(-mx, -mx));
+                        float2 e = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                        sum += e.x + e.y;
+                        e = __fmul2_rn(e, drop_mult_pair<true>(p.drop, pair0 + e2));
+                        pk[e2] = pack_bf16(e.x, e.y);
+                    }
+                    if (row < RPq) {       // a unit holds ceil16(L) rows
+                        uint8_t* pt = sm + ((c16 >> 2) ? uk : uq);
+                        *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                }
+            }
+        }
+        red[256 + half * 128 + row] = sum;
+        __syncthreads();
+        sum = red[256 + row] + red[256 + 128 + row];
+        const float inv = 1.f / sum;
+        if (p.probs && wactive) {          // get_attn: normalised pre-dropout probabilities (S is still intact in TMEM)
+            const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
+#pragma unroll 1
+            for (int c16 = cbeg; c16 < cend; ++c16) {
+                float v[16];
+                tmem_ld16(trow + c16 * 16, v);
+                const int nvalid = Lk - c16 * 16;
+                score16<true>(v, mask16(mb, c16), cs, nvalid);
+                if (row < Lq) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (e < nvalid) p.probs[prow + c16 * 16 + e] = ex2_approx(v[e] - mx) * inv;
+                }
+            }
+        }
+        if (half == 0 && row < Lq && p.lse) p.lse[((size_t)b * p.H + h) * Lq + row] = (mx + __log2f(sum)) * kLn2;
+        fence_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        trace_mark(trace, 4, tile);
+        if (t == 0) {
+            mbar_wait(bar_v, ph);
+            tcgen05_fence_after();
+            const uint32_t idesc = make_idesc(128, 64, false, true);
+            const int nk = NS >> 4;
+            for (int k = 0; k < nk; ++k)
+                umma_bf16(tmem, make_smem_desc(base + ((k >> 2) ? uk : uq) + (k & 3) * 32, 16, 1024),
+                          make_smem_desc(base + L.v + k * 2048, 8192, 1024), idesc, k > 0 ? 1u : 0u);
+            umma_commit(bar_m2);
+        }
+        mbar_wait(bar_m2, ph);
+        __syncwarp();
+        tcgen05_fence_after();
+        trace_mark(trace, 5, tile);
+        if (t == 0 && i + 1 < n) {         // V is dead: request the next tile's
+            const int b1 = (tile + 1) / p.H, h1 = (tile + 1) % p.H;
+            mbar_expect_tx(bar_v, v_bytes);
+            tma_load_2d(base + L.v, &tmV, h1 * 64, b1 * Lk, bar_v);
+        }
+        if (wactive) {
+            float o32[32];
+            tmem_ld32(trow + half * 32, o32);
+            if (row < RPq) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(o32[g * 8 + 2 * e] * inv, o32[g * 8 + 2 * e + 1] * inv);
+                    *reinterpret_cast<uint4*>(sm + uq + swz16(row, half * 4 + g)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);    // Q / P are dead
+                }
+            }
+        }
+        fence_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+        if (t == 0) {
+            tma_store_3d(&tmO, base + uq, h * 64, 0, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        trace_mark(trace, 6, tile);
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
+struct BwdPersistLayout {
+    // units of U bytes: dS block 0 / 1 (the next tile's saved O / V are parked there until the softmax pass overwrites them), dO,
+    // two (Q, K) pairs, Pd block 0 / 1.  Staging of the results: dV over this tile's K, dK over Pd block 0, dQ over this tile's Q.
+    int U, ds, dO, q0, k0, ps, pd, bits, red, csum, bars, total;      // pair x: Q at q0 + x*ps, K at k0 + x*ps
+    __host__ __device__ BwdPersistLayout(int RP) {
+        U = RP * 128;
+        ds = 0; dO = 2 * U; q0 = 3 * U; k0 = 5 * U; ps = U; pd = 7 * U;
+        bits = 9 * U; red = bits + 2048; csum = red + 1024; bars = csum + 768; total = bars + 128;
+        if (total < q0 + ps + 16384) total = q0 + ps + 16384;          // UMMA A operands span 128 rows from their base
+        total += 1024;
+    }
+};
+
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                           const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
+                           const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, AttnBwdParams bp, int ntiles,
+                           unsigned long long* trace) {
+    const AttnParams& p = bp.f;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    const int Lq = p.Lq, Lk = p.Lk;
+    const int RPq = (Lq + 15) & ~15, NS = (Lk + 15) & ~15;
+    const BwdPersistLayout L(RPq > NS ? RPq : NS);
+    const uint32_t U = (uint32_t)L.U;
+    const uint32_t bars = base + L.bars;
+    const uint32_t bar_qk0 = bars, bar_in = bars + 16, bar_m1 = bars + 24, bar_m2 = bars + 32;      // bar_qk1 = bars + 8
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bars + 64);
+    uint32_t* bits = reinterpret_cast<uint32_t*>(sm + L.bits);
+    float* red = reinterpret_cast<float*>(sm + L.red);        // [2 halves][128 rows]
+    float* csum = reinterpret_cast<float*>(sm + L.csum);      // [dV | dK | dQ][64] column sums (bias gradients)
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int q = warp & 3, half = warp >> 2, row = q * 32 + lane;
+    const bool want_bsum = bp.bsum_q != nullptr || bp.bsum_k != nullptr || bp.bsum_v != nullptr;
+    const int first = (int)((long long)blockIdx.x * ntiles / gridDim.x), last = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
+    const int n = last - first;
+    const uint32_t qk_bytes = (uint32_t)(RPq + NS) * 128u, in_bytes = (uint32_t)(NS + 2 * RPq) * 128u;
+    if (t < 192) csum[t] = 0.f;
+    if (t == 0 && n > 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int b0 = first / p.H, h0 = first % p.H;
+        mbar_expect_tx(bar_qk0, qk_bytes);
+        tma_load_2d(base + L.q0, &tmQ, h0 * 64, b0 * Lq, bar_qk0);
+        tma_load_2d(base + L.k0, &tmK, h0 * 64, b0 * Lk, bar_qk0);
+        mbar_expect_tx(bar_in, in_bytes);
+        tma_load_2d(base + L.ds + U, &tmV, h0 * 64, b0 * Lk, bar_in);
+        tma_load_2d(base + L.dO, &tmDO, h0 * 64, b0 * Lq, bar_in);
+        tma_load_2d(base + L.ds, &tmO, h0 * 64, b0 * Lq, bar_in);
+        if (n > 1) {
+            const int b1 = (first + 1) / p.H, h1 = (first + 1) % p.H;
+            mbar_expect_tx(bar_qk0 + 8, qk_bytes);
+            tma_load_2d(base + (L.q0 + L.ps), &tmQ, h1 * 64, b1 * Lq, bar_qk0 + 8);
+            tma_load_2d(base + (L.k0 + L.ps), &tmK, h1 * 64, b1 * Lk, bar_qk0 + 8);
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const bool qok = row < Lq;
+    float lse_next = (qok && n > 0) ? p.lse[(size_t)first * Lq + row] : 0.f;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns: S [0,128)  dP [128,256); after the softmax pass: dV [0,64)  dK [64,128)  dQ [128,192)
+    const bool dense = p.mask_rstride != 0;
+    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
+    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const bool wlive = q * 32 < RPq;                  // warp-uniform: rows the MN-major (query-row K dimension) reads touch
+    const float cs = p.scale * kLog2e;
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    int b_prev = -1;
+    for (int i = 0; i < n; ++i) {
+        const int tile = first + i, b = tile / p.H, h = tile - b * p.H, pr = i & 1;
+        const uint32_t ph = (uint32_t)(i & 1), phqk = (uint32_t)((i >> 1) & 1);
+        const uint32_t uq = (uint32_t)(L.q0 + pr * L.ps), uk = (uint32_t)(L.k0 + pr * L.ps);
+        trace_mark(trace, 0, tile);
+        const bool newmask = p.mask != nullptr && b != b_prev;      // CTA-uniform
+        b_prev = b;
+        if (newmask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
+        const float lse2 = lse_next * kLog2e;
+        if (qok && i + 1 < n) lse_next = p.lse[(size_t)(tile + 1) * Lq + row];       // consumed one tile later
+        if (t == 0) {
+            mbar_wait(bar_qk0 + 8 * pr, phqk);
+            mbar_wait(bar_in, ph);
+            tcgen05_fence_after();
+            trace_mark(trace, 2, tile);
+            const uint32_t idesc = make_idesc(128, NS, false, false);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem, make_smem_desc(base + uq + k * 32, 16, 1024), make_smem_desc(base + uk + k * 32, 16, 1024), idesc,
+                          k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + 128, make_smem_desc(base + L.dO + k * 32, 16, 1024), make_smem_desc(base + L.ds + U + k * 32, 16, 1024),
+                          idesc, k > 0 ? 1u : 0u);
+            umma_commit(bar_m1);
+            // tile i-1's result boxes have left their units (Pd block 0 and the other pair's Q / K units): the softmax pass may
+            // write Pd again, and that pair is free for tile i+1's Q / K
+            if (i > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (i > 0 && i + 1 < n) {
+                const int b1 = (tile + 1) / p.H, h1 = (tile + 1) % p.H;
+                const uint32_t bq = bar_qk0 + 8 * (pr ^ 1);
+                mbar_expect_tx(bq, qk_bytes);
+                tma_load_2d(base + (L.q0 + (pr ^ 1) * L.ps), &tmQ, h1 * 64, b1 * Lq, bq);
+                tma_load_2d(base + (L.k0 + (pr ^ 1) * L.ps), &tmK, h1 * 64, b1 * Lk, bq);
+            }
+        }
+        mbar_wait(bar_in, ph);       // dO and the saved O are in shared memory
+        float D = 0.f;
+        if (qok) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 dv = *reinterpret_cast<const uint4*>(sm + L.dO + swz16(row, half * 4 + c));
+                const uint4 ov = *reinterpret_cast<const uint4*>(sm + L.ds + swz16(row, half * 4 + c));
+                const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&dv);
+                const __nv_bfloat162* o = reinterpret_cast<const __nv_bfloat162*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 af = __bfloat1622float2(a[e]), of = __bfloat1622float2(o[e]);
+                    D = fmaf(af.x, of.x, D);
+                    D = fmaf(af.y, of.y, D);
+                }
+            }
+        }
+        red[half * 128 + row] = D;
+        __syncthreads();             // also: mask bits visible, thread 0 is past its wait_group.read, every reader of O is done
+        D = red[row] + red[128 + row];
+        uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (p.mask) mb = *reinterpret_cast<const uint4*>(bits + (dense ? min(row, Lq - 1) : 0) * 4);
+        const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
+        mbar_wait(bar_m1, ph);
+        __syncwarp();
+        tcgen05_fence_after();
+        trace_mark(trace, 3, tile);
+        if (wlive) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const int c16 = cbeg + ci;
+                if (c16 < cend) {
+                    float s[16], g[16];
+                    tmem_ld16(trow + c16 * 16, s);
+                    tmem_ld16(trow + 128 + c16 * 16, g);
+                    const uint32_t m16 = mask16(mb, c16);
+                    const int nvalid = Lk - c16 * 16;
+                    if (nvalid >= 16) score16<false>(s, m16, cs, 16);
+                    else score16<true>(s, m16, cs, nvalid);
+                    uint32_t pk[8], dk[8];
+                    const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 d = __fadd2_rn(make_float2(s[2 * e], s[2 * e + 1]), make_float2(-lse2, -lse2));
+                        const float2 prb = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+                        const float2 keep = drop_mult_pair<true>(p.drop, pair0 + e);
+                        const float2 pd = __fmul2_rn(prb, keep);
+                        const float2 gd = __ffma2_rn(make_float2(g[2 * e], g[2 * e + 1]), keep, make_float2(-D, -D));
+                        float2 ds = __fmul2_rn(__fmul2_rn(prb, make_float2(p.scale, p.scale)), gd);     // 1/sqrt(dk) of dQ / dK folded in
+                        // no gradient through a masked score (the reference's masked_fill); a padded column has prb = 0 already
+                        if (!(m16 & (1u << (2 * e)))) ds.x = 0.f;
+                        if (!(m16 & (2u << (2 * e)))) ds.y = 0.f;
+                        pk[e] = qok ? pack_bf16(pd.x, pd.y) : 0u;
+                        dk[e] = qok ? pack_bf16(ds.x, ds.y) : 0u;
+                    }
+                    const uint32_t blk = (uint32_t)(c16 >> 2) * U;
+                    const int ch = (c16 & 3) * 2;
+                    if (row < RPq) {      // a unit holds ceil16(L) rows
+                        *reinterpret_cast<uint4*>(sm + L.pd + blk + swz16(row, ch)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(sm + L.pd + blk + swz16(row, ch + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch)) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+                        *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch + 1)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
+                    }
+                }
+            }
+        }
+        fence_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        trace_mark(trace, 4, tile);
+        if (t == 0) {
+            tcgen05_fence_after();
+            const int nq = RPq >> 4, nk = NS >> 4;
+            // dV[key, dk] = Pd^T dO : M = keys (MN-major A, two 64-key blocks U apart), K = query rows, N = dk
+            const uint32_t idT = make_idesc(128, 64, true, true);
+            for (int k = 0; k < nq; ++k)          // 16 query rows per MMA
+                umma_bf16(tmem, make_smem_desc(base + L.pd + k * 2048, U, 1024), make_smem_desc(base + L.dO + k * 2048, 8192, 1024), idT,
+                          k > 0 ? 1u : 0u);
+            // dK[key, dk] = dS^T Q
+            for (int k = 0; k < nq; ++k)
+                umma_bf16(tmem + 64, make_smem_desc(base + L.ds + k * 2048, U, 1024), make_smem_desc(base + uq + k * 2048, 8192, 1024), idT,
+                          k > 0 ? 1u : 0u);
+            // dQ[q, dk] = dS K : A = dS K-major over keys, B = K MN-major
+            const uint32_t idQ = make_idesc(128, 64, false, true);
+            for (int k = 0; k < nk; ++k)
+                umma_bf16(tmem + 128, make_smem_desc(base + L.ds + (k >> 2) * U + (k & 3) * 32, 16, 1024),
+                          make_smem_desc(base + uk + k * 2048, 8192, 1024), idQ, k > 0 ? 1u : 0u);
+            umma_commit(bar_m2);
+        }
+        mbar_wait(bar_m2, ph);
+        __syncwarp();
+        tcgen05_fence_after();
+        trace_mark(trace, 5, tile);
+        if (t == 0 && i + 1 < n) {         // dS and dO are dead: request the next tile's V, dO and saved O
+            const int b1 = (tile + 1) / p.H, h1 = (tile + 1) % p.H;
+            mbar_expect_tx(bar_in, in_bytes);
+            tma_load_2d(base + L.ds + U, &tmV, h1 * 64, b1 * Lk, bar_in);
+            tma_load_2d(base + L.dO, &tmDO, h1 * 64, b1 * Lq, bar_in);
+            tma_load_2d(base + L.ds, &tmO, h1 * 64, b1 * Lq, bar_in);
+        }
+        // each thread: 32 of the 64 columns of its dV / dK row (row = key) and of its dQ row (row = query), parked in a dead unit
+        auto stage_chunk = [&](uint32_t col, uint32_t unit, int Lr, int which) {
+            float v[32];
+            tmem_ld32(trow + col + half * 32, v);
+            const int RPr = (Lr + 15) & ~15;
+            if (row < RPr) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[e] = pack_bf16(v[g4 * 8 + 2 * e], v[g4 * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(sm + unit + swz16(row, half * 4 + g4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            if (want_bsum) {
+                if (row >= Lr) {        // rows past the sequence: not part of the tensor
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = 0.f;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int e = 0; e < off; ++e) {
+                        const float send = up ? v[e] : v[e + off];
+                        const float keep = up ? v[e + off] : v[e];
+                        v[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                atomicAdd(&csum[which * 64 + half * 32 + lane], v[0]);
+            }
+        };
+        if (q * 32 < Lk) {
+            stage_chunk(0, uk, Lk, 0);
+            stage_chunk(64, (uint32_t)L.pd, Lk, 1);
+        }
+        if (q * 32 < Lq) stage_chunk(128, uq, Lq, 2);
+        fence_async_smem();
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+        if (t == 0) {
+            tma_store_3d(&tmDV, base + uk, h * 64, 0, b);
+            tma_store_3d(&tmDK, base + L.pd, h * 64, 0, b);
+            tma_store_3d(&tmDQ, base + uq, h * 64, 0, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (want_bsum && t < 192) {
+            float* dst = (t < 64) ? bp.bsum_v : (t < 128) ? bp.bsum_k : bp.bsum_q;
+            if (dst) atomicAdd(dst + h * 64 + (t & 63), csum[t]);
+            csum[t] = 0.f;
+        }
+        trace_mark(trace, 6, tile);
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
 static int operand_map(const void* ptr, int ld, int rows, int H, int box_rows, CUtensorMap* out) {
@@ -545,7 +1084,20 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
         GCT_TRY(get_tensor_map3(p.O, (uint64_t)p.H * 64, (uint64_t)p.Lq, (uint64_t)p.B, (uint64_t)p.ldo * 2, 64, (uint32_t)RPq, &to));
         box_store = 1;
     }
-    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, to, box_store, p);
+    if (box_store && g_gct_attn_persist && RPq <= 96 && RPk <= 96) {
+        static PerDeviceSize pdone_;
+        if (!pdone_.cur()) {
+            GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdPersistLayout(96).total));
+            GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            pdone_.cur() = 1;
+        }
+        const int ntiles = p.B * p.H, slots = 3 * sm_count();
+        attn_fwd_tc_persist_kernel<<<ntiles < slots ? ntiles : slots, 256, FwdPersistLayout(RPq > RPk ? RPq : RPk).total, st>>>(
+            tq, tk, tv, to, p, ntiles, g_gct_attn_trace);
+        GCT_LAUNCH_CHECK();
+        return GCT_OK;
+    }
+    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, to, box_store, p, g_gct_attn_trace);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
@@ -577,7 +1129,20 @@ static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
         GCT_TRY(get_tensor_map3(bp.dV, (uint64_t)p.H * 64, (uint64_t)p.Lk, (uint64_t)p.B, (uint64_t)bp.lddv * 2, 64, (uint32_t)RPk, &tdv));
         box_io = 1;
     }
-    attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, to, tdq, tdk, tdv, box_io, bp);
+    if (box_io && g_gct_attn_persist && RPq <= 96 && RPk <= 96) {
+        static PerDeviceSize pdone_;
+        if (!pdone_.cur()) {
+            GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdPersistLayout(96).total));
+            GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            pdone_.cur() = 1;
+        }
+        const int ntiles = p.B * p.H, slots = 2 * sm_count();
+        attn_bwd_tc_persist_kernel<<<ntiles < slots ? ntiles : slots, 256, BwdPersistLayout(RPq > RPk ? RPq : RPk).total, st>>>(
+            tq, tk, tv, tdo, to, tdq, tdk, tdv, bp, ntiles, g_gct_attn_trace);
+        GCT_LAUNCH_CHECK();
+        return GCT_OK;
+    }
+    attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, to, tdq, tdk, tdv, box_io, bp, g_gct_attn_trace);
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }

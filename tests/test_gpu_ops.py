@@ -92,6 +92,57 @@ def test_attention_fwd_bwd(dtype, tol, Lq, Lk, dense):
         assert float((got.float() - want).abs().max()) < 2 * tol * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("Lq,Lk,dense", [(81, 81, False), (80, 80, True), (80, 81, False), (96, 33, False), (20, 96, False), (64, 64, True)])
+@pytest.mark.parametrize("sm_budget", [0, 6])
+def test_persistent_attention_matches_one_tile_per_cta(Lq, Lk, dense, sm_budget):
+    """L <= 96 runs the persistent kernels (a CTA walks a range of (batch, head) tiles and prefetches the next tile's operands into
+    dead shared-memory units); per tile they do the arithmetic of the one-tile-per-CTA kernels in the same order, so the outputs
+    must be bit-identical -- with few SMs a CTA walks dozens of tiles (every buffer rotation and barrier phase is exercised)."""
+    B, H, d = 67, 8, 512
+    torch.manual_seed(Lq * 131 + Lk)
+    q, dO = (torch.randn(B, Lq, d, device=DEV).bfloat16() for _ in range(2))
+    k, v = (torch.randn(B, Lk, d, device=DEV).bfloat16() for _ in range(2))
+    if dense:
+        mask = torch.tril(torch.ones(Lq, Lk, device=DEV, dtype=torch.bool)).expand(B, Lq, Lk).clone()
+        mask[:, :, 3] = torch.rand(B, device=DEV)[:, None] < 0.5
+        mb, mr = Lq * Lk, Lk
+    else:
+        lens = torch.randint(1, Lk + 1, (B,), device=DEV)
+        mask = (torch.arange(Lk, device=DEV)[None, :] < lens[:, None]).view(B, 1, Lk)
+        mb, mr = Lk, 0
+    m8 = mask.to(torch.uint8).contiguous()
+    lib = L.lib()
+
+    def run(persistent):
+        lib.gct_set_attention_persistent(persistent)
+        lib.gct_set_sm_budget(sm_budget if persistent else 0)
+        out = torch.zeros(B, Lq, d, device=DEV, dtype=torch.bfloat16)
+        lse = torch.zeros(B, H, Lq, device=DEV)
+        probs = torch.zeros(B, H, Lq, Lk, device=DEV)
+        dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        try:
+            L.check(lib.gct_attention_fwd(L.ptr(q), d, L.ptr(k), d, L.ptr(v), d, L.ptr(m8), mb, mr, L.ptr(out), d, L.ptr(lse), L.ptr(probs),
+                                          B, H, Lq, Lk, 1, L.stream_ptr()))
+            L.check(lib.gct_attention_bwd(L.ptr(q), d, L.ptr(k), d, L.ptr(v), d, L.ptr(m8), mb, mr, L.ptr(lse), L.ptr(out), d, L.ptr(dO), d,
+                                          L.ptr(dq), d, L.ptr(dk), d, L.ptr(dv), d, B, H, Lq, Lk, 1, L.stream_ptr()))
+            torch.cuda.synchronize()
+        finally:
+            lib.gct_set_attention_persistent(1)
+            lib.gct_set_sm_budget(0)
+        return out, lse, probs, dq, dk, dv
+
+    got, want = run(1), run(0)
+    for name, g, w in zip(("out", "lse", "probs", "dq", "dk", "dv"), got, want):
+        assert torch.equal(g, w), f"{name}: max abs diff {float((g.float() - w.float()).abs().max())}"
+    # and the pair against the oracle (fp32 autograd)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _attn_ref(qf, kf, vf, mask)
+    ref.backward(dO.float())
+    assert float((got[0].float() - ref).abs().max()) < 2e-2 * max(1.0, float(ref.abs().max()))
+    for g, w in ((got[3], qf.grad), (got[4], kf.grad), (got[5], vf.grad)):
+        assert float((g.float() - w).abs().max()) < 4e-2 * max(1.0, float(w.abs().max()))
+
+
 def test_masks_match_golden():
     from gct_plus_b200.Model.modules import get_src_mask, get_trg_mask
     m = load_golden("misc")
