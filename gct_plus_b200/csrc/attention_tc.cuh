@@ -1,6 +1,6 @@
 // tcgen05 attention for the training / teacher-forced path: L <= 128, d_k = 64, bf16 operands.
 // One CTA per (batch, head), 256 threads: thread (q = warp % 4, half = warp / 4, lane) owns query row q*32+lane
-// (= its TMEM lane) and one half of the score columns, which it reads from TMEM in 16-column pieces -- twice in the
+// (= its TMEM lane) and every second 16-column chunk of the scores, which it reads from TMEM -- twice in the
 // forward (row max, then exp / sum / dropout), once in the backward -- so the register footprint stays small and
 // several CTAs are co-resident per SM (4 forward, 2 backward): one CTA's TMA / MMA latency hides behind another's math.
 //
@@ -97,6 +97,107 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+
+// ---- the softmax work on one 16-column chunk of a query row, shared by the one-tile-per-CTA and the persistent kernels ----
+// A chunk is classified per WARP (votes over its 32 rows) so that the branch is uniform around the warp-wide tcgen05.ld:
+//   every valid column masked for every row (padded keys, the upper triangle of the causal mask): nothing to load -- the
+//     probabilities are exactly 0 (exp2(fill - max) underflows) as long as the row has one visible key somewhere;
+//   all 16 columns visible for every row: no mask / tail selects, c*s - max as one FMA;
+//   otherwise the general path (the reference's masked_fill(-1e9) semantics, tail columns at -inf).
+// [B200] the selects were ~6 of the ~27 SASS instructions per score of the backward's pass.
+__device__ __forceinline__ uint32_t valid16(int nvalid) { return nvalid >= 16 ? 0xffffu : ((1u << nvalid) - 1u); }
+
+// forward pass 1: running row maximum (mx in scaled log2 units; mx_raw over unscaled scores of all-visible chunks)
+__device__ __forceinline__ void fwd_max_chunk(uint32_t taddr, uint32_t m16, int nvalid, float cs, float& mx, float& mx_raw) {
+    const uint32_t vis = m16 & valid16(nvalid);
+    if (__all_sync(0xffffffffu, vis == 0u)) {
+        mx = fmaxf(mx, kFill2);
+        return;
+    }
+    float v[16];
+    tmem_ld16(taddr, v);
+    if (__all_sync(0xffffffffu, vis == 0xffffu)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx_raw = fmaxf(mx_raw, v[i]);
+        return;
+    }
+    if (nvalid >= 16) score16<false>(v, m16, cs, 16);
+    else score16<true>(v, m16, cs, nvalid);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+}
+
+// forward pass 2: pk[8] = dropout(exp2(c*s - mx)) as packed bf16 pairs, sum2 += the pre-dropout probabilities (even | odd columns)
+__device__ __forceinline__ void fwd_exp_chunk(uint32_t taddr, uint32_t m16, int nvalid, float cs, float mx, const DropCtx& drop,
+                                              uint32_t pair0, float2& sum2, uint32_t* pk) {
+    const uint32_t vis = m16 & valid16(nvalid);
+    if (__all_sync(0xffffffffu, vis == 0u && mx > 0.5f * kFill2)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+        return;
+    }
+    float v[16];
+    tmem_ld16(taddr, v);
+    const bool all = __all_sync(0xffffffffu, vis == 0xffffu);
+    if (!all) {
+        if (nvalid >= 16) score16<false>(v, m16, cs, 16);
+        else score16<true>(v, m16, cs, nvalid);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 sv = make_float2(v[2 * i], v[2 * i + 1]);
+        const float2 d = all ? __ffma2_rn(sv, make_float2(cs, cs), make_float2(-mx, -mx)) : __fadd2_rn(sv, make_float2(-mx, -mx));
+        float2 e = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+        sum2 = __fadd2_rn(sum2, e);
+        e = __fmul2_rn(e, drop_mult_pair<true>(drop, pair0 + i));
+        pk[i] = pack_bf16(e.x, e.y);
+    }
+}
+
+// backward: P = exp2(c*s - lse), Pd = dropout(P) -> pk[8]; dS = P (dropout'(dP) - D) scale -> dk[8]; row sums of both
+__device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tg, uint32_t m16, int nvalid, float cs, float lse2, float D, float scale,
+                                          const DropCtx& drop, uint32_t pair0, bool qok, uint32_t* pk, uint32_t* dk, float2& rs_p,
+                                          float2& rs_s) {
+    const uint32_t vis = m16 & valid16(nvalid);
+    if (__all_sync(0xffffffffu, vis == 0u && lse2 > 0.5f * kFill2)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = dk[i] = 0u;
+        return;
+    }
+    float s[16], g[16];
+    tmem_ld16(ts, s);
+    tmem_ld16(tg, g);
+    const bool all = __all_sync(0xffffffffu, vis == 0xffffu);
+    if (!qok) {          // rows past the sequence (this thread only): zero operand rows for the MMAs that follow
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = dk[i] = 0u;
+        return;
+    }
+    if (!all) {
+        if (nvalid >= 16) score16<false>(s, m16, cs, 16);
+        else score16<true>(s, m16, cs, nvalid);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 sv = make_float2(s[2 * i], s[2 * i + 1]);
+        const float2 d = all ? __ffma2_rn(sv, make_float2(cs, cs), make_float2(-lse2, -lse2)) : __fadd2_rn(sv, make_float2(-lse2, -lse2));
+        const float2 pr = make_float2(ex2_approx(d.x), ex2_approx(d.y));
+        const float2 keep = drop_mult_pair<true>(drop, pair0 + i);
+        const float2 pd = __fmul2_rn(pr, keep);
+        const float2 gd = __ffma2_rn(make_float2(g[2 * i], g[2 * i + 1]), keep, make_float2(-D, -D));
+        float2 ds = __fmul2_rn(__fmul2_rn(pr, make_float2(scale, scale)), gd);     // 1/sqrt(dk) of dQ / dK folded in
+        if (!all) {
+            // no gradient through a masked score (the reference's masked_fill); a padded column has pr = 0 already
+            if (!(m16 & (1u << (2 * i)))) ds.x = 0.f;
+            if (!(m16 & (2u << (2 * i)))) ds.y = 0.f;
+        }
+        pk[i] = pack_bf16(pd.x, pd.y);
+        dk[i] = pack_bf16(ds.x, ds.y);
+        rs_p = __fadd2_rn(rs_p, pd);
+        rs_s = __fadd2_rn(rs_s, ds);
+    }
+}
+
 struct FwdLayout {
     int q, k, v, bits, red, bars, total;       // byte offsets from the 1 KB-aligned base; P aliases [0, 32768)
     __host__ __device__ FwdLayout(int RPq, int RPk) {
@@ -158,9 +259,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                       k > 0 ? 1u : 0u);
         umma_commit(bars + 8);
     }
-    // this thread's 16-column chunks: [cbeg, cend)
-    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
-    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    // this thread's 16-column chunks: half, half + 2, ... (interleaved so that the chunks the mask empties -- padded keys, the
+    // causal mask's upper triangle -- are shared between the two column halves)
+    const int nchk = NS >> 4;
     const bool wactive = q * 32 < Lq;                 // warp-uniform: the warp owns at least one real query row
     uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
     if (p.mask) mb = *reinterpret_cast<const uint4*>(bits + (dense ? min(row, Lq - 1) : 0) * 4);
@@ -172,19 +273,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float mx = -CUDART_INF_F;
     if (wactive) {
+        float mx_raw = -CUDART_INF_F;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-            const int c16 = cbeg + ci;
-            if (c16 < cend) {
-                float v[16];
-                tmem_ld16(trow + c16 * 16, v);
-                const int nvalid = Lk - c16 * 16;
-                if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
-                else score16<true>(v, mask16(mb, c16), cs, nvalid);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
-            }
+            const int c16 = half + 2 * ci;
+            if (c16 < nchk) fwd_max_chunk(trow + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, mx, mx_raw);
         }
+        mx = fmaxf(mx, mx_raw * cs);
     }
     red[half * 128 + row] = mx;
     __syncthreads();
@@ -192,30 +287,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float sum = 0.f;
     const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
     if (wactive) {
+        float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-            const int c16 = cbeg + ci;
-            if (c16 < cend) {
-                float v[16];
-                tmem_ld16(trow + c16 * 16, v);
-                const int nvalid = Lk - c16 * 16;
-                if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
-                else score16<true>(v, mask16(mb, c16), cs, nvalid);
+            const int c16 = half + 2 * ci;
+            if (c16 < nchk) {
                 uint32_t pk[8];
                 const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;      // drow32 is even
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float2 d = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(-mx, -mx));
-                    float2 e = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-                    sum += e.x + e.y;
-                    e = __fmul2_rn(e, drop_mult_pair<true>(p.drop, pair0 + i));
-                    pk[i] = pack_bf16(e.x, e.y);
-                }
+                fwd_exp_chunk(trow + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, mx, p.drop, pair0, sum2, pk);
                 uint8_t* pt = sm + (c16 >> 2) * 16384;
                 *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
         }
+        sum = sum2.x + sum2.y;
     }
     red[256 + half * 128 + row] = sum;
     __syncthreads();
@@ -224,7 +309,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (p.probs && wactive) {          // get_attn: normalised pre-dropout probabilities (S is still intact in TMEM)
         const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
 #pragma unroll 1
-        for (int c16 = cbeg; c16 < cend; ++c16) {
+        for (int c16 = half; c16 < nchk; c16 += 2) {
             float v[16];
             tmem_ld16(trow + c16 * 16, v);
             const int nvalid = Lk - c16 * 16;
@@ -401,8 +486,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     red[half * 128 + row] = D;
     __syncthreads();
     D = red[row] + red[128 + row];
-    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
-    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const int nchk = NS >> 4;                         // this thread's 16-column chunks: half, half + 2, ...
     const bool wlive = q * 32 < RPq;                  // warp-uniform: rows the MN-major (query-row K dimension) reads touch
     uint4 mb = make_uint4(~0u, ~0u, ~0u, ~0u);
     if (p.mask) mb = *reinterpret_cast<const uint4*>(bits + (dense ? min(row, Lq - 1) : 0) * 4);
@@ -416,31 +500,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (wlive) {
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
-            const int c16 = cbeg + ci;
-            if (c16 < cend) {
-                float s[16], g[16];
-                tmem_ld16(trow + c16 * 16, s);
-                tmem_ld16(trow + 128 + c16 * 16, g);
-                const uint32_t m16 = mask16(mb, c16);
-                const int nvalid = Lk - c16 * 16;
-                if (nvalid >= 16) score16<false>(s, m16, cs, 16);
-                else score16<true>(s, m16, cs, nvalid);
+            const int c16 = half + 2 * ci;
+            if (c16 < nchk) {
                 uint32_t pk[8], dk[8];
                 const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float2 d = __fadd2_rn(make_float2(s[2 * i], s[2 * i + 1]), make_float2(-lse2, -lse2));
-                    const float2 pr = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-                    const float2 keep = drop_mult_pair<true>(p.drop, pair0 + i);
-                    const float2 pd = __fmul2_rn(pr, keep);
-                    const float2 gd = __ffma2_rn(make_float2(g[2 * i], g[2 * i + 1]), keep, make_float2(-D, -D));
-                    float2 ds = __fmul2_rn(__fmul2_rn(pr, make_float2(p.scale, p.scale)), gd);     // 1/sqrt(dk) of dQ / dK folded in
-                    // no gradient through a masked score (the reference's masked_fill); a padded column has pr = 0 already
-                    if (!(m16 & (1u << (2 * i)))) ds.x = 0.f;
-                    if (!(m16 & (2u << (2 * i)))) ds.y = 0.f;
-                    pk[i] = qok ? pack_bf16(pd.x, pd.y) : 0u;
-                    dk[i] = qok ? pack_bf16(ds.x, ds.y) : 0u;
-                }
+                float2 rs_p = make_float2(0.f, 0.f), rs_s = rs_p;       // row sums: unused here
+                bwd_chunk(trow + c16 * 16, trow + 128 + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, lse2, D, p.scale, p.drop, pair0, qok, pk, dk,
+                          rs_p, rs_s);
                 const uint32_t blk = (uint32_t)(c16 >> 2) * (uint32_t)L.BS, blkp = (uint32_t)(c16 >> 2) * (uint32_t)L.LBOP;
                 const int ch = (c16 & 3) * 2;
                 if (row < RPq) {      // a block holds RPq rows: rows past it would land in the next block / tile
@@ -620,8 +686,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
     const bool dense = p.mask_rstride != 0;
-    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
-    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const int nchk = NS >> 4;                         // this thread's 16-column chunks: half, half + 2, ...
     const bool wactive = q * 32 < Lq;                 // warp-uniform: the warp owns at least one real query row
     const float cs = p.scale * kLog2e;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
@@ -663,19 +728,13 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         trace_mark(trace, 3, tile);
         float mx = -CUDART_INF_F;
         if (wactive) {
+            float mx_raw = -CUDART_INF_F;
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                const int c16 = cbeg + ci;
-                if (c16 < cend) {
-                    float v[16];
-                    tmem_ld16(trow + c16 * 16, v);
-                    const int nvalid = Lk - c16 * 16;
-                    if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
-                    else score16<true>(v, mask16(mb, c16), cs, nvalid);
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) mx = fmaxf(mx, v[e]);
-                }
+                const int c16 = half + 2 * ci;
+                if (c16 < nchk) fwd_max_chunk(trow + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, mx, mx_raw);
             }
+            mx = fmaxf(mx, mx_raw * cs);
         }
         red[half * 128 + row] = mx;
         __syncthreads();
@@ -683,25 +742,14 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         float sum = 0.f;
         const uint32_t drow32 = (uint32_t)((((size_t)b * p.H + h) * Lq + row) * ((Lk + 1) & ~1));    // dropout index base
         if (wactive) {
+            float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                const int c16 = cbeg + ci;
-                if (c16 < cend) {
-                    float v[16];
-                    tmem_ld16(trow + c16 * 16, v);
-                    const int nvalid = Lk - c16 * 16;
-                    if (nvalid >= 16) score16<false>(v, mask16(mb, c16), cs, 16);
-                    else score16<true>(v, mask16(mb, c16), cs, nvalid);
+                const int c16 = half + 2 * ci;
+                if (c16 < nchk) {
                     uint32_t pk[8];
                     const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;      // drow32 is even
-#pragma unroll
-                    for (int e2 = 0; e2 < 8; ++e2) {
-                        const float2 d = __fadd2_rn(make_float2(v[2 * e2], v[2 * e2 + 1]), make_float2(-mx, -mx));
-                        float2 e = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-                        sum += e.x + e.y;
-                        e = __fmul2_rn(e, drop_mult_pair<true>(p.drop, pair0 + e2));
-                        pk[e2] = pack_bf16(e.x, e.y);
-                    }
+                    fwd_exp_chunk(trow + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, mx, p.drop, pair0, sum2, pk);
                     if (row < RPq) {       // a unit holds ceil16(L) rows
                         uint8_t* pt = sm + ((c16 >> 2) ? uk : uq);
                         *reinterpret_cast<uint4*>(pt + swz16(row, (c16 & 3) * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -709,6 +757,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                     }
                 }
             }
+            sum = sum2.x + sum2.y;
         }
         red[256 + half * 128 + row] = sum;
         __syncthreads();
@@ -717,7 +766,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (p.probs && wactive) {          // get_attn: normalised pre-dropout probabilities (S is still intact in TMEM)
             const size_t prow = (((size_t)b * p.H + h) * Lq + row) * Lk;
 #pragma unroll 1
-            for (int c16 = cbeg; c16 < cend; ++c16) {
+            for (int c16 = half; c16 < nchk; c16 += 2) {
                 float v[16];
                 tmem_ld16(trow + c16 * 16, v);
                 const int nvalid = Lk - c16 * 16;
@@ -853,8 +902,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t tmem = *tmem_slot;
     // TMEM columns: S [0,128)  dP [128,256); after the softmax pass: dV [0,64)  dK [64,128)  dQ [128,192)
     const bool dense = p.mask_rstride != 0;
-    const int nchk = NS >> 4, hb = (nchk + 1) >> 1;
-    const int cbeg = half ? hb : 0, cend = half ? nchk : hb;
+    const int nchk = NS >> 4;                         // this thread's 16-column chunks: half, half + 2, ...
     const bool wlive = q * 32 < RPq;                  // warp-uniform: rows the MN-major (query-row K dimension) reads touch
     const float cs = p.scale * kLog2e;
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
@@ -922,34 +970,16 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         __syncwarp();
         tcgen05_fence_after();
         trace_mark(trace, 3, tile);
+        float2 rs_p = make_float2(0.f, 0.f), rs_s = make_float2(0.f, 0.f);     // this thread's part of rowsum(Pd), rowsum(dS) (even | odd columns)
         if (wlive) {
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                const int c16 = cbeg + ci;
-                if (c16 < cend) {
-                    float s[16], g[16];
-                    tmem_ld16(trow + c16 * 16, s);
-                    tmem_ld16(trow + 128 + c16 * 16, g);
-                    const uint32_t m16 = mask16(mb, c16);
-                    const int nvalid = Lk - c16 * 16;
-                    if (nvalid >= 16) score16<false>(s, m16, cs, 16);
-                    else score16<true>(s, m16, cs, nvalid);
+                const int c16 = half + 2 * ci;
+                if (c16 < nchk) {
                     uint32_t pk[8], dk[8];
                     const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float2 d = __fadd2_rn(make_float2(s[2 * e], s[2 * e + 1]), make_float2(-lse2, -lse2));
-                        const float2 prb = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-                        const float2 keep = drop_mult_pair<true>(p.drop, pair0 + e);
-                        const float2 pd = __fmul2_rn(prb, keep);
-                        const float2 gd = __ffma2_rn(make_float2(g[2 * e], g[2 * e + 1]), keep, make_float2(-D, -D));
-                        float2 ds = __fmul2_rn(__fmul2_rn(prb, make_float2(p.scale, p.scale)), gd);     // 1/sqrt(dk) of dQ / dK folded in
-                        // no gradient through a masked score (the reference's masked_fill); a padded column has prb = 0 already
-                        if (!(m16 & (1u << (2 * e)))) ds.x = 0.f;
-                        if (!(m16 & (2u << (2 * e)))) ds.y = 0.f;
-                        pk[e] = qok ? pack_bf16(pd.x, pd.y) : 0u;
-                        dk[e] = qok ? pack_bf16(ds.x, ds.y) : 0u;
-                    }
+                    bwd_chunk(trow + c16 * 16, trow + 128 + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, lse2, D, p.scale, p.drop, pair0, qok, pk,
+                              dk, rs_p, rs_s);
                     const uint32_t blk = (uint32_t)(c16 >> 2) * U;
                     const int ch = (c16 & 3) * 2;
                     if (row < RPq) {      // a unit holds ceil16(L) rows
@@ -959,6 +989,14 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                         *reinterpret_cast<uint4*>(sm + L.ds + blk + swz16(row, ch + 1)) = make_uint4(dk[4], dk[5], dk[6], dk[7]);
                     }
                 }
+            }
+            // Bias gradients of the v / k projections = column sums of dV / dK over the keys.  colsum(dV) = sum_q rowsum(Pd)[q] dO[q, :]
+            // and colsum(dK) = sum_q rowsum(dS)[q] Q[q, :], so the row sums, written as two extra key columns (126, 127: one per
+            // column half; L <= 96 leaves them free), make the dV / dK MMAs deliver the column sums in their rows 126 / 127.
+            if (want_bsum && row < RPq) {
+                const uint32_t off = U + swz16(row, 7) + (uint32_t)(6 + half) * 2u;
+                *reinterpret_cast<__nv_bfloat16*>(sm + L.pd + off) = __float2bfloat16_rn(rs_p.x + rs_p.y);      // 0 for rows past the sequence
+                *reinterpret_cast<__nv_bfloat16*>(sm + L.ds + off) = __float2bfloat16_rn(rs_s.x + rs_s.y);
             }
         }
         fence_async_smem();
@@ -1009,7 +1047,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                     *reinterpret_cast<uint4*>(sm + unit + swz16(row, half * 4 + g4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
             }
-            if (want_bsum) {
+            if (want_bsum && which == 2) {
                 if (row >= Lr) {        // rows past the sequence: not part of the tensor
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = 0.f;
@@ -1032,6 +1070,18 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             stage_chunk(64, (uint32_t)L.pd, Lk, 1);
         }
         if (q * 32 < Lq) stage_chunk(128, uq, Lq, 2);
+        if (want_bsum && q == 3) {         // rows 126 / 127 of dV and dK: the column sums (two partial sums each)
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                float v[32];
+                tmem_ld32(trow + which * 64 + half * 32, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = v[e] + __shfl_down_sync(0xffffffffu, v[e], 1);
+                    if (lane == 30) csum[which * 64 + half * 32 + e] = x;       // this warp owns these slots
+                }
+            }
+        }
         fence_async_smem();
         tcgen05_fence_before();
         __syncthreads();
