@@ -833,12 +833,16 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
 
 struct BwdPersistLayout {
     // units of U bytes: dS block 0 / 1 (the next tile's saved O / V are parked there until the softmax pass overwrites them), dO,
-    // two (Q, K) pairs, Pd block 0 / 1.  Staging of the results: dV over this tile's K, dK over Pd block 0, dQ over this tile's Q.
-    int U, ds, dO, q0, k0, ps, pd, bits, red, csum, bars, total;      // pair x: Q at q0 + x*ps, K at k0 + x*ps
+    // the (Q, K) units, Pd block 0 / 1.  Staging of the results: dV over this tile's K, dK over Pd block 0, dQ over this tile's Q.
+    // L <= 96: two (Q, K) pairs (nine units; the next tile's pair is loaded a whole tile ahead); 96 < L <= 112: nine units no
+    // longer fit twice per SM, so one pair (seven units), reloaded as soon as this tile's dQ / dV boxes have left it.
+    int U, ds, dO, q0, k0, ps, pd, bits, red, csum, bars, total;      // pair x: Q at q0 + x*ps, K at k0 + x*ps (ps = 0: one pair)
     __host__ __device__ BwdPersistLayout(int RP) {
         U = RP * 128;
-        ds = 0; dO = 2 * U; q0 = 3 * U; k0 = 5 * U; ps = U; pd = 7 * U;
-        bits = 9 * U; red = bits + 2048; csum = red + 1024; bars = csum + 768; total = bars + 128;
+        ds = 0; dO = 2 * U;
+        if (RP <= 96) { q0 = 3 * U; k0 = 5 * U; ps = U; pd = 7 * U; bits = 9 * U; }
+        else          { q0 = 3 * U; k0 = 4 * U; ps = 0; pd = 5 * U; bits = 7 * U; }
+        red = bits + 2048; csum = red + 1024; bars = csum + 768; total = bars + 128;
         if (total < q0 + ps + 16384) total = q0 + ps + 16384;          // UMMA A operands span 128 rows from their base
         total += 1024;
     }
@@ -870,6 +874,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int first = (int)((long long)blockIdx.x * ntiles / gridDim.x), last = (int)((long long)(blockIdx.x + 1) * ntiles / gridDim.x);
     const int n = last - first;
     const uint32_t qk_bytes = (uint32_t)(RPq + NS) * 128u, in_bytes = (uint32_t)(NS + 2 * RPq) * 128u;
+    const bool dbl = L.ps != 0;                       // two (Q, K) pairs
     if (t < 192) csum[t] = 0.f;
     if (t == 0 && n > 0) {
         for (int i = 0; i < 5; ++i) mbar_init(bars + 8 * i, 1);
@@ -882,7 +887,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         tma_load_2d(base + L.ds + U, &tmV, h0 * 64, b0 * Lk, bar_in);
         tma_load_2d(base + L.dO, &tmDO, h0 * 64, b0 * Lq, bar_in);
         tma_load_2d(base + L.ds, &tmO, h0 * 64, b0 * Lq, bar_in);
-        if (n > 1) {
+        if (dbl && n > 1) {
             const int b1 = (first + 1) / p.H, h1 = (first + 1) % p.H;
             mbar_expect_tx(bar_qk0 + 8, qk_bytes);
             tma_load_2d(base + (L.q0 + L.ps), &tmQ, h1 * 64, b1 * Lq, bar_qk0 + 8);
@@ -908,8 +913,8 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     int b_prev = -1;
     for (int i = 0; i < n; ++i) {
-        const int tile = first + i, b = tile / p.H, h = tile - b * p.H, pr = i & 1;
-        const uint32_t ph = (uint32_t)(i & 1), phqk = (uint32_t)((i >> 1) & 1);
+        const int tile = first + i, b = tile / p.H, h = tile - b * p.H, pr = dbl ? (i & 1) : 0;
+        const uint32_t ph = (uint32_t)(i & 1), phqk = dbl ? (uint32_t)((i >> 1) & 1) : ph;
         const uint32_t uq = (uint32_t)(L.q0 + pr * L.ps), uk = (uint32_t)(L.k0 + pr * L.ps);
         trace_mark(trace, 0, tile);
         const bool newmask = p.mask != nullptr && b != b_prev;      // CTA-uniform
@@ -935,7 +940,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             // tile i-1's result boxes have left their units (Pd block 0 and the other pair's Q / K units): the softmax pass may
             // write Pd again, and that pair is free for tile i+1's Q / K
             if (i > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            if (i > 0 && i + 1 < n) {
+            if (dbl && i > 0 && i + 1 < n) {
                 const int b1 = (tile + 1) / p.H, h1 = (tile + 1) % p.H;
                 const uint32_t bq = bar_qk0 + 8 * (pr ^ 1);
                 mbar_expect_tx(bq, qk_bytes);
@@ -973,7 +978,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         float2 rs_p = make_float2(0.f, 0.f), rs_s = make_float2(0.f, 0.f);     // this thread's part of rowsum(Pd), rowsum(dS) (even | odd columns)
         if (wlive) {
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
+            for (int ci = 0; ci < 4; ++ci) {
                 const int c16 = half + 2 * ci;
                 if (c16 < nchk) {
                     uint32_t pk[8], dk[8];
@@ -1091,6 +1096,13 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
             tma_store_3d(&tmDK, base + L.pd, h * 64, 0, b);
             tma_store_3d(&tmDQ, base + uq, h * 64, 0, b);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (!dbl && i + 1 < n) {           // one (Q, K) pair: reload it as soon as the dQ / dV boxes have been read out of it
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                const int b1 = (tile + 1) / p.H, h1 = (tile + 1) % p.H;
+                mbar_expect_tx(bar_qk0, qk_bytes);
+                tma_load_2d(base + L.q0, &tmQ, h1 * 64, b1 * Lq, bar_qk0);
+                tma_load_2d(base + L.k0, &tmK, h1 * 64, b1 * Lk, bar_qk0);
+            }
         }
         if (want_bsum && t < 192) {
             float* dst = (t < 64) ? bp.bsum_v : (t < 128) ? bp.bsum_k : bp.bsum_q;
@@ -1179,7 +1191,7 @@ static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
         GCT_TRY(get_tensor_map3(bp.dV, (uint64_t)p.H * 64, (uint64_t)p.Lk, (uint64_t)p.B, (uint64_t)bp.lddv * 2, 64, (uint32_t)RPk, &tdv));
         box_io = 1;
     }
-    if (box_io && g_gct_attn_persist && RPq <= 96 && RPk <= 96) {
+    if (box_io && g_gct_attn_persist && RPq <= 112 && RPk <= 112) {
         static PerDeviceSize pdone_;
         if (!pdone_.cur()) {
             GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdPersistLayout(96).total));

@@ -92,11 +92,12 @@ def test_attention_fwd_bwd(dtype, tol, Lq, Lk, dense):
         assert float((got.float() - want).abs().max()) < 2 * tol * max(1.0, float(want.abs().max()))
 
 
-@pytest.mark.parametrize("Lq,Lk,dense", [(81, 81, False), (80, 80, True), (80, 81, False), (96, 33, False), (20, 96, False), (64, 64, True)])
+@pytest.mark.parametrize("Lq,Lk,dense", [(81, 81, False), (80, 80, True), (80, 81, False), (96, 33, False), (20, 96, False), (64, 64, True),
+                                           (101, 101, False), (100, 100, True), (100, 101, False), (112, 97, False)])
 @pytest.mark.parametrize("sm_budget", [0, 6])
 def test_persistent_attention_matches_one_tile_per_cta(Lq, Lk, dense, sm_budget):
-    """L <= 96 runs the persistent kernels (a CTA walks a range of (batch, head) tiles and prefetches the next tile's operands into
-    dead shared-memory units); per tile they do the arithmetic of the one-tile-per-CTA kernels in the same order, so the outputs
+    """L <= 96 (forward) / L <= 112 (backward, one (Q, K) pair above 96) runs the persistent kernels (a CTA walks a range of
+    (batch, head) tiles and prefetches the next tile's operands into dead shared-memory units); per tile they do the arithmetic of the one-tile-per-CTA kernels in the same order, so the outputs
     must be bit-identical -- with few SMs a CTA walks dozens of tiles (every buffer rotation and barrier phase is exercised)."""
     B, H, d = 67, 8, 512
     torch.manual_seed(Lq * 131 + Lk)
