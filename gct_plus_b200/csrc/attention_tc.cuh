@@ -23,7 +23,7 @@
 #include <math_constants.h>
 
 extern int g_gct_attn_box;
-extern int g_gct_attn_persist;                    // persistent, operand-prefetching kernels for L <= 96 (gct_set_attention_persistent)
+extern int g_gct_attn_persist;                    // persistent, operand-prefetching kernels (gct_set_attention_persistent): bit 0 forward, bit 1 backward
 extern unsigned long long* g_gct_attn_trace;      // debugging hook (gct_set_attention_trace): per-CTA phase timestamps
 
 namespace atc {
@@ -1146,7 +1146,7 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
         GCT_TRY(get_tensor_map3(p.O, (uint64_t)p.H * 64, (uint64_t)p.Lq, (uint64_t)p.B, (uint64_t)p.ldo * 2, 64, (uint32_t)RPq, &to));
         box_store = 1;
     }
-    if (box_store && g_gct_attn_persist && RPq <= 96 && RPk <= 96) {
+    if (box_store && (g_gct_attn_persist & 1) && RPq <= 96 && RPk <= 96) {
         static PerDeviceSize pdone_;
         if (!pdone_.cur()) {
             GCT_CUDA(cudaFuncSetAttribute(attn_fwd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdPersistLayout(96).total));
@@ -1191,7 +1191,7 @@ static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
         GCT_TRY(get_tensor_map3(bp.dV, (uint64_t)p.H * 64, (uint64_t)p.Lk, (uint64_t)p.B, (uint64_t)bp.lddv * 2, 64, (uint32_t)RPk, &tdv));
         box_io = 1;
     }
-    if (box_io && g_gct_attn_persist && RPq <= 112 && RPk <= 112) {
+    if (box_io && (g_gct_attn_persist & 2) && RPq <= 112 && RPk <= 112) {
         static PerDeviceSize pdone_;
         if (!pdone_.cur()) {
             GCT_CUDA(cudaFuncSetAttribute(attn_bwd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdPersistLayout(96).total));

@@ -18,7 +18,7 @@ int g_za_cfg = 3;
 int g_gct_sm_budget = 0;
 int g_gct_res_box = 1;
 int g_gct_attn_box = 1;
-int g_gct_attn_persist = 1;
+int g_gct_attn_persist = 2;      // backward only: the persistent forward is no faster than four one-tile CTAs per SM (profiles/r02_ab_train_attention.txt)
 unsigned long long* g_gct_attn_trace = nullptr;
 int g_gct_rownorm = 0;
 int g_gct_rownorm_res_tma = 1;
@@ -48,7 +48,7 @@ int gct_set_tma_store(int enabled) { g_gct_tma_store = enabled; return GCT_OK; }
 int gct_set_epilogue_warps16(int enabled) { g_gct_ew4 = enabled; return GCT_OK; }
 int gct_set_cta_pair_gemm(int enabled) { g_gct_pair = enabled; return GCT_OK; }
 int gct_set_rownorm_fusion(int mode) { g_gct_rownorm = mode & 3; g_gct_rownorm_res_tma = (mode & 4) ? 0 : 1; return GCT_OK; }
-int gct_set_attention_persistent(int enabled) { g_gct_attn_persist = enabled ? 1 : 0; return GCT_OK; }
+int gct_set_attention_persistent(int mode) { g_gct_attn_persist = mode & 3; return GCT_OK; }
 int gct_set_attention_trace(void* dev_buf) { g_gct_attn_trace = static_cast<unsigned long long*>(dev_buf); return GCT_OK; }
 int gct_set_residual_box(int enabled) { g_gct_res_box = enabled & 1; g_gct_attn_box = (enabled & 2) ? 0 : 1; return GCT_OK; }
 int gct_set_sm_budget(int sms) { g_gct_sm_budget = sms; return GCT_OK; }

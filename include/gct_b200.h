@@ -95,8 +95,9 @@ int gct_set_cta_pair_gemm(int level);               /* persistent GEMM over CTA 
 int gct_set_residual_box(int mode);                /* bit 0 (default 1): persistent GEMM epilogues fetch the fp32 residual / the multiply-by-aux factor as
                                                        TMA boxes into the staging tile; bit 1 set: the tcgen05 attention kernels store O / dQ / dK / dV (and
                                                        load the saved O) per lane instead of as TMA boxes */
-int gct_set_attention_persistent(int enabled);     /* tcgen05 attention for L <= 96: persistent CTAs that prefetch the next (batch, head) tile's
-                                                       operands (default 1); 0 = one tile per CTA */
+int gct_set_attention_persistent(int mode);        /* tcgen05 attention with persistent CTAs that prefetch the next (batch, head) tile's operands:
+                                                       bit 0 the forward (L <= 96), bit 1 the backward (L <= 112); default 2 (the persistent forward measured
+                                                       no faster than four one-tile CTAs per SM), 0 = one tile per CTA */
 int gct_set_attention_trace(void* dev_buf);         /* debugging: when non-null, the tcgen05 attention kernels write per-CTA phase timestamps
                                                        ([B*H][16] u64: globaltimer ns of phases 0..6, %smid, SM clock of phases 0..6) */
 int gct_set_sm_budget(int sms);                     /* persistent GEMMs use at most this many SMs (0 = all): room for a concurrent NCCL kernel */

@@ -20,9 +20,10 @@ tr = FusedTrainer(model, case["mt"])
 batch = bench.make_train_batch(512, case["S"], 3, case["sca"], 1, dev=dev)
 # gct_set_residual_box: bit 0 = GEMM epilogue operands (fp32 residual, multiply-by-aux factor) as TMA boxes; bit 1 set = attention
 # kernels store / load per lane instead of as TMA boxes
-# third field: gct_set_attention_persistent (persistent attention kernels need the attention boxes)
+# third field: gct_set_attention_persistent (bit 0 forward, bit 1 backward; the persistent kernels need the attention boxes)
 settings = [("gemm boxes off, attention boxes off", 2, 0), ("gemm boxes on, attention boxes off", 3, 0),
-            ("gemm boxes on, attention boxes on, one tile per CTA", 1, 0), ("gemm boxes on, attention boxes on, persistent attention", 1, 1)]
+            ("gemm boxes on, attention boxes on, one tile per CTA", 1, 0), ("gemm boxes on, attention boxes on, persistent attention backward", 1, 2),
+            ("gemm boxes on, attention boxes on, persistent attention forward + backward", 1, 3)]
 
 
 def run(n):

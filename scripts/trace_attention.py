@@ -75,7 +75,7 @@ def report(name, fn):
 
 
 for persistent in (0, 1):
-    lib.gct_set_attention_persistent(persistent)
+    lib.gct_set_attention_persistent(3 if persistent else 0)
     trace.zero_()
     report(f"attention forward (no dropout), persistent={persistent}", fwd)
     trace.zero_()
@@ -90,6 +90,7 @@ model = Cvaetf(32, 32, dropout=0.1, nconds=3, use_cond2lat=True, compute_dtype="
 tr = FusedTrainer(model, "pvaetf")
 batch = bench.make_train_batch(512, 78, 3, 0, 1, dev=dev)
 for persistent in (0, 1, 0, 1):
-    lib.gct_set_attention_persistent(persistent)
+    lib.gct_set_attention_persistent(3 if persistent else 0)
     trace.zero_()
     report(f"training step (trace = its last attention backward), persistent={persistent}", lambda: tr.step(batch, 0.5))
+lib.gct_set_attention_persistent(2)

@@ -115,7 +115,7 @@ def test_persistent_attention_matches_one_tile_per_cta(Lq, Lk, dense, sm_budget)
     lib = L.lib()
 
     def run(persistent):
-        lib.gct_set_attention_persistent(persistent)
+        lib.gct_set_attention_persistent(3 if persistent else 0)
         lib.gct_set_sm_budget(sm_budget if persistent else 0)
         out = torch.zeros(B, Lq, d, device=DEV, dtype=torch.bfloat16)
         lse = torch.zeros(B, H, Lq, device=DEV)
@@ -128,7 +128,7 @@ def test_persistent_attention_matches_one_tile_per_cta(Lq, Lk, dense, sm_budget)
                                           L.ptr(dq), d, L.ptr(dk), d, L.ptr(dv), d, B, H, Lq, Lk, 1, L.stream_ptr()))
             torch.cuda.synchronize()
         finally:
-            lib.gct_set_attention_persistent(1)
+            lib.gct_set_attention_persistent(2)
             lib.gct_set_sm_budget(0)
         return out, lse, probs, dq, dk, dv
 
