@@ -195,7 +195,9 @@ attn_bwd_kernel(AttnBwdParams bp) {
                 if (j < Lk) {
                     float sc = s[jj] * p.scale;
                     if (mrow && mrow[j] == 0) sc = -1e9f;
-                    pr = expf(sc - lse);
+                    // a row without one visible key: every score is the fill value, softmax is uniform -- and lse = -1e9 + log(Lk)
+                    // has lost the log(Lk) to fp32 rounding, so exp(sc - lse) would be 1
+                    pr = (lse <= -5e8f) ? 1.f / (float)Lk : expf(sc - lse);
                     pd[jj] = drop_apply(p.drop, drow + j, pr);          // dropped probability used in PV
                     dp[jj] = drop_apply(p.drop, drow + j, dp[jj]);      // gradient through the same mask
                     Dsum += pr * dp[jj];
@@ -208,7 +210,8 @@ attn_bwd_kernel(AttnBwdParams bp) {
             if (jj < nj) {
                 const int j = jj * 32 + lane;
                 if (j < Lk) {
-                    const float ds = s[jj] * (dp[jj] - Dsum);
+                    float ds = s[jj] * (dp[jj] - Dsum);
+                    if (lse <= -5e8f && mrow && mrow[j] == 0) ds = 0.f;     // masked_fill passes no gradient to a masked score
                     dSs[(size_t)i * Lk + j] = ds;
                     Pds[(size_t)i * Lk + j] = pd[jj];
                     s[jj] = ds;

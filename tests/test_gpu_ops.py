@@ -144,6 +144,42 @@ def test_persistent_attention_matches_one_tile_per_cta(Lq, Lk, dense, sm_budget)
         assert float((g.float() - w).abs().max()) < 4e-2 * max(1.0, float(w.abs().max()))
 
 
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("Lq,Lk", [(9, 21), (40, 81)])
+def test_attention_row_without_a_visible_key(dtype, tol, Lq, Lk):
+    """The reference fills masked scores with -1e9 (Model/sublayers.py:33-35): a query whose keys are ALL masked gets the uniform
+    distribution over the Lk keys, its value gradient is dO / Lk and no gradient reaches q / k.  Never happens with valid batches
+    (the first key is <sos> or a condition row); the kernels follow the reference anyway."""
+    B, H, d = 3, 2, 128
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    torch.manual_seed(Lq + Lk)
+    q, dO = (torch.randn(B, Lq, d, device=DEV).to(tdt) for _ in range(2))
+    k, v = (torch.randn(B, Lk, d, device=DEV).to(tdt) for _ in range(2))
+    lens = torch.tensor([Lk, 0, max(1, Lk - 3)], device=DEV)
+    mask = (torch.arange(Lk, device=DEV)[None, :] < lens[:, None]).view(B, 1, Lk)
+    m8 = mask.to(torch.uint8).contiguous()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref, pref = _attn_ref(qf, kf, vf, mask)
+    ref.backward(dO.float())
+    out = torch.empty(B, Lq, d, device=DEV, dtype=tdt)
+    lse = torch.empty(B, H, Lq, device=DEV)
+    probs = torch.empty(B, H, Lq, Lk, device=DEV)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dt = 0 if dtype == "fp32" else 1
+    lib = L.lib()
+    L.check(lib.gct_attention_fwd(L.ptr(q), d, L.ptr(k), d, L.ptr(v), d, L.ptr(m8), Lk, 0, L.ptr(out), d, L.ptr(lse), L.ptr(probs), B, H, Lq, Lk,
+                                  dt, L.stream_ptr()))
+    L.check(lib.gct_attention_bwd(L.ptr(q), d, L.ptr(k), d, L.ptr(v), d, L.ptr(m8), Lk, 0, L.ptr(lse), L.ptr(out), d, L.ptr(dO), d, L.ptr(dq), d,
+                                  L.ptr(dk), d, L.ptr(dv), d, B, H, Lq, Lk, dt, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert float((probs[1] - 1.0 / Lk).abs().max()) < 1e-6
+    assert float((out.float() - ref.detach()).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+    assert float((probs - pref.detach()).abs().max()) < tol
+    assert float(dq[1].float().abs().max()) == 0.0 and float(dk[1].float().abs().max()) == 0.0
+    for got, want in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
+        assert float((got.float() - want).abs().max()) < 2 * tol * max(1.0, float(want.abs().max()))
+
+
 def test_masks_match_golden():
     from gct_plus_b200.Model.modules import get_src_mask, get_trg_mask
     m = load_golden("misc")
