@@ -268,6 +268,43 @@ def run_sampling(args, rank, world, dev):
         sampler.z_on_device = False
         public["note"] = ("sampler.sample_smiles(n) exactly as the reference drivers call it (uc_sampling.py:16-23): sample_toklen + sample_z "
                           "inside the timed call; z_on_host draws 30000 x Lz x 128 normals with torch's CPU generator like the reference")
+    # ---- active-row decode (sampler kwarg skip_finished=True; NOT the headline: `value` / `e2e` above decode every row at every
+    # step like the reference's loop).  Same inputs; rows that have emitted <eos> stop costing attention work and are gathered out of
+    # the batch, so the cost follows the sum of the generated lengths instead of rows x steps.  How much that saves depends on
+    # when rows emit <eos>: with these random-init weights ~1 / vocabulary per step.
+    active = None
+    if getattr(args, "active_rows", True) and BATCH >= 4096:
+        sampler.skip_finished = True
+        reps = max(2, min(K, 4))
+        for i in range(2):
+            sampler.decode(zs=dev_in[i][0], ys=ys0, src_mask=dev_in[i][1])
+        barrier(world)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        row_steps = all_steps = 0
+        for i in range(W, W + reps):
+            sampler.decode(zs=dev_in[i][0], ys=ys0, src_mask=dev_in[i][1])
+            row_steps += sampler.last_row_steps
+            all_steps += sampler.last_steps_executed * BATCH
+        a1.record()
+        torch.cuda.synchronize()
+        ams = max_over_ranks(a0.elapsed_time(a1), world, dev)
+        sampler.sample_smiles(BATCH, zs=inputs[0][1], toklen=list(inputs[0][0]))
+        barrier(world)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(W, W + reps):
+            sampler.sample_smiles(BATCH, zs=inputs[i][1], toklen=list(inputs[i][0]))
+        torch.cuda.synchronize()
+        at = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+        sampler.skip_finished = False
+        active = {"value": world * reps * BATCH / (ams / 1e3), "e2e": world * reps * BATCH / (at / 1e3), "unit": "SMILES/s", "calls": reps,
+                  "ms_per_call": ams / reps, "row_steps_fraction": row_steps / max(1, all_steps),
+                  "compact_every": sampler.compact_every,
+                  "note": "opt-in sampler kwarg skip_finished=True: same strings (tests/test_gpu_active_rows.py), rows x steps the step "
+                          "kernels ran on / rows x steps of the plain loop = row_steps_fraction; attention of finished rows inside a "
+                          "chunk is skipped as well"}
     h2d = int(np.mean([z.numel() * 4 + BATCH * z.size(1) + BATCH * 8 for _, z in inputs[W:]]))
     d2h = BATCH * MAX_STRLEN * 2          # int16 token ids
     cfg = sampler.model._cfg()
@@ -276,7 +313,8 @@ def run_sampling(args, rank, world, dev):
     Sm_mean = float(np.mean([z.size(1) for _, z in inputs[W:]]))
     Sm_true = float(np.mean([np.mean(tl) for tl, _ in inputs[W:]]))       # keys actually attended (rows differ in length)
     return dict(value=value, ms_per_step=ms / K, e2e_value=world * K * BATCH / (t_e2e / 1e3), h2d=h2d, d2h=d2h, clocks=ck,
-                launches=launches, sampler=sampler, Sm_mean=Sm_mean, Sm_true=Sm_true, decode_steps=n_steps_run / K, public=public)
+                launches=launches, sampler=sampler, Sm_mean=Sm_mean, Sm_true=Sm_true, decode_steps=n_steps_run / K, public=public,
+                active=active)
 
 
 def make_train_batch(B, S, nc, scaffold, seed, dev=None, pinned=False):
@@ -714,7 +752,7 @@ def main():
         big = BATCH
         BATCH = 512
         a2 = argparse.Namespace(**vars(args))
-        a2.steps, a2.warmup, a2.public_call = 12, 3, False
+        a2.steps, a2.warmup, a2.public_call, a2.active_rows = 12, 3, False, False
         r = run_sampling(a2, rank, world, dev)
         b512 = {"batch": 512, "value": r["value"], "unit": "SMILES/s", "ms_per_step": r["ms_per_step"], "steps": 12,
                 "e2e": r["e2e_value"], "note": "the reference driver's default -batch_size (uc_sampling.py:16-23)"}
@@ -749,7 +787,7 @@ def main():
                 "config": base_config(BATCH, world, f"working set (KV cache {0.9 * BATCH / 512:.1f} GB per batch) larger than L2, no flush needed"),
                 "e2e": {"value": s["e2e_value"], "unit": "SMILES/s", "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"],
                         "call": "sampler.sample_smiles(n, zs=<pinned host latents>, toklen=<host list>) -> Python strings"},
-                "e2e_public_call": s["public"],
+                "e2e_public_call": s["public"], "active_row_decode": s["active"],
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
                 "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -85,6 +85,17 @@ class Sampling:
         self.z_on_device = kwargs.get('z_on_device', False)
         self.host_z_exact = kwargs.get('host_z_exact', False)
         self.decode_streams = kwargs.get('decode_streams', None)   # row groups decoded on concurrent streams (None = by batch size)
+        # Active-row decode (opt-in; the reference re-runs EVERY row until the last one has emitted <eos>, :144-183): rows that
+        # have emitted <eos> append <pad> from then on, their attention work is skipped, and -- for calls of at least
+        # compact_min_rows rows -- every compact_every steps the rows still running are gathered through a row map so that the
+        # GEMMs / Norms shrink with them (batch rounded up to compact_quantum rows).  The strings sample_smiles returns are
+        # unchanged (id_to_smi stops at the first <eos>); decode()'s ys differs from the reference's AFTER each row's <eos>.
+        self.skip_finished = kwargs.get('skip_finished', False)
+        self.compact_every = kwargs.get('compact_every', 8)
+        self.compact_quantum = kwargs.get('compact_quantum', None)      # None: n / 32 rounded up to a multiple of 256
+        self.compact_min_rows = kwargs.get('compact_min_rows', 4096)
+        self.last_row_steps = 0          # sum over the steps run of the rows the step kernels worked on
+        self.last_steps_executed = 0     # steps the device ran (whole chunks), >= last_decode_steps
         self._group_streams = []
         self._host_s_per_row = 0.0
         self._side_stream = None
@@ -283,7 +294,9 @@ class Sampling:
         G = self._row_groups(n, probe)
         bounds = [(n * g // G, n * (g + 1) // G) for g in range(G)]
 
-        key = (n, Lzp, max_len, t0, greedy, nc, model.compute_dtype, G)
+        skip = bool(self.skip_finished) and not probe
+        compacting = skip and G == 1 and n >= self.compact_min_rows
+        key = (n, Lzp, max_len, t0, greedy, nc, model.compute_dtype, G, skip)
         st = self._static.get(key)
         if st is None:
             st = dict(zs=torch.zeros((n, Lzp, self.latent_dim), device=dev, dtype=torch.float32),
@@ -306,6 +319,8 @@ class Sampling:
             st['mask'][:, Lz:].zero_()
         st['mask'][:, :Lz].copy_(src_mask.reshape(n, Lz).to(torch.uint8), non_blocking=True)
         st['ys'][:, :t0].copy_(ys, non_blocking=True)
+        if skip:
+            st['ys'][:, t0:].fill_(int(self.pad_id))      # rows gathered away after their <eos> are not written any more
         if nc > 0:
             st['dconds'].copy_(dconds.float(), non_blocking=True)
         if not greedy:
@@ -330,7 +345,7 @@ class Sampling:
                                     dconds=st['dconds'][lo:].data_ptr() if nc > 0 else None,
                                     uniforms=None if greedy else st['uni'][g].data_ptr(), ys=st['ys'][lo:].data_ptr(),
                                     status=st['status'][g].data_ptr(), forced=L._p(forced), probs_out=L._p(probs_out),
-                                    logits_out=L._p(logits_out)))
+                                    logits_out=L._p(logits_out), skip_done=int(skip), n_active=0, rowmap=None))
         if G > 1 and len(self._group_streams) < G - 1:
             self._group_streams += [torch.cuda.Stream(device=dev) for _ in range(G - 1 - len(self._group_streams))]
 
@@ -359,7 +374,9 @@ class Sampling:
         gkey = key + (wptrs, w.params_f32, w.params_bf16, self.sync_every)
         for gk in [gk for gk in self._graphs if gk[:len(key)] == key and gk[len(key)] != wptrs]:
             del self._graphs[gk]                # a grow-only workspace was reallocated: those graphs point at freed memory
-        use_graph = self.use_cuda_graph and not probe      # probe buffers are per call: not baked into a graph
+        # probe buffers are per call: not baked into a graph; a compacting decode changes its batch between chunks and has
+        # >= compact_min_rows rows per step kernel, so the host stays ahead of the device without graphs
+        use_graph = self.use_cuda_graph and not probe and not compacting
         graphs = self._graphs.get(gkey) if use_graph else None
         if use_graph and graphs is None and st.get('warm'):
             # second call with this shape: capture begin + every chunk once, replay from now on
@@ -383,11 +400,39 @@ class Sampling:
             graphs[0].replay()
         else:
             begin()
+        row_steps = executed = 0
+        if compacting:
+            q = self.compact_quantum or max(256, -(-n // (32 * 256)) * 256)
+            rowmap = st.get('rowmap')
+            if rowmap is None:
+                rowmap = st['rowmap'] = torch.empty(n, device=dev, dtype=torch.int32)
+            dec, ws, rows = decs[0], wss[0], n
+            chunks = []                                   # the loop below replaces the chunked one
+            s0 = 0
+            while s0 < steps:
+                s1 = min(steps, s0 + max(1, int(self.compact_every)))
+                run(s0, s1)
+                row_steps += rows * (s1 - s0)
+                executed += s1 - s0
+                if idle_work is not None:
+                    idle_work.step()
+                s0 = s1
+                if s0 < steps:
+                    if all_done():
+                        break
+                    n_act = n - int(st['status_host'][0, 0])
+                    want = min(n, max(q, -(-n_act // q) * q))
+                    if want < rows:
+                        L.check(lib.gct_decode_compact(C.byref(cfg), C.byref(dec), want, L.ptr(rowmap), L.ptr(ws), ws.numel(),
+                                                       L.stream_ptr()), "gct_decode_compact")
+                        dec.n_active, dec.rowmap, rows = want, rowmap.data_ptr(), want
         for ci, (s0, s1) in enumerate(chunks):
             if graphs is not None:
                 graphs[1 + ci].replay()
             else:
                 run(s0, s1)
+            row_steps += n * (s1 - s0)
+            executed += s1 - s0
             if idle_work is not None:
                 idle_work.step()          # bounded slice of host work while the GPU runs this chunk
             if s1 < steps and all_done():
@@ -395,6 +440,9 @@ class Sampling:
         if all_done():
             steps_run = int(st['status_host'][:, 1].max()) + 1      # the step at which the LAST group completed
         self.last_decode_steps = steps_run
+        self.last_steps_executed = executed
+        self.last_row_steps = row_steps           # rows x steps the step kernels ran on (chunks run to their end: >= n * steps_run
+                                                  # for a plain decode that stopped early inside a chunk)
         return st['ys'][:, :t0 + steps_run].clone()
 
     def teacher_forced_logits(self, zs, ys_full, src_mask, dconds=None, t0=1, want_probs=False):

@@ -41,7 +41,8 @@ class GctIO(C.Structure):
 class GctDecode(C.Structure):
     _fields_ = [("B", i32), ("Lz", i32), ("max_len", i32), ("prefix_len", i32), ("greedy", i32), ("eos_id", i32),
                 ("seed", C.c_uint32), ("zs", vp), ("src_mask", vp), ("dconds", vp), ("uniforms", vp), ("ys", vp),
-                ("status", vp), ("forced", vp), ("probs_out", vp), ("logits_out", vp)]
+                ("status", vp), ("forced", vp), ("probs_out", vp), ("logits_out", vp), ("skip_done", i32), ("n_active", i32),
+                ("rowmap", vp)]
 
 
 class GctBucket(C.Structure):
@@ -99,6 +100,7 @@ _PROTOS = {
     "gct_noam_lr": (C.c_double, [i64, C.c_int, i64]),
     "gct_decode_workspace_bytes": (sz, [C.POINTER(GctConfig), C.c_int, C.c_int, C.c_int]),
     "gct_decode_begin": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), vp, sz, vp]),
+    "gct_decode_compact": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctDecode), C.c_int, vp, vp, sz, vp]),
     "gct_decode_steps": (C.c_int, [C.POINTER(GctConfig), C.POINTER(GctWeights), C.POINTER(GctDecode), C.c_int, C.c_int,
                                    vp, sz, vp]),
     "gct_collate": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp,

@@ -15,6 +15,10 @@ struct DecAttnParams {
     const uint8_t* key_valid; int kv_stride; // [B, kv_stride] 1 = attend (0 -> score -1e9)
     void* out; int ldo;                      // [B, ldo]
     int H; float scale;
+    // active-row decode (gct_decode_t.rowmap / skip_done): q / knew / vnew / out are indexed by the COMPACT row i, the caches and
+    // key_valid by the physical row rowmap[i]; a row whose `done` flag is set is not touched at all (no cache append, out stale)
+    const int* rowmap = nullptr;
+    const uint8_t* done = nullptr;
 };
 
 // One CTA per batch row: a producer warp streams that row's K and V cache slabs (contiguous [keys][H*64]) through a
@@ -60,8 +64,12 @@ decode_attn_kernel(DecAttnParams p, int B) {
     pdl_launch_dependents();
     const int nc = p.n_cached;
     const int nall = nc + (p.knew ? 1 : 0);
+    auto phys = [&](int r) { return p.rowmap ? p.rowmap[b0 + r] : b0 + r; };
+    auto skipped = [&](int r) { return p.done != nullptr && p.done[phys(r)] != 0; };      // uniform over the CTA
+    if (DA_ROWS == 1 && skipped(0)) return;
     for (int r = 0; r < nrows_cta; ++r) {
-        const uint8_t* valid = p.key_valid + (size_t)(b0 + r) * p.kv_stride;
+        if (DA_ROWS > 1 && skipped(r)) continue;
+        const uint8_t* valid = p.key_valid + (size_t)phys(r) * p.kv_stride;
         for (int j = threadIdx.x; j < nall; j += blockDim.x) {
             const uint8_t v = valid[j];
             valid_s[r][j] = v;
@@ -78,9 +86,10 @@ decode_attn_kernel(DecAttnParams p, int B) {
         if (lane == 0) {
             int g = 0;
             for (int r = 0; r < nrows_cta; ++r) {
+                if (DA_ROWS > 1 && skipped(r)) continue;
                 const int nrow = row_keys(r);
-                const T* kslab = reinterpret_cast<const T*>(p.kcache) + (size_t)(b0 + r) * p.cache_bstride;
-                const T* vslab = reinterpret_cast<const T*>(p.vcache) + (size_t)(b0 + r) * p.cache_bstride;
+                const T* kslab = reinterpret_cast<const T*>(p.kcache) + (size_t)phys(r) * p.cache_bstride;
+                const T* vslab = reinterpret_cast<const T*>(p.vcache) + (size_t)phys(r) * p.cache_bstride;
                 for (int c = 0; c * DA_CHUNK < nrow; ++c, ++g) {
                     const int s = g % DA_NS;
                     tc::mbar_wait(bar0 + 8 * (DA_NS + s), ((g / DA_NS) & 1) ^ 1);
@@ -101,12 +110,13 @@ decode_attn_kernel(DecAttnParams p, int B) {
     const unsigned gmask = 0xFFu << (gq * 8);
     int g = 0;
     for (int r = 0; r < nrows_cta; ++r) {
+        if (DA_ROWS > 1 && skipped(r)) continue;
         const int b = b0 + r;
         const int nrow = row_keys(r);
         const int nchunks = (nrow + DA_CHUNK - 1) / DA_CHUNK;
         const uint8_t* vld = valid_s[r];
-        T* kslab = reinterpret_cast<T*>(p.kcache) + (size_t)b * p.cache_bstride;
-        T* vslab = reinterpret_cast<T*>(p.vcache) + (size_t)b * p.cache_bstride;
+        T* kslab = reinterpret_cast<T*>(p.kcache) + (size_t)phys(r) * p.cache_bstride;
+        T* vslab = reinterpret_cast<T*>(p.vcache) + (size_t)phys(r) * p.cache_bstride;
         const f8 q = ld8(reinterpret_cast<const T*>(p.q) + (size_t)b * p.ldq + col);
         f8 kn, vn;
         if (p.knew) {
@@ -257,15 +267,18 @@ static int launch_decode_attn(const DecAttnParams& p, int B, cudaStream_t st) {
 // x[b,:] = table[ys[b,pos]]*sqrt(d) + pe[pos + pe_off]; key_valid[b,pos] = tok != pad
 __global__ void decode_embed_kernel(const int64_t* __restrict__ ys, int ys_stride, int pos, const float* __restrict__ table,
                                     int vocab, const float* __restrict__ pe, int pe_off, int d, float scale, int pad_id,
-                                    float* __restrict__ x, uint8_t* __restrict__ key_valid, int kv_stride, int B) {
+                                    float* __restrict__ x, uint8_t* __restrict__ key_valid, int kv_stride, int B,
+                                    const int* __restrict__ rowmap) {
     // one warp per batch row, four rows per CTA (a CTA per row left the 30 000-row launch bound by CTA issue, not by its 61 MB)
+    // rowmap (active-row decode): x is written at the compact row b, ys / key_valid belong to the physical row rowmap[b]
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     pdl_wait();
     pdl_launch_dependents();
     if (b >= B) return;
-    long long t = ys[(size_t)b * ys_stride + pos];
-    if (lane == 0) key_valid[(size_t)b * kv_stride + pos] = (t != pad_id);
+    const int bp = rowmap ? rowmap[b] : b;
+    long long t = ys[(size_t)bp * ys_stride + pos];
+    if (lane == 0) key_valid[(size_t)bp * kv_stride + pos] = (t != pad_id);
     if (t < 0 || t >= vocab) t = 0;
     const float* e = table + (size_t)t * d;
     const float* per = pe + (size_t)(pos + pe_off) * d;
@@ -288,6 +301,9 @@ struct SampleParams {
     uint8_t* done; int* n_done; int* first_all_done; int B;
     float* probs_out;                             // optional [B, V]
     float* logits_out;                            // optional [B, V]
+    // active-row decode: logits rows are COMPACT (B of them); ys / done / uniforms / the counter hash / the all-done count use
+    // the physical row rowmap[b] of Bphys; with skip_done a finished row appends pad_id and nothing else happens to it
+    const int* rowmap; int Bphys; int skip_done; int pad_id;
 };
 
 // one warp per row, V <= 128.  Matches the reference's order of operations: softmax over the
@@ -298,6 +314,11 @@ __global__ void decode_sample_kernel(SampleParams p) {
     pdl_wait();
     pdl_launch_dependents();
     if (b >= p.B) return;
+    const int bp = p.rowmap ? p.rowmap[b] : b;
+    if (p.skip_done && p.done[bp]) {
+        if (lane == 0) p.ys[(size_t)bp * p.ys_stride + p.pos + 1] = p.pad_id;
+        return;
+    }
     const float* lr = p.logits + (size_t)b * p.ld;
     float v[4];
     float mx = -INFINITY;
@@ -320,7 +341,7 @@ __global__ void decode_sample_kernel(SampleParams p) {
     }
     int tok;
     if (p.forced) {
-        tok = (int)p.forced[(size_t)b * p.forced_stride];
+        tok = (int)p.forced[(size_t)bp * p.forced_stride];
     } else if (p.greedy) {
         float best = -1.f; int bi = 0;
 #pragma unroll
@@ -337,8 +358,8 @@ __global__ void decode_sample_kernel(SampleParams p) {
         tok = bi;
     } else {
         float u;
-        if (p.uniforms) u = p.uniforms[b];
-        else u = (float)(mix32(p.seed ^ mix32((uint32_t)p.step * 0x9e3779b9U + (uint32_t)b)) >> 8) * (1.0f / 16777216.0f);
+        if (p.uniforms) u = p.uniforms[bp];
+        else u = (float)(mix32(p.seed ^ mix32((uint32_t)p.step * 0x9e3779b9U + (uint32_t)bp)) >> 8) * (1.0f / 16777216.0f);
         // sequential cumulative sum in index order (same order as a CPU cumsum); threshold u*total
         // (only the 32-column blocks the vocabulary reaches: V = 27-32 for MOSES is one block)
         const int nblk = (p.V + 31) >> 5;
@@ -368,11 +389,43 @@ __global__ void decode_sample_kernel(SampleParams p) {
         tok = pick;
     }
     if (lane == 0) {
-        p.ys[(size_t)b * p.ys_stride + p.pos + 1] = tok;
-        if (!p.forced && tok == p.eos_id && !p.done[b]) {
-            p.done[b] = 1;
+        p.ys[(size_t)bp * p.ys_stride + p.pos + 1] = tok;
+        if (!p.forced && tok == p.eos_id && !p.done[bp]) {
+            p.done[bp] = 1;
             const int n = atomicAdd(p.n_done, 1) + 1;
-            if (n == p.B) *p.first_all_done = p.step;
+            if (n == p.Bphys) *p.first_all_done = p.step;
         }
     }
+}
+
+// Active-row decode: rowmap[0 .. n_active) = the rows whose `done` flag is clear, ascending; rowmap[n_active .. n_out) = the
+// first finished row (a finished row costs the attention kernels nothing and appends pad_id), so that the batch the step
+// kernels see can be rounded up to a size the host chooses.  One CTA: B <= a few 10^5 flags, once per chunk of steps.
+__global__ void __launch_bounds__(1024) decode_compact_kernel(const uint8_t* __restrict__ done, int B, int* __restrict__ rowmap, int n_out) {
+    __shared__ int wsum[32];
+    __shared__ int base_s, first_done_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { base_s = 0; first_done_s = B; }
+    __syncthreads();
+    for (int i0 = 0; i0 < B; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const bool in = i < B;
+        const bool act = in && done[i] == 0;
+        if (in && !act) atomicMin(&first_done_s, i);
+        const uint32_t bal = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        if (act) {
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            if (slot < n_out) rowmap[slot] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += wsum[w]; base_s += t; }
+        __syncthreads();
+    }
+    const int n_act = base_s;
+    const int filler = first_done_s < B ? first_done_s : 0;
+    for (int i = n_act + threadIdx.x; i < n_out; i += 1024) rowmap[i] = filler;
 }

@@ -59,6 +59,9 @@ struct ZAttnParams {
     const bf16* kvc; int nc;            // condition rows: [B][nc][2*64H] = (Wk u_i | Wv u_i), or nc = 0
     bf16* out; int ldo;                 // [B, ldo]: columns [0, LAT*H) zbar in (dim, head) order: a*H + h; then 64H columns ac
     int H; int B;
+    // active-row decode: qz / out rows are COMPACT, z / key_valid / kvc belong to the physical row rowmap[b]; finished rows return
+    const int* rowmap = nullptr;
+    const uint8_t* done = nullptr;
 };
 
 template <int LAT, int MINB>
@@ -72,9 +75,11 @@ decode_zattn_kernel(ZAttnParams p) {
     pdl_wait();
     pdl_launch_dependents();
     if (b >= p.B) return;
+    const int bp = p.rowmap ? p.rowmap[b] : b;
+    if (p.done != nullptr && p.done[bp] != 0) return;
     const int H = p.H, d = 64 * H, nkeys = p.n_keys;
-    const bf16* zg = p.z + (size_t)b * p.z_bstride + t * 8;
-    const uint8_t* valid = p.key_valid + (size_t)b * p.kv_stride;
+    const bf16* zg = p.z + (size_t)bp * p.z_bstride + t * 8;
+    const uint8_t* valid = p.key_valid + (size_t)bp * p.kv_stride;
     const bf16* qrow = p.qz + (size_t)b * p.ldq;
 
     // The first TWO 16-key chunks are requested before anything else (their addresses depend on nothing but n_keys): with the
@@ -111,7 +116,7 @@ decode_zattn_kernel(ZAttnParams p) {
     float sc[2][MAXC];                          // log2-scaled score of condition row i for the head of piece j, replicated over its 8 lanes
     const int npieces = 8 * H;                  // 16-byte pieces per 64H row
     if (p.nc > 0) {
-        const bf16* kv = p.kvc + (size_t)b * p.nc * 2 * d;
+        const bf16* kv = p.kvc + (size_t)bp * p.nc * 2 * d;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int pc = lane + 32 * j;
@@ -242,7 +247,7 @@ decode_zattn_kernel(ZAttnParams p) {
     }
     // ---- condition values: ac[head of the piece][8 dims] = sum_i p_i (Wv u_i)
     if (p.nc > 0) {
-        const bf16* kv = p.kvc + (size_t)b * p.nc * 2 * d + d;
+        const bf16* kv = p.kvc + (size_t)bp * p.nc * 2 * d + d;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int pc = lane + 32 * j;

@@ -512,6 +512,10 @@ static int decode_steps_impl(const gct_config_t* cfg, const gct_weights_t* w, co
     DecodeWs<T> W;
     W.carve(*cfg, d->B, d->Lz, d->max_len, ws);
     GCT_REQUIRE(W.bytes <= ws_bytes, "decode: workspace too small");
+    GCT_REQUIRE(d->n_active >= 0 && d->n_active <= d->B && (d->n_active == 0 || d->rowmap || d->n_active == d->B),
+                "decode: n_active %d needs a rowmap and must not exceed B = %d", d->n_active, d->B);
+    GCT_REQUIRE(!(d->skip_done || d->rowmap) || !(d->forced || d->probs_out || d->logits_out),
+                "decode: active-row decode cannot be combined with forced tokens / per-step probes");
     for (int s = s0; s < s1; ++s) {
         const int pos = d->prefix_len - 1 + s;
         GCT_REQUIRE(pos + 1 < d->max_len, "decode: step %d overflows ys (max_len %d)", s, d->max_len);
@@ -531,6 +535,19 @@ int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_
     GCT_REQUIRE(cfg && w && d && workspace, "decode_steps: null argument");
     return cfg->dtype == GCT_DTYPE_F32 ? decode_steps_impl<float>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream)
                                        : decode_steps_impl<bf16>(cfg, w, d, step_begin, step_end, workspace, workspace_bytes, stream);
+}
+int gct_decode_compact(const gct_config_t* cfg, const gct_decode_t* d, int n_out, int32_t* rowmap_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    GCT_REQUIRE(cfg && d && rowmap_out && workspace, "decode_compact: null argument");
+    GCT_REQUIRE(n_out >= 1 && n_out <= d->B, "decode_compact: n_out %d outside [1, %d]", n_out, d->B);
+    uint8_t* done;
+    size_t bytes;
+    if (cfg->dtype == GCT_DTYPE_F32) { DecodeWs<float> W; W.carve(*cfg, d->B, d->Lz, d->max_len, workspace); done = W.done; bytes = W.bytes; }
+    else { DecodeWs<bf16> W; W.carve(*cfg, d->B, d->Lz, d->max_len, workspace); done = W.done; bytes = W.bytes; }
+    GCT_REQUIRE(bytes <= workspace_bytes, "decode_compact: workspace too small");
+    decode_compact_kernel<<<1, 1024, 0, ST(stream)>>>(done, d->B, rowmap_out, n_out);
+    GCT_LAUNCH_CHECK();
+    return GCT_OK;
 }
 int gct_decode_launches_per_step(const gct_config_t* cfg) { return 1 + cfg->n_layers * 11 + 3; }
 int gct_decode_launches_per_step_at(const gct_config_t* cfg, int B) {

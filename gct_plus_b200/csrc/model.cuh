@@ -900,19 +900,22 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
 // one position: reads ys[:, pos], writes ys[:, pos+1] (sampled, or left untouched while inside the prefix)
 template <typename T>
 static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int pos, int step, bool sample) {
-    const int d = m.d, dff = m.dff, N = m.N, B = W.B, Sm = W.Sm, Lmax = W.Lmax;
+    // B = rows the step kernels run on (active-row decode: the compact rows of D.rowmap), Bp = rows of the caches / ys / uniforms
+    const int d = m.d, dff = m.dff, N = m.N, Bp = W.B, B = D.n_active > 0 ? D.n_active : W.B, Sm = W.Sm, Lmax = W.Lmax;
+    const int* rowmap = D.n_active > 0 ? D.rowmap : nullptr;
+    const uint8_t* skip = (D.skip_done && sample) ? W.done : nullptr;
     cudaStream_t st = m.st;
     GCT_CUDA(launch_k(decode_embed_kernel, dim3(cdiv(B, 4)), dim3(128), 0, st, true, (const int64_t*)D.ys, D.max_len, pos, m.P(GCT_SLOT_DEC_EMB),
-                      m.c.trg_vocab, m.P(GCT_SLOT_DEC_PE), 0, d, sqrtf((float)d), m.c.pad_id, W.x, W.key_valid, Lmax, B));
+                      m.c.trg_vocab, m.P(GCT_SLOT_DEC_PE), 0, d, sqrtf((float)d), m.c.pad_id, W.x, W.key_valid, Lmax, B, rowmap));
     for (int l = 0; l < N; ++l) {
         GCT_TRY(m.norm_fwd(W.x, m.dec_slot(l, D_N1A), m.dec_slot(l, D_N1B), W.xn, nullptr, B));
         GCT_TRY(m.linear_T(W.xn, B, d, m.dec_slot(l, D_QKV_W), m.dec_slot(l, D_QKV_B), 3 * d, W.qkv));
         {
             DecAttnParams p;
             p.q = W.qkv; p.ldq = 3 * d; p.knew = W.qkv + d; p.vnew = W.qkv + 2 * d; p.ldnew = 3 * d;
-            p.kcache = W.kc + (size_t)l * B * Lmax * d; p.vcache = W.vc + (size_t)l * B * Lmax * d;
+            p.kcache = W.kc + (size_t)l * Bp * Lmax * d; p.vcache = W.vc + (size_t)l * Bp * Lmax * d;
             p.cache_bstride = (long long)Lmax * d; p.pitch = d; p.n_cached = pos; p.key_valid = W.key_valid; p.kv_stride = Lmax;
-            p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
+            p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f; p.rowmap = rowmap; p.done = skip;
             GCT_TRY(launch_decode_attn<T>(p, B, st));
         }
         GCT_TRY(m.linear_res_norm(W.att, B, d, m.WT(m.dec_slot(l, D_O1_W)), m.P(m.dec_slot(l, D_O1_B)), W.x, W.x, m.site(0),
@@ -927,8 +930,8 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
                 }
                 ZAttnParams zp;
                 zp.qz = W.qz; zp.ldq = KZ; zp.z = W.zlat; zp.z_bstride = (long long)W.Lz * m.lat; zp.key_valid = W.cross_mask + W.nck;
-                zp.kv_stride = Sm; zp.n_keys = W.Lz; zp.kvc = W.nck ? W.kvc + (size_t)l * B * W.nck * 2 * d : nullptr; zp.nc = W.nck;
-                zp.out = W.zbar; zp.ldo = KZ; zp.H = m.H; zp.B = B;
+                zp.kv_stride = Sm; zp.n_keys = W.Lz; zp.kvc = W.nck ? W.kvc + (size_t)l * Bp * W.nck * 2 * d : nullptr; zp.nc = W.nck;
+                zp.out = W.zbar; zp.ldo = KZ; zp.H = m.H; zp.B = B; zp.rowmap = rowmap; zp.done = skip;
                 GCT_TRY(launch_decode_zattn(zp, m.lat, st));
                 GCT_TRY(m.linear_res_norm(W.zbar, B, KZ, W.woz + (size_t)l * d * KZ, W.boz + (size_t)l * d, W.x, W.x, m.site(0),
                                           m.dec_slot(l, D_N3A), m.dec_slot(l, D_N3B), W.xn, nullptr));
@@ -939,9 +942,10 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             {
                 DecAttnParams p;
                 p.q = W.q2; p.ldq = d; p.knew = nullptr; p.vnew = nullptr; p.ldnew = 0;
-                p.kcache = W.kx + (size_t)l * B * Sm * d; p.vcache = W.vx + (size_t)l * B * Sm * d;
+                p.kcache = W.kx + (size_t)l * Bp * Sm * d; p.vcache = W.vx + (size_t)l * Bp * Sm * d;
                 p.cache_bstride = (long long)Sm * d; p.pitch = d; p.n_cached = Sm;
                 p.key_valid = W.cross_mask; p.kv_stride = Sm; p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f;
+                p.rowmap = rowmap; p.done = skip;
                 GCT_TRY(launch_decode_attn<T>(p, B, st));
             }
             GCT_TRY(m.linear_res_norm(W.att, B, d, m.WT(m.dec_slot(l, D_O2_W)), m.P(m.dec_slot(l, D_O2_B)), W.x, W.x, m.site(0),
@@ -951,7 +955,9 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F1_B)), dff); e.flags = EPI_GELU; e.outT = W.hbuf;
             GCT_TRY(m.gemm(W.xn, false, d, m.WT(m.dec_slot(l, D_F1_W)), false, d, B, dff, d, e));
         }
-        if (B <= 1024) {   // x += hbuf W2^T + b2 : in-place accumulate lets the long-K GEMM use split-K (bias from split 0 only)
+        // (chosen by the call's PHYSICAL batch: an active-row decode that shrinks below 1025 rows keeps the residual form, so a row's
+        // arithmetic does not depend on how many other rows are still running)
+        if (Bp <= 1024) {  // x += hbuf W2^T + b2 : in-place accumulate lets the long-K GEMM use split-K (bias from split 0 only)
             Epilogue e = Model<T>::epi(m.P(m.dec_slot(l, D_F2_B)), d); e.out32 = W.x; e.flags = EPI_ACCUM;
             GCT_TRY(m.gemm(W.hbuf, false, dff, m.WT(m.dec_slot(l, D_F2_W)), false, dff, B, d, dff, e, 2));
         } else {           // enough row tiles to fill the machine: residual form, served by the specialised epilogue
@@ -968,10 +974,10 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
     SampleParams sp;
     sp.logits = W.logits; sp.ld = m.c.trg_vocab; sp.V = m.c.trg_vocab; sp.ys = D.ys; sp.ys_stride = D.max_len; sp.pos = pos;
     sp.forced = D.forced ? D.forced + pos + 1 : nullptr; sp.forced_stride = D.max_len;
-    sp.uniforms = D.uniforms ? D.uniforms + (size_t)step * B : nullptr;
+    sp.uniforms = D.uniforms ? D.uniforms + (size_t)step * Bp : nullptr;
     sp.seed = D.seed; sp.step = step; sp.greedy = D.greedy; sp.eos_id = D.eos_id; sp.done = W.done; sp.n_done = D.status;
-    sp.first_all_done = D.status + 1; sp.B = B;
-    const size_t step_off = (size_t)step * B * m.c.trg_vocab;
+    sp.first_all_done = D.status + 1; sp.B = B; sp.rowmap = rowmap; sp.Bphys = Bp; sp.skip_done = D.skip_done; sp.pad_id = m.c.pad_id;
+    const size_t step_off = (size_t)step * Bp * m.c.trg_vocab;
     sp.probs_out = D.probs_out ? D.probs_out + step_off : nullptr;
     sp.logits_out = D.logits_out ? D.logits_out + step_off : nullptr;
     GCT_CUDA(launch_k(decode_sample_kernel, dim3(cdiv(B, 4)), dim3(128), 0, st, true, sp));

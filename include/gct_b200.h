@@ -212,6 +212,14 @@ typedef struct {
                                   the drawn token (scoring given sequences; per-step parity tests); no <eos> bookkeeping */
     float* probs_out;          /* optional [max_steps,B,Vt]: softmax(logits) of every step                       */
     float* logits_out;         /* optional [max_steps,B,Vt]: the logits of every step (model.decode(...)[:, -1])  */
+    /* Active-row decode (not in the reference, whose loop re-runs every row until the LAST one has emitted <eos>,
+       Inference/sampling_tool.py:144-183).  skip_done = 1: a row that has emitted <eos> appends pad_id from then on and
+       its attention work is skipped (the strings id_to_smi builds, :54-61, are unchanged: they end at the first <eos>).
+       rowmap / n_active: the step kernels run on n_active COMPACT rows, row i standing for physical row rowmap[i] of
+       the caches / ys / uniforms (built by gct_decode_compact between chunks of steps); NULL / 0 = all B rows.        */
+    int32_t skip_done;
+    int32_t n_active;
+    const int32_t* rowmap;
 } gct_decode_t;
 
 size_t gct_decode_workspace_bytes(const gct_config_t* cfg, int B, int Lz, int max_len);
@@ -221,6 +229,11 @@ int gct_decode_begin(const gct_config_t* cfg, const gct_weights_t* w, const gct_
 /* runs decode steps [step_begin, step_end): step i reads ys[:, prefix_len-1+i] and writes ys[:, prefix_len+i] */
 int gct_decode_steps(const gct_config_t* cfg, const gct_weights_t* w, const gct_decode_t* d, int step_begin,
                      int step_end, void* workspace, size_t workspace_bytes, void* stream);
+/* Active-row decode: writes the physical indices of the rows that have NOT emitted <eos> yet (ascending) into
+ * rowmap[0 .. n_active) and pads rowmap[n_active .. n_out) with a finished row; n_out >= n_active is the caller's
+ * rounded-up batch (n_active = B - status[0], read by the caller after the previous chunk of steps).  One launch. */
+int gct_decode_compact(const gct_config_t* cfg, const gct_decode_t* d, int n_out, int32_t* rowmap_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
 /* number of kernels one decode step launches (for bench.py's gpu_launches claim) */
 int gct_decode_launches_per_step(const gct_config_t* cfg);
 int gct_decode_launches_per_step_at(const gct_config_t* cfg, int B);   /* at batch B (large batches fuse two Norms per layer away) */
