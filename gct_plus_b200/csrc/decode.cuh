@@ -19,6 +19,7 @@ struct DecAttnParams {
     // key_valid by the physical row rowmap[i]; a row whose `done` flag is set is not touched at all (no cache append, out stale)
     const int* rowmap = nullptr;
     const uint8_t* done = nullptr;
+    long long rows_phys = 0;                 // rows of the caches (0 = B): the extent of the tensor maps' row dimension
 };
 
 // One CTA per batch row: a producer warp streams that row's K and V cache slabs (contiguous [keys][H*64]) through a
@@ -216,7 +217,10 @@ decode_attn_kernel(DecAttnParams p, int B) {
     }
 }
 
-extern int g_da_cfg;      // tuning knob: chunk*100 + stages*10 + rows (0 = default)
+extern int g_da_cfg;      // tuning knob: chunk*100 + stages*10 + rows (0 = default); 2 / 3 / 4 = tensor-core form with that many
+                          // ring stages, 12 / 13 / 14 = the same with one box per head; -1 = the bulk-copy kernels for every call
+
+#include "decode_attn_mma.cuh"
 
 template <typename T, int CH, int NS, int ROWS>
 static int launch_decode_attn_cfg(const DecAttnParams& p, int B, cudaStream_t st) {
@@ -236,6 +240,15 @@ static int launch_decode_attn(const DecAttnParams& p, int B, cudaStream_t st) {
     if constexpr (sizeof(T) == 4) {
         return launch_decode_attn_cfg<T, 8, 3, 1>(p, B, st);
     } else {
+        // self-attention over the growing cache: tensor-core form (decode_attn_mma.cuh).  Cross-attention in K / V form keeps the
+        // bulk-copy kernel: its rows end at different keys, which a box clipped per launch cannot express.
+        if (p.knew != nullptr && g_da_cfg >= 0 && g_da_cfg < 100) {
+            const long long rows = p.rows_phys > 0 ? p.rows_phys : B;
+            const int ns = g_da_cfg % 10, ph = g_da_cfg >= 10;
+            if (ns == 3) return damma::launch_cfg<3>(p, B, rows, ph, st);
+            if (ns == 4) return damma::launch_cfg<4>(p, B, rows, ph, st);
+            return damma::launch_cfg<2>(p, B, rows, ph, st);
+        }
         switch (g_da_cfg) {
             case 1631: return launch_decode_attn_cfg<T, 16, 3, 1>(p, B, st);
             case 1632: return launch_decode_attn_cfg<T, 16, 3, 2>(p, B, st);

@@ -915,7 +915,7 @@ static int decode_one(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W, int po
             p.q = W.qkv; p.ldq = 3 * d; p.knew = W.qkv + d; p.vnew = W.qkv + 2 * d; p.ldnew = 3 * d;
             p.kcache = W.kc + (size_t)l * Bp * Lmax * d; p.vcache = W.vc + (size_t)l * Bp * Lmax * d;
             p.cache_bstride = (long long)Lmax * d; p.pitch = d; p.n_cached = pos; p.key_valid = W.key_valid; p.kv_stride = Lmax;
-            p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f; p.rowmap = rowmap; p.done = skip;
+            p.out = W.att; p.ldo = d; p.H = m.H; p.scale = 0.125f; p.rowmap = rowmap; p.done = skip; p.rows_phys = Bp;
             GCT_TRY(launch_decode_attn<T>(p, B, st));
         }
         GCT_TRY(m.linear_res_norm(W.att, B, d, m.WT(m.dec_slot(l, D_O1_W)), m.P(m.dec_slot(l, D_O1_B)), W.x, W.x, m.site(0),

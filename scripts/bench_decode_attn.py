@@ -17,7 +17,7 @@ for B in ([int(x) for x in sys.argv[1:]] or [512, 4096]):
     qkv = torch.randn(B, 3 * d, device=dev).bfloat16()
     out = torch.empty(B, d, device=dev, dtype=torch.bfloat16)
     valid = torch.ones(B, Lmax, device=dev, dtype=torch.uint8)
-    for cfg in (1631, 831, 832, 841, 821, 1621, 1622, 431, 441):
+    for cfg in ([int(x) for x in os.environ.get("GCT_DA_CFGS", "").split(",") if x] or (2, 3, 4, 12, 831, 1621)):
         lib.gct_set_decode_attn_config(cfg)
 
         def launch(l, t):

@@ -155,12 +155,14 @@ def test_autograd_bridge_at_cfg3_shape_matches_fused_trainer():
 
 
 # ------------------------------------------------------------------------------------------ decode attention alone
-@pytest.mark.parametrize("cfg", [0, 831, 1621])
+@pytest.mark.parametrize("cfg", [0, 3, 12, 831, 1621])
 @pytest.mark.parametrize("n_cached", [0, 1, 49, 67, 68, 99])
 def test_decode_attention_kernel_vs_oracle_attention(n_cached, cfg):
     """gct_decode_attention (bf16 tier): one query per (row, head) over n_cached cached keys + this step's key, ragged
     key_valid masks, against O.attention (Model/sublayers.py:29-41) on the same bf16-rounded operands; cfg 0 = the automatic
-    choice (8-key chunks / 3-stage ring below 68 cached keys, 16-key chunks / 2 stages from 68 on), 831 / 1621 force each."""
+    choice (tensor-core form, decode_attn_mma.cuh, 2-stage ring of 16-key TMA boxes), 3 = the same with 3 stages, 12 = one box per
+    head; 831 / 1621 = the bulk-copy FMA kernels (8-key chunks / 3 stages, 16-key chunks / 2 stages).  Cache rows past the cached
+    keys hold +inf: a kernel that fetched them would turn p = 0 into NaN."""
     lib = L.lib()
     B, H, d, Lmax = 777, 8, 512, 128
     g = torch.Generator().manual_seed(100 + n_cached)
@@ -173,6 +175,8 @@ def test_decode_attention_kernel_vs_oracle_attention(n_cached, cfg):
     valid[5, :n_cached] = 0                   # only this step's key
     valid = valid.to(DEV)
     out = torch.zeros(B, d, device=DEV, dtype=torch.bfloat16)
+    kc[:, n_cached + 1:] = float("inf")
+    vc[:, n_cached + 1:] = float("inf")
     kc0, vc0 = kc.clone(), vc.clone()
     lib.gct_set_decode_attn_config(cfg)
     try:
