@@ -45,6 +45,11 @@ __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -64,50 +69,100 @@ struct ZAttnParams {
     const uint8_t* done = nullptr;
 };
 
-template <int LAT, int MINB>
+// SM = true (round 2, late): the row's latent block is staged in shared memory by bulk async copies issued BEFORE the programmatic
+// dependency wait -- the latent rows, masks and condition K/V are constants of the decode call, only the queries come from the
+// preceding GEMM -- so for the CTAs of the first wave the bytes arrive while that GEMM drains, and every later warp has its whole
+// row (not two 16-key chunks) in flight after one round trip.  The warp's buffer is private (no CTA-level synchronisation); the
+// first 32 keys are requested at once, the rest as soon as the mask has told where the row ends.  The MMA fragments are then read
+// from shared memory with the same 16-byte-per-lane pattern the global loads used (2-way bank conflicts: irrelevant at 4 KB per
+// chunk), which frees the 64 registers of the second in-flight chunk: 4 CTAs per SM.
+template <int LAT, int MINB, bool SM>
 __global__ void __launch_bounds__(ZA_WARPS * 32, MINB)
 decode_zattn_kernel(ZAttnParams p) {
     constexpr int NB = LAT / 32;                // 32-dim blocks of a latent row (one 16-byte load per lane and block)
     constexpr float kL2e = 1.4426950408889634f;
+    extern __shared__ __align__(128) uint8_t za_smem[];
+    __shared__ __align__(8) uint64_t za_bars[ZA_WARPS][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.x * ZA_WARPS + warp;
-    pdl_wait();
-    pdl_launch_dependents();
-    if (b >= p.B) return;
-    const int bp = p.rowmap ? p.rowmap[b] : b;
-    if (p.done != nullptr && p.done[bp] != 0) return;
+    if constexpr (!SM) {
+        pdl_wait();
+        pdl_launch_dependents();
+    }
+    const bool live = b < p.B;
+    const int bp = live ? (p.rowmap ? p.rowmap[b] : b) : 0;
+    const bool run = live && !(p.done != nullptr && p.done[bp] != 0);
+    if constexpr (!SM) { if (!run) return; }
     const int H = p.H, d = 64 * H, nkeys = p.n_keys;
     const bf16* zg = p.z + (size_t)bp * p.z_bstride + t * 8;
     const uint8_t* valid = p.key_valid + (size_t)bp * p.kv_stride;
     const bf16* qrow = p.qz + (size_t)b * p.ldq;
+    // ---- SM: request the row before waiting for the producer of the queries
+    const uint32_t zs = tc::smem_u32(za_smem) + (uint32_t)warp * (uint32_t)nkeys * (LAT * 2);
+    const uint32_t bar_a = tc::smem_u32(&za_bars[warp][0]), bar_b = bar_a + 8;
+    int nrow_sm = 0;
+    if constexpr (SM) {
+        if (run) {
+            if (lane == 0) {
+                tc::mbar_init(bar_a, 1);
+                tc::mbar_init(bar_b, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                const uint32_t n0 = (uint32_t)min(nkeys, 32) * (LAT * 2);
+                tc::mbar_expect_tx(bar_a, n0);
+                bulk_g2s(zs, p.z + (size_t)bp * p.z_bstride, n0, bar_a);
+            }
+            for (int j0 = 0; j0 < nkeys; j0 += 32) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, j0 + lane < nkeys && valid[j0 + lane] != 0);
+                if (bal) nrow_sm = j0 + 32 - __clz(bal);
+            }
+            if (nrow_sm == 0 && p.nc == 0) nrow_sm = nkeys;
+            if (nrow_sm > 32 && lane == 0) {
+                const uint32_t n1 = (uint32_t)(nrow_sm - 32) * (LAT * 2);
+                tc::mbar_expect_tx(bar_b, n1);
+                bulk_g2s(zs + 32 * (LAT * 2), p.z + (size_t)bp * p.z_bstride + (size_t)32 * LAT, n1, bar_b);
+            }
+        }
+        pdl_wait();
+        pdl_launch_dependents();
+        if (!run) return;
+    }
 
     // The first TWO 16-key chunks are requested before anything else (their addresses depend on nothing but n_keys): with the
     // query fragments and the validity bytes that is one round trip to memory for every row of up to 32 keys, two for the rest
     // (ncu, first version with one chunk in flight: 47 % of the stall samples were long-scoreboard waits, 22 % occupancy).
-    uint4 za[NB], zb[NB], na[NB], nb[NB];
+    uint4 za[NB], zb[NB], na[SM ? 1 : NB], nb[SM ? 1 : NB];
     auto load_chunk = [&](int chunk, uint4* da, uint4* db, int limit) {
         const int ka = chunk * 16 + g, kb = ka + 8;
         const bool ia = ka < limit, ib = kb < limit;
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-            da[k] = ia ? ldg_nc16(zg + (size_t)ka * LAT + k * 32) : make_uint4(0, 0, 0, 0);
-            db[k] = ib ? ldg_nc16(zg + (size_t)kb * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+            if constexpr (SM) {
+                da[k] = ia ? lds16(zs + (uint32_t)ka * (LAT * 2) + k * 64 + t * 16) : make_uint4(0, 0, 0, 0);
+                db[k] = ib ? lds16(zs + (uint32_t)kb * (LAT * 2) + k * 64 + t * 16) : make_uint4(0, 0, 0, 0);
+            } else {
+                da[k] = ia ? ldg_nc16(zg + (size_t)ka * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+                db[k] = ib ? ldg_nc16(zg + (size_t)kb * LAT + k * 32) : make_uint4(0, 0, 0, 0);
+            }
         }
     };
-    load_chunk(0, za, zb, nkeys);
-    load_chunk(1, na, nb, nkeys);
+    if constexpr (!SM) {
+        load_chunk(0, za, zb, nkeys);
+        load_chunk(1, na, nb, nkeys);
+    }
     // query fragments: lane (g,t) = head g, dims 32*blk + 8t .. +8 (same permutation as the latent rows)
     uint4 q[NB];
 #pragma unroll
     for (int k = 0; k < NB; ++k) q[k] = (g < H) ? ldg_nc16(qrow + (size_t)g * LAT + k * 32 + t * 8) : make_uint4(0, 0, 0, 0);
     // last attendable latent key: later ones are never fetched
-    int nrow = 0;
-    for (int j0 = 0; j0 < nkeys; j0 += 32) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, j0 + lane < nkeys && valid[j0 + lane] != 0);
-        if (bal) nrow = j0 + 32 - __clz(bal);
+    int nrow = nrow_sm;
+    if constexpr (!SM) {
+        for (int j0 = 0; j0 < nkeys; j0 += 32) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, j0 + lane < nkeys && valid[j0 + lane] != 0);
+            if (bal) nrow = j0 + 32 - __clz(bal);
+        }
+        if (nrow == 0 && p.nc == 0) nrow = nkeys;   // nothing attendable: every score is -1e9 -> uniform softmax over all keys (masked_fill semantics)
     }
-    if (nrow == 0 && p.nc == 0) nrow = nkeys;   // nothing attendable: every score is -1e9 -> uniform softmax over all keys (masked_fill semantics)
 
     // running softmax state of heads 2t (index 0) and 2t+1 (index 1); l is a per-lane partial, reduced over g at the end
     float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
@@ -208,8 +263,16 @@ decode_zattn_kernel(ZAttnParams p) {
             mma_bf16_16816(acc[2 * k + 1], movmatrix_trans(ca[k].z), movmatrix_trans(ca[k].w), movmatrix_trans(cb[k].z), movmatrix_trans(cb[k].w), pb0, pb1);
         }
     };
+    if constexpr (SM) {
+        for (int c0 = 0; c0 < nrow; c0 += 16) {
+            if (c0 == 0) tc::mbar_wait(bar_a, 0);
+            if (c0 == 32) tc::mbar_wait(bar_b, 0);
+            load_chunk(c0 >> 4, za, zb, nrow);
+            consume(za, zb, c0);
+        }
+    }
     // two register buffers, each refilled with the chunk two ahead as soon as it has been consumed
-    for (int c0 = 0; c0 < nrow; c0 += 32) {
+    for (int c0 = 0; !SM && c0 < nrow; c0 += 32) {
         consume(za, zb, c0);
         if (c0 + 32 < nrow) load_chunk((c0 >> 4) + 2, za, zb, nrow);
         if (c0 + 16 < nrow) {
@@ -275,13 +338,21 @@ decode_zattn_kernel(ZAttnParams p) {
     }
 }
 
-extern int g_za_cfg;      // tuning knob: resident CTAs per SM the kernel is compiled for (3: 160 registers, no spills; 4: 128 registers)
+extern int g_za_cfg;      // tuning knob: 0 = rows staged in shared memory (default); 3 / 4 = rows straight from global memory into registers,
+                          // compiled for that many resident CTAs per SM (3: 160 registers, no spills; 4: 128 registers)
 
 template <int LAT>
 static int launch_decode_zattn_lat(const ZAttnParams& p, cudaStream_t st) {
     const dim3 grid((p.B + ZA_WARPS - 1) / ZA_WARPS), block(ZA_WARPS * 32);
-    if (g_za_cfg == 4) GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 4>, grid, block, 0, st, true, p));
-    else GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 3>, grid, block, 0, st, true, p));
+    const size_t smem = (size_t)ZA_WARPS * p.n_keys * LAT * 2;
+    if (g_za_cfg == 4) GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 4, false>, grid, block, 0, st, true, p));
+    else if (g_za_cfg == 3 || smem > 100 * 1024) GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 3, false>, grid, block, 0, st, true, p));
+    else {
+        // rows staged in shared memory (default): 4 warps x n_keys x LAT x 2 bytes per CTA
+        auto kern = decode_zattn_kernel<LAT, 4, true>;
+        GCT_SMEM_LIMIT(kern, smem);
+        GCT_CUDA(launch_k(kern, grid, block, smem, st, true, p));
+    }
     return GCT_OK;
 }
 static bool zattn_supported(int lat, int H, int nc) { return (lat == 128 || lat == 64 || lat == 32) && H >= 1 && H <= 8 && nc >= 0 && nc <= 8; }

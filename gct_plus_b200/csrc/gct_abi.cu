@@ -14,7 +14,7 @@ int g_gct_tma_store = 1;
 int g_gct_ew4 = 1;
 int g_gct_pair = 2;
 int g_gct_attn_bias_separate = 0;
-int g_za_cfg = 3;
+int g_za_cfg = 0;
 int g_gct_sm_budget = 0;
 int g_gct_res_box = 1;
 int g_gct_attn_box = 1;

@@ -22,7 +22,7 @@ zs = zs.to(dev)
 ys0 = torch.full((B, 1), 2, dtype=torch.long, device=dev)
 s.decode(zs=zs, ys=ys0, src_mask=mask)
 for rep in range(2):
-    for name, pair in (("zattn 3 CTAs/SM", 3), ("zattn 4 CTAs/SM", 4)):
+    for name, pair in (("zattn rows from global memory, 3 CTAs/SM", 3), ("zattn rows staged in shared memory", 0)):
         lib.gct_set_zattn_config(pair)
         s.decode(zs=zs, ys=ys0, src_mask=mask)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
