@@ -63,16 +63,22 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
     }
     __syncthreads();
-    pdl_wait();
-    pdl_launch_dependents();
+    // Programmatic dependent launch: the kernel before this one (the QKV projection) produces only q and this step's K / V row.
+    // The cached keys, the validity bytes, `done` and the row map were written at least two kernels earlier, and a kernel is
+    // launched only after its predecessor has passed ITS dependency wait, i.e. after everything older has completed -- so the
+    // producer warp streams the cache without waiting, and the boxes of a CTA's first stages arrive while the projection drains.
     const int b = blockIdx.x;
     const int bp = p.rowmap ? p.rowmap[b] : b;
-    if (p.done != nullptr && p.done[bp] != 0) return;          // uniform over the CTA
+    if (p.done != nullptr && p.done[bp] != 0) {                // uniform over the CTA
+        pdl_wait();                                            // keeps "launched => everything older has completed" true for the successors
+        pdl_launch_dependents();
+        return;
+    }
     const int nc = p.n_cached;
     const int nchunks = (nc + CH - 1) / CH;
 
     if (warp == H) {
-        // ---------------- producer ----------------
+        // ---------------- producer (no dependency wait, see above; it does not release the dependents either) ----------------
         if (lane == 0) {
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % NS;
@@ -101,6 +107,8 @@ decode_attn_mma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
     // warp's own lanes for keys 16c + g (+8), so a warp-wide copy + __syncwarp would do -- but the slots are shared, hence the
     // named barrier over the consumer warps below
     for (int j = threadIdx.x; j <= nc && j < DEC_MAX_KEYS; j += H * 32) valid_s[j] = valid[j];
+    pdl_wait();
+    pdl_launch_dependents();
     const bf16* qrow = reinterpret_cast<const bf16*>(p.q) + (size_t)b * p.ldq + h * 64;
     uint32_t qf[4][2];
 #pragma unroll
