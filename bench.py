@@ -789,7 +789,7 @@ def main():
                         "call": "sampler.sample_smiles(n, zs=<pinned host latents>, toklen=<host list>) -> Python strings"},
                 "e2e_public_call": s["public"], "active_row_decode": s["active"],
                 "gpu_launches": s["launches"], "clocks": s["clocks"],
-                "roofline": {"bound": "hbm", "kernel": "decode_attn_kernel<bf16> (self-attention over the KV cache)",
+                "roofline": {"bound": "hbm", "kernel": "damma::decode_attn_mma_kernel<2> (self-attention over the KV cache, bf16)",
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                              "traffic": NCU_TRAFFIC["dram_bytes_per_launch"], "traffic_detail": NCU_TRAFFIC,
                              "peak_source": peak_src, "launches_timed": nl, "us_per_launch": ms_per_launch * 1e3,

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "libgct_b200.so")
 SOURCES = ["gct_abi.cu"]
-HEADERS = ["common.cuh", "epilogue.cuh", "elementwise.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_rownorm.cuh", "attention.cuh", "attention_tc.cuh", "decode.cuh", "decode_zattn.cuh",
+HEADERS = ["common.cuh", "epilogue.cuh", "elementwise.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "gemm_rownorm.cuh", "attention.cuh", "attention_tc.cuh", "decode.cuh", "decode_attn_mma.cuh", "decode_zattn.cuh",
            "model.cuh", os.path.join("..", "..", "include", "gct_b200.h")]
 
 

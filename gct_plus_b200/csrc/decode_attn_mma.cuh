@@ -44,8 +44,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 // NS ring stages of (K box | V box), each box H x 16 keys x 128 B.  per_head = 1: the maps are rank 3 (dims, key, row) and a chunk
 // is H boxes of one head each (same shared-memory image); used when the driver refuses the permuted strides of the rank-4 map.
+// Three CTAs per SM (NS = 2: 3 x 70 KB of shared memory) need <= 75 registers per thread: without the bound ptxas took 93 for
+// the version with the early producer start and the kernel dropped to two CTAs per SM (ncu: 5.64 instead of 6.6 TB/s).
 template <int NS>
-__global__ void __launch_bounds__(288)
+__global__ void __launch_bounds__(288, NS <= 2 ? 3 : (NS == 3 ? 2 : 1))
 decode_attn_mma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, DecAttnParams p, int B, int per_head) {
     extern __shared__ uint8_t dam_smem[];
     __shared__ uint8_t valid_s[DEC_MAX_KEYS];

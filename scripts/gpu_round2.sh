@@ -36,15 +36,17 @@ if has full; then
   export_rep() { ncu -i $1.ncu-rep --page details > $1_ncu_details.txt 2>&1; ncu -i $1.ncu-rep --page raw --csv > $1_ncu_raw.csv 2>&1;
                  ncu -i $1.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $1_ncu_source.csv.gz; rm -f $1.ncu-rep; }
   timeout 300 python scripts/one_decode_attn.py 30000 49 > $O/plain_da.log 2>&1 && \
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_attn_kernel -s 3 -c 1 -o $O/r02_decode_attn_b30000_t49_$TAG -f \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_attn -s 3 -c 1 -o $O/r02_decode_attn_b30000_t49_$TAG -f \
       python scripts/one_decode_attn.py 30000 49 > $O/ncu_da.log 2>&1
   echo "decode_attn full exit $?"; export_rep $O/r02_decode_attn_b30000_t49_$TAG
   GCT_PROFILE_B=30000 timeout 900 $NCU_FULL -k regex:decode_zattn_kernel -c 1 -o $O/r02_decode_zattn_b30000_$TAG -f python scripts/profile_decode.py > $O/ncu_za.log 2>&1
   echo "zattn full exit $?"; export_rep $O/r02_decode_zattn_b30000_$TAG
+  if has heavy; then
   timeout 900 $NCU_FULL -k regex:norm_bwd_kernel -s 4 -c 1 -o $O/r02_norm_bwd_$TAG -f python scripts/profile_train.py > $O/ncu_nb.log 2>&1
   echo "norm_bwd full exit $?"; export_rep $O/r02_norm_bwd_$TAG
   timeout 900 $NCU_FULL -k regex:attn_bwd_tc_kernel -s 4 -c 1 -o $O/r02_attn_bwd_$TAG -f python scripts/profile_train.py > $O/ncu_ab.log 2>&1
   echo "attn_bwd full exit $?"; export_rep $O/r02_attn_bwd_$TAG
+  fi
   grep -E "dram__bytes_(read|write).sum|gpu__time_duration.sum" $O/*_ncu_raw.csv | head -5
 fi
 ls -la $O | tail -30

@@ -10,6 +10,9 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 dev = torch.device("cuda:0")
+if os.environ.get("GCT_DA_CFG") is not None:          # decode self-attention form: 0 tensor-core (default), -1 bulk-copy FMA kernels
+    import gct_plus_b200._lib as L
+    L.lib().gct_set_decode_attn_config(int(os.environ["GCT_DA_CFG"]))
 for B in ([int(x) for x in sys.argv[1:]] or [512, 30000]):
     bench.BATCH = B
     s = bench.build_sampler(dev)
