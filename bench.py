@@ -37,11 +37,11 @@ ARCH = dict(N=6, d_model=512, dff=2048, h=8, latent_dim=128)
 VOCAB = 32
 MAX_STRLEN = 100
 BATCH = 512
-# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attn launch (ncu --set full, B=30000 = the rows per launch of the
-# roofline leg and of the benched decode, 49 cached keys, profiles/r02_decode_attn_b30000_t49_v1_ncu_details.txt: 3105.9 MB
-# read + 96.3 MB written in 509.9 us) next to the algorithmic bytes of that same launch
-NCU_TRAFFIC = {"dram_bytes_per_launch": 3202196024, "algorithmic_bytes_same_launch": 3194880000, "shape": "B=30000, 49 cached keys + 1 new",
-               "source": "profiles/r02_decode_attn_b30000_t49_v1_ncu_details.txt"}
+# dram__bytes_read.sum + dram__bytes_write.sum of one damma::decode_attn_mma_kernel<2> launch (ncu --set full, B=30000 = the rows
+# per launch of the roofline leg and of the benched decode, 49 cached keys, profiles/r02_decode_attn_b30000_t49_v7_ncu_raw.csv:
+# 3106.2 MB read + 98.0 MB written in 489.2 us) next to the algorithmic bytes of that same launch
+NCU_TRAFFIC = {"dram_bytes_per_launch": 3204180864, "algorithmic_bytes_same_launch": 3194880000, "shape": "B=30000, 49 cached keys + 1 new",
+               "source": "profiles/r02_decode_attn_b30000_t49_v7_ncu_details.txt"}
 SCAFFOLD20 = "c1ccc(cc1)C(=O)NCCOC"        # 20 tokens under the character tokeniser below (cfg 5)
 ITOS = ["<unk>", "<pad>", "<sos>", "<eos>", "<sep>"] + list("CcNnOoSsFIBrl()[]=#123456+-H@/")[:27]
 
