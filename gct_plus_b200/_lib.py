@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgct_b200.so")
+LIB_PATH = os.environ.get("GCT_B200_LIB") or os.path.join(_HERE, "libgct_b200.so")     # override: A/B of two builds of the library
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 NUM_GLOBAL_SLOTS, ENC_LAYER_SLOTS, DEC_LAYER_SLOTS = 22, 12, 20

@@ -156,7 +156,7 @@ __device__ __forceinline__ void fwd_exp_chunk(uint32_t taddr, uint32_t m16, int 
 
 // backward: P = exp2(c*s - lse), Pd = dropout(P) -> pk[8]; dS = P (dropout'(dP) - D) scale -> dk[8]; row sums of both
 __device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tg, uint32_t m16, int nvalid, float cs, float lse2, float D, float scale,
-                                          const DropCtx& drop, uint32_t pair0, bool qok, float inv_lk, uint32_t* pk, uint32_t* dk,
+                                          const DropCtx& drop, uint32_t pair0, bool qok, float log2_lk, uint32_t* pk, uint32_t* dk,
                                           float2& rs_p, float2& rs_s) {
     const uint32_t vis = m16 & valid16(nvalid);
     if (__all_sync(0xffffffffu, vis == 0u && lse2 > 0.5f * kFill2)) {
@@ -176,17 +176,21 @@ __device__ __forceinline__ void bwd_chunk(uint32_t ts, uint32_t tg, uint32_t m16
     if (!all) {
         if (nvalid >= 16) score16<false>(s, m16, cs, 16);
         else score16<true>(s, m16, cs, nvalid);
+        if (lse2 <= 0.5f * kFill2) {
+            // a row without one visible key (this thread only, practically never): every score is the fill value, softmax is
+            // uniform over the Lk keys -- and lse = fill + log(Lk) has lost the log(Lk) to fp32 rounding.  Re-base the row:
+            // scores 0 (tail columns stay at -inf), lse = log2(Lk).  Done ahead of the loop so that the loop body, which
+            // decides the kernel's registers, is the same for every row.
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[i] -= kFill2;
+            lse2 = log2_lk;
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float2 sv = make_float2(s[2 * i], s[2 * i + 1]);
         const float2 d = all ? __ffma2_rn(sv, make_float2(cs, cs), make_float2(-lse2, -lse2)) : __fadd2_rn(sv, make_float2(-lse2, -lse2));
-        float2 pr = make_float2(ex2_approx(d.x), ex2_approx(d.y));
-        if (!all && lse2 <= 0.5f * kFill2) {
-            // a row without one visible key: every score is the fill value, softmax is uniform over the Lk keys -- and
-            // lse = fill + log(Lk) has lost the log(Lk) to fp32 rounding
-            pr = make_float2(2 * i < nvalid ? inv_lk : 0.f, 2 * i + 1 < nvalid ? inv_lk : 0.f);
-        }
+        const float2 pr = make_float2(ex2_approx(d.x), ex2_approx(d.y));
         const float2 keep = drop_mult_pair<true>(drop, pair0 + i);
         const float2 pd = __fmul2_rn(pr, keep);
         const float2 gd = __ffma2_rn(make_float2(g[2 * i], g[2 * i + 1]), keep, make_float2(-D, -D));
@@ -510,7 +514,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 uint32_t pk[8], dk[8];
                 const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;
                 float2 rs_p = make_float2(0.f, 0.f), rs_s = rs_p;       // row sums: unused here
-                bwd_chunk(trow + c16 * 16, trow + 128 + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, lse2, D, p.scale, p.drop, pair0, qok, 1.f / (float)Lk, pk,
+                bwd_chunk(trow + c16 * 16, trow + 128 + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, lse2, D, p.scale, p.drop, pair0, qok, log2f((float)Lk), pk,
                           dk, rs_p, rs_s);
                 const uint32_t blk = (uint32_t)(c16 >> 2) * (uint32_t)L.BS, blkp = (uint32_t)(c16 >> 2) * (uint32_t)L.LBOP;
                 const int ch = (c16 & 3) * 2;
@@ -988,7 +992,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                 if (c16 < nchk) {
                     uint32_t pk[8], dk[8];
                     const uint32_t pair0 = (drow32 + (uint32_t)(c16 * 16)) >> 1;
-                    bwd_chunk(trow + c16 * 16, trow + 128 + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, lse2, D, p.scale, p.drop, pair0, qok, 1.f / (float)Lk,
+                    bwd_chunk(trow + c16 * 16, trow + 128 + c16 * 16, mask16(mb, c16), Lk - c16 * 16, cs, lse2, D, p.scale, p.drop, pair0, qok, log2f((float)Lk),
                               pk, dk, rs_p, rs_s);
                     const uint32_t blk = (uint32_t)(c16 >> 2) * U;
                     const int ch = (c16 & 3) * 2;

@@ -293,6 +293,45 @@ def test_fp32_kv_decode_every_step_matches_oracle_at_b2048():
     assert float(clear.float().mean()) > 0.99
 
 
+def test_bf16_kv_decode_at_the_benched_batch_of_30000_rows_matches_oracle():
+    """BASELINE cfg 2 at its full size: ONE teacher-forced 99-step bf16 decode of 30 000 rows (the batch bench.py times: persistent
+    CTA-pair GEMMs over 235 row tiles, decode_attn_mma over a 52.7 GB cache, latent-space cross-attention), every step's logits
+    of 1 500 rows spread over the whole batch (first / last rows and both ends of the last row tile included) against the
+    oracle's un-cached decoder on those rows (Inference/sampling_tool.py:150-160); and the rows are independent of their
+    neighbours: the same 1 500 rows decoded in a call of their own give the same logits to bf16 rounding."""
+    B, max_strlen, Lz = 30000, 100, 55
+    steps = max_strlen - 1
+    torch.manual_seed(0)
+    m = Vaetf(V, V, dropout=0.1, nconds=0, compute_dtype="bf16", **ARCH)
+    sd = {k: v.detach().clone().to(DEV) for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    s = _sampler(m, "vaetf", 0, max_strlen, latent_bucket=64)
+    g = torch.Generator().manual_seed(19)
+    zs = torch.randn(B, Lz, ARCH["latent_dim"], generator=g)
+    lens = torch.clamp(torch.round(35 + 7 * torch.randn(B, generator=g)), 13, Lz).long()      # bench.py's length law
+    lens[0], lens[B - 1] = Lz, 13
+    mask = torch.arange(Lz)[None, None, :] < lens[:, None, None]
+    ys = torch.randint(5, V, (B, 1 + steps), generator=g)
+    ys[:, 0] = 2
+    got = s.teacher_forced_logits(zs, ys, mask)                                  # (steps, B, V)
+    pick = torch.unique(torch.cat([torch.arange(0, B, 20), torch.tensor([1, 127, 128, 255, 256, 29951, 29952, B - 2, B - 1])]))
+    cfg = O.ModelCfg(model_type="vaetf", src_vocab=V, trg_vocab=V)
+    trg = ys[pick, :-1].to(DEV)
+    with torch.no_grad():
+        want = O.decode_logits(sd, cfg, trg, zs[pick].to(DEV), mask[pick].to(DEV), O.trg_mask(trg, 1)).transpose(0, 1)
+    sub = got[:, pick.to(DEV), :]
+    scale = float(want.abs().max())
+    per_step = (sub - want).abs().amax(dim=(1, 2)) / scale
+    print(f"30000-row decode: worst step {int(per_step.argmax())} rel err {float(per_step.max()):.3e}, mean {float(per_step.mean()):.3e}")
+    assert float(per_step.max()) < 1e-2, (int(per_step.argmax()), float(per_step.max()))
+    assert torch.isfinite(got).all()
+    del got
+    alone = s.teacher_forced_logits(zs[pick], ys[pick], mask[pick])
+    e = float((alone - sub).abs().max()) / scale
+    print(f"30000-row decode vs the same rows alone: rel diff {e:.3e}")
+    assert e < 5e-3, e
+
+
 @pytest.mark.parametrize("mode", ["overlap", "nccl"])
 def test_dp_backward_with_a_one_rank_communicator_equals_plain_backward(mode):
     """gct_backward_dp (bucketed NCCL all-reduce issued from inside the backward on a side stream) and gct_allreduce_grads on a
