@@ -305,6 +305,7 @@ __device__ __forceinline__ void epi_finish(const Epilogue& e, int row, int col, 
 }
 
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk16);
+__device__ __forceinline__ void stage_wait_free(int lane);
 
 // Compile-time specialised epilogue for one 16-column chunk of one row (the persistent kernel's hot path):
 // no per-element branches, no 64-bit index arithmetic (the caller passes element offsets), operands requested
@@ -312,9 +313,11 @@ __device__ __forceinline__ uint32_t stage_off(int row, int chunk16);
 // With stg != nullptr the results are not stored to global memory by this thread: they are parked in the warp's
 // swizzled staging tile (32 rows x 128 B) at 16-byte chunk `sc` (and `sc_aux` for the saved GELU pre-activation) and
 // leave later as whole row segments (stage_flush), which cuts the number of L2 write requests by 4-8x.
+// wait_stg: the staging tile may still be read by the TMA store of the previous segment (stage_tma_store_async): wait for that
+// read just before the first write, i.e. AFTER this chunk's TMEM load and math, which is what hides the store's latency.
 template <bool HAS_BIAS, int ACT, bool HAS_RES, bool OUT_F32, int WHICH = 0>
 __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __restrict__ bias, uint32_t taddr, size_t off, int col,
-                                            uint8_t* stg = nullptr, int lane = 0, int sc = 0, int sc_aux = 0) {
+                                            uint8_t* stg = nullptr, int lane = 0, int sc = 0, int sc_aux = 0, bool wait_stg = false) {
     float4 b4[4], r4[4];
     uint4 h2[2];
     if constexpr (HAS_BIAS) {
@@ -337,6 +340,7 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
     }
     if constexpr (ACT == 1) {
         if (WHICH != 2 && e.aux_out) {
+            if (wait_stg) stage_wait_free(lane);
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 uint4 u;
@@ -396,6 +400,7 @@ __device__ __forceinline__ void epi_chunk16(const Epilogue& e, const float* __re
         for (int i = 0; i < 16; ++i) sum += v[i];
         if (sum != 1.2345e30f) return;
     }
+    if (WHICH != 1 && wait_stg) stage_wait_free(lane);
     if constexpr (OUT_F32) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -460,6 +465,23 @@ __device__ __forceinline__ void stage_tma_store(const CUtensorMap* map, uint32_t
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    __syncwarp();
+}
+
+// The same store without the wait: the caller calls stage_wait_free before it writes the tile again (and before the kernel ends).
+__device__ __forceinline__ void stage_tma_store_async(const CUtensorMap* map, uint32_t stg_smem, int col, int row, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                         reinterpret_cast<uint64_t>(map)),
+                     "r"(col), "r"(row), "r"(stg_smem)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void stage_wait_free(int lane) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
 }
 
@@ -924,6 +946,9 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     uint8_t* stg = smem_raw + (base - smem_u32(smem_raw)) + L::STAGING_OFF + (warp - 2) * 4096;
                     const int rows_valid = 32;                      // full tile
                     const size_t row0_off = (size_t)(m0 + q * 32) * e.ldc + colb;     // element offset of staged row 0
+                    // use_tma_store bit 3: TMA stores of the staging tile are not waited for where they are issued but just
+                    // before the tile's next write (after the next segment's TMEM load and math) and at the end of the kernel
+                    const bool defer = (use_tma_store & 8) != 0;
 #define GCT_EPI_RUN(HB, ACT_, HR, F32)                                                                                  \
     {                                                                                                                   \
         constexpr int ESZ = F32 ? 4 : 2;                                                                                \
@@ -937,9 +962,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (ACT_ == 1 && e.aux_out) {                             /* pass A: saved pre-activation */                 \
                 _Pragma("unroll 1") for (int ci = 0; ci < CPS; ++ci)                                                    \
                     epi_chunk16<HB, ACT_, HR, F32, 1>(e, bias, tslice + (c0 + ci) * 16, off0 + (c0 + ci) * 16,           \
-                                                      colb + (c0 + ci) * 16, stg, lane, 0, ci * 2);                      \
+                                                      colb + (c0 + ci) * 16, stg, lane, 0, ci * 2, defer && ci == 0);     \
                 if (use_tma_store && SEG_COLS * 2 == 128) {                                                             \
-                    stage_tma_store(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);                                     \
+                    if (defer) stage_tma_store_async(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);                    \
+                    else stage_tma_store(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);                                \
                 } else {                                                                                                \
                     __syncwarp();                                                                                       \
                     stage_flush(stg, lane, 0, CPS * 2, reinterpret_cast<uint8_t*>(e.aux_out) + (row0_off + seg0) * 2,   \
@@ -949,9 +975,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }                                                                                                           \
             _Pragma("unroll 1") for (int ci = 0; ci < CPS; ++ci)                                                        \
                 epi_chunk16<HB, ACT_, HR, F32, 2>(e, bias, tslice + (c0 + ci) * 16, off0 + (c0 + ci) * 16,               \
-                                                  colb + (c0 + ci) * 16, stg, lane, ci * C16, 0);                        \
+                                                  colb + (c0 + ci) * 16, stg, lane, ci * C16, 0, defer && ci == 0);      \
             if (use_tma_store && SEG_COLS * ESZ == 128) {                                                               \
-                stage_tma_store(&tmC, stg_s, colb + seg0, m0 + q * 32, lane);                                           \
+                if (defer) stage_tma_store_async(&tmC, stg_s, colb + seg0, m0 + q * 32, lane);                          \
+                else stage_tma_store(&tmC, stg_s, colb + seg0, m0 + q * 32, lane);                                      \
             } else {                                                                                                    \
                 __syncwarp();                                                                                           \
                 uint8_t* gout = F32 ? reinterpret_cast<uint8_t*>(e.out32) : reinterpret_cast<uint8_t*>(e.outT);         \
@@ -983,6 +1010,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                 for (int ci = 0; ci < CPS; ++ci) {
                                     uint32_t gp[8];
                                     epi_gelu16(e, bias, tslice + (c0 + ci) * 16, off0 + (c0 + ci) * 16, colb + (c0 + ci) * 16, gp, dgp[ci]);
+                                    if (defer && ci == 0) stage_wait_free(lane);      // the previous segment's gradient-factor store
                                     *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2)) = make_uint4(gp[0], gp[1], gp[2], gp[3]);
                                     *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2 + 1)) = make_uint4(gp[4], gp[5], gp[6], gp[7]);
                                 }
@@ -1000,7 +1028,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                                     *reinterpret_cast<uint4*>(stg + stage_off(lane, ci * 2 + 1)) = make_uint4(dgp[ci][4], dgp[ci][5], dgp[ci][6], dgp[ci][7]);
                                 }
                                 if (tma) {
-                                    stage_tma_store(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);
+                                    if (defer) stage_tma_store_async(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);
+                                    else stage_tma_store(&tmAux, stg_s, colb + seg0, m0 + q * 32, lane);
                                 } else {
                                     __syncwarp();
                                     stage_flush(stg, lane, 0, CPS * 2, reinterpret_cast<uint8_t*>(e.aux_out) + (row0_off + seg0) * 2,
@@ -1043,6 +1072,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (use_tma_store & 8) stage_wait_free(lane);      // deferred TMA stores: the staging tile outlives their reads
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -1225,7 +1255,7 @@ static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, int M, i
         const int esz = f32 ? 4 : 2;
         if ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0 && ((size_t)epi.ldc * esz) % 16 == 0) {
             GCT_TRY(get_tensor_map(cptr, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * esz, 128 / esz, 32, &tc_, esz));
-            use_tma = 1;
+            use_tma = 1 | (g_gct_tma_store == 1 ? 8 : 0);
             if ((epi.flags & EPI_GELU) && epi.aux_out)
                 GCT_TRY(get_tensor_map(epi.aux_out, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 2, 64, 32, &taux, 2));
         }
@@ -1259,7 +1289,7 @@ static int launch_persist_pair(const CUtensorMap& ta, const CUtensorMap& tb_mn, 
         const int esz = f32 ? 4 : 2;
         if ((reinterpret_cast<uintptr_t>(cptr) & 15) == 0 && ((size_t)epi.ldc * esz) % 16 == 0) {
             GCT_TRY(get_tensor_map(cptr, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * esz, 128 / esz, 32, &tc_, esz));
-            use_tma = 1;
+            use_tma = 1 | (g_gct_tma_store == 1 ? 8 : 0);
             if ((epi.flags & EPI_GELU) && epi.aux_out)
                 GCT_TRY(get_tensor_map(epi.aux_out, (uint64_t)N, (uint64_t)M, (uint64_t)epi.ldc * 2, 64, 32, &taux, 2));
         }

@@ -89,7 +89,8 @@ int gct_set_ffn_saved_activation(int preact);        /* training FFN: 0 (default
 int gct_set_latent_cross_attention(int enabled);    /* bf16 decode: 1 (default) evaluates cross-attention in latent space when the
                                                        memory has no condition rows, 0 keeps the per-layer K/V form */
 int gct_set_decode_attn_config(int cfg);           /* tuning: chunk*100 + ring stages*10 + rows per CTA (0 = default) */
-int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue (default on) */
+int gct_set_tma_store(int enabled);                 /* TMA tensor stores in the persistent GEMM epilogue: 0 off, 1 (default) on, the wait for a
+                                                        store's shared-memory read deferred to the staging tile's next write, 2 on, wait at the store */
 int gct_set_cta_pair_gemm(int level);               /* persistent GEMM over CTA pairs (tcgen05.mma.cta_group::2): 0 off, 1 K-major
                                                        operands only, 2 (default) also dgrad / wgrad operand layouts */
 int gct_set_residual_box(int mode);                /* bit 0 (default 1): persistent GEMM epilogues fetch the fp32 residual / the multiply-by-aux factor as
