@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(256, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, int box_store, AttnParams p,
                    unsigned long long* trace) {
+    pdl_wait();        // programmatic dependent launch: q / k / v (dO, O, lse) come from the kernels just before this one
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -253,6 +254,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();       // only now: a dependent that allocates TMEM in its prologue must not get ahead of this CTA's allocation
     trace_mark(trace, 1);
     const bool dense = p.mask_rstride != 0;
     if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
@@ -410,6 +412,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
                    const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, int box_io, AttnBwdParams bp,
                    unsigned long long* trace) {
+    pdl_wait();        // programmatic dependent launch: q / k / v (dO, O, lse) come from the kernels just before this one
     const AttnParams& p = bp.f;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -447,6 +450,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();       // only now: a dependent that allocates TMEM in its prologue must not get ahead of this CTA's allocation
     // TMEM columns: S [0,128)  dP [128,256); after the softmax pass: dV [0,64)  dK [64,128)  dQ [128,192)
     const bool dense = p.mask_rstride != 0;
     if (p.mask) build_mask_bits(p.mask + (size_t)b * p.mask_bstride, dense ? Lq : 1, Lk, dense ? p.mask_rstride : 0, bits, warp, lane, 8);
@@ -653,6 +657,7 @@ __global__ void __launch_bounds__(256, 3)
 attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnParams p, int ntiles,
                            unsigned long long* trace) {
+    pdl_wait();        // programmatic dependent launch: q / k / v (dO, O, lse) come from the kernels just before this one
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -694,6 +699,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();       // only now: a dependent that allocates TMEM in its prologue must not get ahead of this CTA's allocation
     const bool dense = p.mask_rstride != 0;
     const int nchk = NS >> 4;                         // this thread's 16-column chunks: half, half + 2, ...
     const bool wactive = q * 32 < Lq;                 // warp-uniform: the warp owns at least one real query row
@@ -863,6 +869,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
                            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmDQ,
                            const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV, AttnBwdParams bp, int ntiles,
                            unsigned long long* trace) {
+    pdl_wait();        // programmatic dependent launch: q / k / v (dO, O, lse) come from the kernels just before this one
     const AttnParams& p = bp.f;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -914,6 +921,7 @@ attn_bwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();       // only now: a dependent that allocates TMEM in its prologue must not get ahead of this CTA's allocation
     // TMEM columns: S [0,128)  dP [128,256); after the softmax pass: dV [0,64)  dK [64,128)  dQ [128,192)
     const bool dense = p.mask_rstride != 0;
     const int nchk = NS >> 4;                         // this thread's 16-column chunks: half, half + 2, ...
@@ -1163,12 +1171,12 @@ static int launch_fwd(const AttnParams& p, cudaStream_t st) {
             pdone_.cur() = 1;
         }
         const int ntiles = p.B * p.H, slots = 3 * sm_count();
-        attn_fwd_tc_persist_kernel<<<ntiles < slots ? ntiles : slots, 256, FwdPersistLayout(RPq > RPk ? RPq : RPk).total, st>>>(
-            tq, tk, tv, to, p, ntiles, g_gct_attn_trace);
+        GCT_CUDA(launch_k(attn_fwd_tc_persist_kernel, dim3(ntiles < slots ? ntiles : slots), dim3(256), (size_t)(FwdPersistLayout(RPq > RPk ? RPq : RPk).total), st, true, 
+            tq, tk, tv, to, p, ntiles, g_gct_attn_trace));
         GCT_LAUNCH_CHECK();
         return GCT_OK;
     }
-    attn_fwd_tc_kernel<<<p.B * p.H, 256, FwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, to, box_store, p, g_gct_attn_trace);
+    GCT_CUDA(launch_k(attn_fwd_tc_kernel, dim3(p.B * p.H), dim3(256), (size_t)(FwdLayout(RPq, RPk).total), st, true, tq, tk, tv, to, box_store, p, g_gct_attn_trace));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
@@ -1208,12 +1216,12 @@ static int launch_bwd(const AttnBwdParams& bp, cudaStream_t st) {
             pdone_.cur() = 1;
         }
         const int ntiles = p.B * p.H, slots = 2 * sm_count();
-        attn_bwd_tc_persist_kernel<<<ntiles < slots ? ntiles : slots, 256, BwdPersistLayout(RPq > RPk ? RPq : RPk).total, st>>>(
-            tq, tk, tv, tdo, to, tdq, tdk, tdv, bp, ntiles, g_gct_attn_trace);
+        GCT_CUDA(launch_k(attn_bwd_tc_persist_kernel, dim3(ntiles < slots ? ntiles : slots), dim3(256), (size_t)(BwdPersistLayout(RPq > RPk ? RPq : RPk).total), st, true, 
+            tq, tk, tv, tdo, to, tdq, tdk, tdv, bp, ntiles, g_gct_attn_trace));
         GCT_LAUNCH_CHECK();
         return GCT_OK;
     }
-    attn_bwd_tc_kernel<<<p.B * p.H, 256, BwdLayout(RPq, RPk).total, st>>>(tq, tk, tv, tdo, to, tdq, tdk, tdv, box_io, bp, g_gct_attn_trace);
+    GCT_CUDA(launch_k(attn_bwd_tc_kernel, dim3(p.B * p.H), dim3(256), (size_t)(BwdLayout(RPq, RPk).total), st, true, tq, tk, tv, tdo, to, tdq, tdk, tdv, box_io, bp, g_gct_attn_trace));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }

@@ -13,6 +13,8 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ tok, int Ltok, const
                                 int vocab, const float* __restrict__ conds, const float* __restrict__ cond_W,
                                 const float* __restrict__ cond_B, int nc, const float* __restrict__ pe,
                                 float* __restrict__ out, int d, float scale, DropCtx drop) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int L = nc + Ltok;
     const int row = blockIdx.x;            // b*L + l
     const int b = row / L, l = row % L;
@@ -51,6 +53,8 @@ __global__ void embed_pe_kernel(const int64_t* __restrict__ tok, int Ltok, const
 constexpr int EMB_BWD_ROWS = 128;
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ tok, int B, int Ltok, int nc, const float* __restrict__ dx,
                                  int d, float scale, DropCtx drop, float* __restrict__ dtable, int vocab) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     extern __shared__ float acc[];           // [vocab][128]
     const int c = blockIdx.y * 128 + threadIdx.x;
     for (int i = threadIdx.x; i < vocab * 128; i += 128) acc[i] = 0.f;
@@ -89,6 +93,8 @@ constexpr int COND_BWD_BATCH = 16;
 __global__ void cond_embed_bwd_kernel(const float* __restrict__ dx, int B, int L, int nc, int d,
                                       const float* __restrict__ conds, float scale, DropCtx drop, int use_drop_index,
                                       float* __restrict__ dW, float* __restrict__ dB) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int l = blockIdx.x;
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= d) return;
@@ -120,6 +126,8 @@ __global__ void cond_embed_bwd_kernel(const float* __restrict__ dx, int B, int L
 template <typename T>
 __global__ void cond_tokens_kernel(const float* __restrict__ conds, const float* __restrict__ W,
                                    const float* __restrict__ Bv, int nc, int d, T* __restrict__ mem, int Lmem) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int b = blockIdx.x / nc, j = blockIdx.x % nc;
     T* o = mem + ((size_t)b * Lmem + j) * d;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -197,6 +205,8 @@ norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
                                 const float* __restrict__ dy, const float* __restrict__ add,
                                 float* __restrict__ dx, float* __restrict__ dalpha, float* __restrict__ dbias,
                                 int rows, float eps, T* __restrict__ dropT, DropCtx dc, float* __restrict__ dropsum) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int d = NV * 128;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     extern __shared__ float sm[];              // [nwarp][3][d] per-warp partials
@@ -294,6 +304,8 @@ template <typename T>
 __global__ void reparam_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps, int rows, int lat,
                                    int Se, int Sm, float* __restrict__ mu, float* __restrict__ lv,
                                    float* __restrict__ z, T* __restrict__ zpad) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * lat) return;
     const size_t row = i / lat;
@@ -313,6 +325,8 @@ template <typename T>
 __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ dmu_ext,
                                    const float* __restrict__ dlv_ext, const float* __restrict__ eps,
                                    const float* __restrict__ lv, int rows, int lat, T* __restrict__ dmulv) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * lat) return;
     const size_t row = i / lat;
@@ -333,6 +347,8 @@ __global__ void reparam_bwd_kernel(const float* __restrict__ dz, const float* __
 __global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int rows, int V,
                                int ld, int pad_id, float* __restrict__ row_loss, float* __restrict__ dlogits,
                                float gscale) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -369,6 +385,8 @@ __global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* 
 // KL partial sums: part[block] = sum over its slice of -0.5*(1 + lv - mu^2 - exp(lv))
 __global__ void kl_partial_kernel(const float* __restrict__ mu, const float* __restrict__ lv, size_t n,
                                   float* __restrict__ part) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     __shared__ float sm[32];
     float acc = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -381,6 +399,8 @@ __global__ void kl_partial_kernel(const float* __restrict__ mu, const float* __r
 
 // deterministic single-block sum of n floats -> out[0] (double accumulation)
 __global__ void final_sum_kernel(const float* __restrict__ in, size_t n, float* __restrict__ out) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     __shared__ double sm[32];
     double acc = 0.0;
     for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)in[i];
@@ -400,6 +420,8 @@ __global__ void final_sum_kernel(const float* __restrict__ in, size_t n, float* 
 __global__ void prop_head_kernel(const float* __restrict__ logits, int B, int Ld, int nc, int V, const float* __restrict__ w,
                                  const float* __restrict__ b0, const float* __restrict__ target, float gscale, float* __restrict__ prop_out,
                                  float* __restrict__ out4, float* __restrict__ dlogits, float* __restrict__ dw, float* __restrict__ db) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= B * nc) return;
@@ -436,6 +458,8 @@ __global__ void prop_head_kernel(const float* __restrict__ logits, int B, int Ld
 // d(KL)/dmu = beta*mu ; d(KL)/dlv = beta*0.5*(exp(lv)-1)   (scaled by upstream gscale)
 __global__ void kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, size_t n, float g,
                               float* __restrict__ dmu, float* __restrict__ dlv) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     dmu[i] = g * mu[i];
@@ -447,6 +471,8 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mu, const float* __restr
 // ==========================================================================================
 // key mask [B, nc+L]: first nc entries 1, then tok != pad
 __global__ void src_mask_kernel(const int64_t* __restrict__ tok, int B, int L, int nc, int pad, uint8_t* __restrict__ m) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = nc + L;
     if (i >= B * W) return;
@@ -455,6 +481,8 @@ __global__ void src_mask_kernel(const int64_t* __restrict__ tok, int B, int L, i
 }
 // dense target mask [B, nc+T, nc+T] (nc = 0 unless cond2dec): keypad(j) & nopeak(i,j)
 __global__ void trg_mask_kernel(const int64_t* __restrict__ tok, int B, int T, int nc, int pad, uint8_t* __restrict__ m) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int W = nc + T;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * W * W) return;
@@ -497,6 +525,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 cast_drop_colsum_kernel(const float* __restrict__ in, T* __restrict__ out, int rows, int cols, DropCtx drop,
                         float* __restrict__ colsum) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     __shared__ float red[4][256];
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int c = (blockIdx.y * 64 + tx) * 4;
@@ -532,6 +562,8 @@ cast_drop_colsum_kernel(const float* __restrict__ in, T* __restrict__ out, int r
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __restrict__ colsum) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     __shared__ float red[8][256];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = (blockIdx.y * 32 + tx) * 8;
@@ -564,6 +596,8 @@ colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __res
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, bf16* __restrict__ shadow, size_t n, float lr, float b1, float b2,
                             float eps, float bc1, float bc2_sqrt, float gscale) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float gr = g[i] * gscale;

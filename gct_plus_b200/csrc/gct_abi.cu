@@ -144,14 +144,14 @@ int gct_attention_bwd(const void* q, int ldq, const void* k, int ldk, const void
 int gct_src_mask(const int64_t* tok, int B, int L, int nc, int pad, uint8_t* out, void* stream) {
     const int n = B * (nc + L);
     if (n <= 0) return GCT_OK;
-    src_mask_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(tok, B, L, nc, pad, out);
+    GCT_CUDA(launch_k(src_mask_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST(stream), true, tok, B, L, nc, pad, out));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
 int gct_trg_mask(const int64_t* tok, int B, int T, int nc, int pad, uint8_t* out, void* stream) {
     const size_t n = (size_t)B * (nc + T) * (nc + T);
     if (n == 0) return GCT_OK;
-    trg_mask_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(tok, B, T, nc, pad, out);
+    GCT_CUDA(launch_k(trg_mask_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST(stream), true, tok, B, T, nc, pad, out));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
@@ -180,6 +180,8 @@ static const int KL_BLOCKS = 592;
 size_t gct_loss_scratch_bytes(int64_t rows, int64_t n_latent) { (void)n_latent; return (size_t)(rows + KL_BLOCKS + 64) * sizeof(float); }
 
 __global__ void loss_combine_kernel(const float* rce, const float* kld, float beta, float* out4) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     out4[0] = rce[0] + beta * kld[0]; out4[1] = rce[0]; out4[2] = 0.f; out4[3] = kld[0];
 }
 
@@ -192,18 +194,18 @@ int gct_loss_fwd_bwd(const float* logits, int ld, int V, const int64_t* target, 
     float* part = row_loss + rows;
     float* sums = part + KL_BLOCKS;       // [0] = RCE, [1] = KLD
     cudaStream_t st = ST(stream);
-    ce_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(logits, target, (int)rows, V, ld, pad_id, row_loss, dlogits, gscale);
+    GCT_CUDA(launch_k(ce_rows_kernel, dim3(cdiv(rows, 8)), dim3(256), (size_t)(0), st, true, logits, target, (int)rows, V, ld, pad_id, row_loss, dlogits, gscale));
     GCT_LAUNCH_CHECK();
-    final_sum_kernel<<<1, 1024, 0, st>>>(row_loss, (size_t)rows, sums);
+    GCT_CUDA(launch_k(final_sum_kernel, dim3(1), dim3(1024), (size_t)(0), st, true, row_loss, (size_t)rows, sums));
     GCT_LAUNCH_CHECK();
-    kl_partial_kernel<<<KL_BLOCKS, 256, 0, st>>>(mu, log_var, (size_t)n_latent, part);
+    GCT_CUDA(launch_k(kl_partial_kernel, dim3(KL_BLOCKS), dim3(256), (size_t)(0), st, true, mu, log_var, (size_t)n_latent, part));
     GCT_LAUNCH_CHECK();
-    final_sum_kernel<<<1, 1024, 0, st>>>(part, (size_t)KL_BLOCKS, sums + 1);
+    GCT_CUDA(launch_k(final_sum_kernel, dim3(1), dim3(1024), (size_t)(0), st, true, part, (size_t)KL_BLOCKS, sums + 1));
     GCT_LAUNCH_CHECK();
-    loss_combine_kernel<<<1, 1, 0, st>>>(sums, sums + 1, beta, out4);
+    GCT_CUDA(launch_k(loss_combine_kernel, dim3(1), dim3(1), (size_t)(0), st, true, sums, sums + 1, beta, out4));
     GCT_LAUNCH_CHECK();
     if (dmu && dlv) {
-        kl_bwd_kernel<<<cdiv(n_latent, 256), 256, 0, st>>>(mu, log_var, (size_t)n_latent, beta * gscale, dmu, dlv);
+        GCT_CUDA(launch_k(kl_bwd_kernel, dim3(cdiv(n_latent, 256)), dim3(256), (size_t)(0), st, true, mu, log_var, (size_t)n_latent, beta * gscale, dmu, dlv));
         GCT_LAUNCH_CHECK();
     }
     return GCT_OK;
@@ -214,7 +216,7 @@ int gct_prop_head_fwd_bwd(const float* logits, int B, int Ld, int nc, int V, con
     GCT_REQUIRE(logits && w && b0 && target && B >= 0 && nc >= 1 && nc <= Ld && V >= 1 && V <= 128, "prop_head: bad arguments");
     GCT_REQUIRE(!dlogits || (dw && db), "prop_head: gradient outputs missing");
     if (B == 0) return GCT_OK;
-    prop_head_kernel<<<cdiv((long long)B * nc, 8), 256, 0, ST(stream)>>>(logits, B, Ld, nc, V, w, b0, target, gscale, prop_out, out4, dlogits, dw, db);
+    GCT_CUDA(launch_k(prop_head_kernel, dim3(cdiv((long long)B * nc, 8)), dim3(256), (size_t)(0), ST(stream), true, logits, B, Ld, nc, V, w, b0, target, gscale, prop_out, out4, dlogits, dw, db));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
@@ -279,8 +281,8 @@ int gct_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
     if (n <= 0) return GCT_OK;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    adam_kernel<<<cdiv(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, (bf16*)bf16_shadow, (size_t)n, lr, beta1,
-                                                      beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+    GCT_CUDA(launch_k(adam_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST(stream), true, params, grads, exp_avg, exp_avg_sq, (bf16*)bf16_shadow, (size_t)n, lr, beta1,
+                                                      beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }

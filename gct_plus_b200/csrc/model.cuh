@@ -136,7 +136,7 @@ struct Model {
         if (do_bias) {
             const int gy = cdiv(Nout, 256);
             dim3 grid(max(1, min(cdiv(R, 64), 1184 / gy)), gy);   // 8 CTAs of 256 threads per SM: full occupancy (ncu: 4 per SM left DRAM at 4.0 TB/s)
-            colsum_kernel<T><<<grid, 256, 0, st>>>(dY, R, Nout, ldy, G(bslot));
+            GCT_CUDA(launch_k(colsum_kernel<T>, dim3(grid), dim3(256), (size_t)(0), st, true, dY, R, Nout, ldy, G(bslot)));
             GCT_LAUNCH_CHECK();
         }
         return GCT_OK;
@@ -178,7 +178,7 @@ struct Model {
         const int nv = d / 128;
         dim3 grid(min(cdiv(rows, 8), 148 * 3));
         const size_t sm = (size_t)8 * 3 * d * sizeof(float);
-#define GCT_NORMB_CASE(NV) case NV: if (sm > 48 * 1024) GCT_SMEM_LIMIT((norm_bwd_kernel<T, NV>), sm); norm_bwd_kernel<T, NV><<<grid, 256, sm, st>>>(x, P(aslot), dy, add, dx, G(aslot), G(bslot), rows, 1e-6f, dropT, dc, dropsum); break;
+#define GCT_NORMB_CASE(NV) case NV: if (sm > 48 * 1024) GCT_SMEM_LIMIT((norm_bwd_kernel<T, NV>), sm); GCT_CUDA(launch_k(norm_bwd_kernel<T, NV>, dim3(grid), dim3(256), (size_t)(sm), st, true, x, P(aslot), dy, add, dx, G(aslot), G(bslot), rows, 1e-6f, dropT, dc, dropsum)); break;
         switch (nv) { GCT_NORMB_CASE(1) GCT_NORMB_CASE(2) GCT_NORMB_CASE(3) GCT_NORMB_CASE(4) GCT_NORMB_CASE(5) GCT_NORMB_CASE(6)
                       GCT_NORMB_CASE(7) GCT_NORMB_CASE(8) default: GCT_FAIL(GCT_ERR_UNSUPPORTED, "norm width %d", d); }
 #undef GCT_NORMB_CASE
@@ -189,7 +189,7 @@ struct Model {
     int cast_drop(const float* in, T* out, int rows, int cols, DropCtx dc, float* colsum) {
         const int gy = cdiv(cols, 256);
         dim3 grid(max(1, min(cdiv(rows, 32), 592 / gy)), gy);
-        cast_drop_colsum_kernel<T><<<grid, 256, 0, st>>>(in, out, rows, cols, dc, colsum);
+        GCT_CUDA(launch_k(cast_drop_colsum_kernel<T>, dim3(grid), dim3(256), (size_t)(0), st, true, in, out, rows, cols, dc, colsum));
         GCT_LAUNCH_CHECK();
         return GCT_OK;
     }
@@ -221,7 +221,7 @@ struct Model {
                 if (!dst) return GCT_OK;
                 const int gy = cdiv(d, 256);
                 dim3 grid(max(1, min(cdiv(rows, 64), 1184 / gy)), gy);
-                colsum_kernel<T><<<grid, 256, 0, st>>>(g, rows, d, ld, dst);
+                GCT_CUDA(launch_k(colsum_kernel<T>, dim3(grid), dim3(256), (size_t)(0), st, true, g, rows, d, ld, dst));
                 GCT_LAUNCH_CHECK();
                 return GCT_OK;
             };
@@ -289,6 +289,8 @@ struct Acts {
 };
 
 __global__ void cross_mask_kernel(const uint8_t* __restrict__ src_mask, int B, int Se, int Sm, uint8_t* __restrict__ out) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Sm) return;
     const int b = i / Sm, j = i % Sm, off = Sm - Se;
@@ -297,6 +299,8 @@ __global__ void cross_mask_kernel(const uint8_t* __restrict__ src_mask, int B, i
 // z (fp32, caller supplied) -> zpad (T) with `off` leading rows per batch left untouched
 template <typename T>
 __global__ void zpad_kernel(const float* __restrict__ z, int B, int Se, int Sm, int lat, T* __restrict__ zpad) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * Sm * lat) return;
     const int c = (int)(i % lat);
@@ -306,6 +310,8 @@ __global__ void zpad_kernel(const float* __restrict__ z, int B, int Se, int Sm, 
 }
 template <typename T>
 __global__ void zero_rows_kernel(T* __restrict__ x, int B, int L, int nrows, int cols) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * nrows * cols) return;
     const int c = (int)(i % cols);
@@ -316,6 +322,8 @@ __global__ void zero_rows_kernel(T* __restrict__ x, int B, int L, int nrows, int
 // dz[b,s,:] = dzpad[b, off+s, :] (+ dz_ext)
 __global__ void dz_gather_kernel(const float* __restrict__ dzpad, const float* __restrict__ dz_ext, int B, int Se, int Sm,
                                  int lat, float* __restrict__ dz) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * Se * lat) return;
     const int c = (int)(i % lat);
@@ -328,6 +336,8 @@ __global__ void dz_gather_kernel(const float* __restrict__ dzpad, const float* _
 // fp32 [rows, V] -> T [rows, Vpad] zero padded
 template <typename T>
 __global__ void pad_cast_kernel(const float* __restrict__ in, int rows, int V, int Vpad, T* __restrict__ out) {
+    pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
+    pdl_launch_dependents();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)rows * Vpad) return;
     const int c = (int)(i % Vpad);
@@ -349,9 +359,9 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
         GCT_REQUIRE(io.src && io.src_mask, "forward: src / src_mask missing");
         GCT_REQUIRE(nc == 0 || io.econds, "forward: econds missing");
         GCT_REQUIRE(Se <= 200, "encoder length %d exceeds the 200-row positional table", Se);
-        embed_pe_kernel<<<Me, 128, 0, st>>>(io.src, A.S, m.P(GCT_SLOT_ENC_EMB), m.c.src_vocab, io.econds,
+        GCT_CUDA(launch_k(embed_pe_kernel, dim3(Me), dim3(128), (size_t)(0), st, true, io.src, A.S, m.P(GCT_SLOT_ENC_EMB), m.c.src_vocab, io.econds,
                                             nc ? m.P(GCT_SLOT_ENC_C2E_W) : nullptr, nc ? m.P(GCT_SLOT_ENC_C2E_B) : nullptr, nc,
-                                            m.P(GCT_SLOT_ENC_PE), A.x0, d, sqd, m.site(S_ENC_PE));
+                                            m.P(GCT_SLOT_ENC_PE), A.x0, d, sqd, m.site(S_ENC_PE)));
         GCT_LAUNCH_CHECK();
         const float* xin = A.x0;
         for (int l = 0; l < N; ++l) {
@@ -385,8 +395,8 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
         }
         GCT_REQUIRE(io.mu && io.log_var && io.z, "forward: mu/log_var/z outputs missing");
         const size_t n = (size_t)Me * lat;
-        reparam_fwd_kernel<T><<<cdiv(n, 256), 256, 0, st>>>(A.mulv, io.eps, Me, lat, Se, Sm, io.mu, io.log_var, io.z,
-                                                            io.run_decoder ? A.zpad : nullptr);
+        GCT_CUDA(launch_k(reparam_fwd_kernel<T>, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), st, true, A.mulv, io.eps, Me, lat, Se, Sm, io.mu, io.log_var, io.z,
+                                                            io.run_decoder ? A.zpad : nullptr));
         GCT_LAUNCH_CHECK();
     }
     if (!io.run_decoder) return GCT_OK;
@@ -396,13 +406,13 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
     if (!io.run_encoder) {
         GCT_REQUIRE(io.z_in && io.src_mask, "decode: z_in / src_mask missing");
         const size_t n = (size_t)Mm * lat;
-        zpad_kernel<T><<<cdiv(n, 256), 256, 0, st>>>(io.z_in, B, Se, Sm, lat, A.zpad);
+        GCT_CUDA(launch_k(zpad_kernel<T>, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), st, true, io.z_in, B, Se, Sm, lat, A.zpad));
         GCT_LAUNCH_CHECK();
     } else if (Sm > Se) {
-        zero_rows_kernel<T><<<cdiv((size_t)B * (Sm - Se) * lat, 256), 256, 0, st>>>(A.zpad, B, Sm, Sm - Se, lat);
+        GCT_CUDA(launch_k(zero_rows_kernel<T>, dim3(cdiv((size_t)B * (Sm - Se) * lat, 256)), dim3(256), (size_t)(0), st, true, A.zpad, B, Sm, Sm - Se, lat));
         GCT_LAUNCH_CHECK();
     }
-    cross_mask_kernel<<<cdiv(B * Sm, 256), 256, 0, st>>>(io.src_mask, B, Se, Sm, A.cross_mask);
+    GCT_CUDA(launch_k(cross_mask_kernel, dim3(cdiv(B * Sm, 256)), dim3(256), (size_t)(0), st, true, io.src_mask, B, Se, Sm, A.cross_mask));
     GCT_LAUNCH_CHECK();
     GCT_TRY(m.linear_T(A.zpad, Mm, lat, GCT_SLOT_FCZ_W, GCT_SLOT_FCZ_B, d, A.mem));
     const bool c2d = m.c.use_cond2dec && nc > 0, c2l = m.c.use_cond2lat && nc > 0 && !c2d;
@@ -411,13 +421,13 @@ static int model_forward(Model<T>& m, const gct_io_t& io, Acts<T>& A) {
         // cond2dec AND cond2lat set the reference still extends src_mask by nc ones (cvaetf.py:114-116) but
         // does not prepend tokens -- that combination is rejected by the host wrapper.
         GCT_REQUIRE(c2l && io.dconds, "cond2lat memory rows need dconds");
-        cond_tokens_kernel<T><<<B * nc, 128, 0, st>>>(io.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, A.mem, Sm);
+        GCT_CUDA(launch_k(cond_tokens_kernel<T>, dim3(B * nc), dim3(128), (size_t)(0), st, true, io.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, A.mem, Sm));
         GCT_LAUNCH_CHECK();
     }
     GCT_REQUIRE(!c2d || io.dconds, "cond2dec needs dconds");
-    embed_pe_kernel<<<Md, 128, 0, st>>>(io.trg, A.Tt, m.P(GCT_SLOT_DEC_EMB), m.c.trg_vocab, io.dconds,
+    GCT_CUDA(launch_k(embed_pe_kernel, dim3(Md), dim3(128), (size_t)(0), st, true, io.trg, A.Tt, m.P(GCT_SLOT_DEC_EMB), m.c.trg_vocab, io.dconds,
                                         c2d ? m.P(GCT_SLOT_DEC_C2D_W) : nullptr, c2d ? m.P(GCT_SLOT_DEC_C2D_B) : nullptr,
-                                        c2d ? nc : 0, m.P(GCT_SLOT_DEC_PE), A.y0, d, sqd, m.site(S_DEC_PE));
+                                        c2d ? nc : 0, m.P(GCT_SLOT_DEC_PE), A.y0, d, sqd, m.site(S_DEC_PE)));
     GCT_LAUNCH_CHECK();
     const float* yin = A.y0;
     for (int l = 0; l < N; ++l) {
@@ -531,7 +541,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
 
     if (io.run_decoder && dlogits) {
         // ---- vocabulary projection ----
-        pad_cast_kernel<T><<<cdiv((size_t)Md * Vpad, 256), 256, 0, st>>>(dlogits, Md, V, Vpad, S.dlogT);
+        GCT_CUDA(launch_k(pad_cast_kernel<T>, dim3(cdiv((size_t)Md * Vpad, 256)), dim3(256), (size_t)(0), st, true, dlogits, Md, V, Vpad, S.dlogT));
         GCT_LAUNCH_CHECK();
         GCT_TRY(m.wgrad(S.dlogT, Vpad, A.yd, d, Md, V, d, GCT_SLOT_OUT_W, GCT_SLOT_OUT_B, true));
         {
@@ -607,27 +617,27 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
         // decoder embedding (+ cond2dec tokens)
         {
             dim3 grid(cdiv((long long)B * A.Tt, EMB_BWD_ROWS), cdiv(d, 128));
-            embed_bwd_kernel<<<grid, 128, (size_t)m.c.trg_vocab * 128 * sizeof(float), st>>>(io.trg, B, A.Tt, c2d ? nc : 0, dy, d, sqd, m.site(S_DEC_PE),
-                                                   m.G(GCT_SLOT_DEC_EMB), m.c.trg_vocab);
+            GCT_CUDA(launch_k(embed_bwd_kernel, dim3(grid), dim3(128), (size_t)((size_t)m.c.trg_vocab * 128 * sizeof(float)), st, true, io.trg, B, A.Tt, c2d ? nc : 0, dy, d, sqd, m.site(S_DEC_PE),
+                                                   m.G(GCT_SLOT_DEC_EMB), m.c.trg_vocab));
             GCT_LAUNCH_CHECK();
             if (c2d) {
                 dim3 g2(nc, cdiv(d, 128), cdiv(B, COND_BWD_BATCH));
-                cond_embed_bwd_kernel<<<g2, 128, 0, st>>>(dy, B, Ld, nc, d, io.dconds, sqd, m.site(S_DEC_PE), 1,
-                                                          m.G(GCT_SLOT_DEC_C2D_W), m.G(GCT_SLOT_DEC_C2D_B));
+                GCT_CUDA(launch_k(cond_embed_bwd_kernel, dim3(g2), dim3(128), (size_t)(0), st, true, dy, B, Ld, nc, d, io.dconds, sqd, m.site(S_DEC_PE), 1,
+                                                          m.G(GCT_SLOT_DEC_C2D_W), m.G(GCT_SLOT_DEC_C2D_B)));
                 GCT_LAUNCH_CHECK();
             }
         }
         // memory: cond2lat tokens, fc_z
         if (c2l) {
             dim3 g2(nc, cdiv(d, 128), cdiv(B, COND_BWD_BATCH));
-            cond_embed_bwd_kernel<<<g2, 128, 0, st>>>(S.dmem, B, Sm, nc, d, io.dconds, 1.f, m.site(0), 0,
-                                                      m.G(GCT_SLOT_DEC_C2L_W), m.G(GCT_SLOT_DEC_C2L_B));
+            GCT_CUDA(launch_k(cond_embed_bwd_kernel, dim3(g2), dim3(128), (size_t)(0), st, true, S.dmem, B, Sm, nc, d, io.dconds, 1.f, m.site(0), 0,
+                                                      m.G(GCT_SLOT_DEC_C2L_W), m.G(GCT_SLOT_DEC_C2L_B)));
             GCT_LAUNCH_CHECK();
         }
         DropCtx nodrop; nodrop.seed = 0; nodrop.thresh = 0; nodrop.scale = 1.f;
         GCT_TRY(m.cast_drop(S.dmem, S.dmemT, Mm, d, nodrop, nullptr));
         if (Sm > Se) {
-            zero_rows_kernel<T><<<cdiv((size_t)B * (Sm - Se) * d, 256), 256, 0, st>>>(S.dmemT, B, Sm, Sm - Se, d);
+            GCT_CUDA(launch_k(zero_rows_kernel<T>, dim3(cdiv((size_t)B * (Sm - Se) * d, 256)), dim3(256), (size_t)(0), st, true, S.dmemT, B, Sm, Sm - Se, d));
             GCT_LAUNCH_CHECK();
         }
         GCT_TRY(m.wgrad(S.dmemT, d, A.zpad, lat, Mm, d, lat, GCT_SLOT_FCZ_W, GCT_SLOT_FCZ_B, true));
@@ -635,7 +645,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
             Epilogue e = Model<T>::epi(nullptr, lat); e.out32 = S.dzpad;
             GCT_TRY(m.gemm(S.dmemT, false, d, m.WT(GCT_SLOT_FCZ_W), true, lat, Mm, lat, d, e));
         }
-        dz_gather_kernel<<<cdiv((size_t)Me * lat, 256), 256, 0, st>>>(S.dzpad, dz_ext, B, Se, Sm, lat, S.dz);
+        GCT_CUDA(launch_k(dz_gather_kernel, dim3(cdiv((size_t)Me * lat, 256)), dim3(256), (size_t)(0), st, true, S.dzpad, dz_ext, B, Se, Sm, lat, S.dz));
         GCT_LAUNCH_CHECK();
         dz_from_dec = S.dz;
     } else {
@@ -645,7 +655,7 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
     if (!dz_from_dec && !dmu && !dlv) return GCT_OK;
 
     // ---- latent heads ----
-    reparam_bwd_kernel<T><<<cdiv((size_t)Me * lat, 256), 256, 0, st>>>(dz_from_dec, dmu, dlv, io.eps, io.log_var, Me, lat, S.dmulvT);
+    GCT_CUDA(launch_k(reparam_bwd_kernel<T>, dim3(cdiv((size_t)Me * lat, 256)), dim3(256), (size_t)(0), st, true, dz_from_dec, dmu, dlv, io.eps, io.log_var, Me, lat, S.dmulvT));
     GCT_LAUNCH_CHECK();
     GCT_TRY(m.wgrad(S.dmulvT, 2 * lat, A.xe, d, Me, 2 * lat, d, GCT_SLOT_MULV_W, GCT_SLOT_MULV_B, true));
     {
@@ -688,12 +698,12 @@ static int model_backward(Model<T>& m, const gct_io_t& io, Acts<T>& A, BwdScratc
     }
     {
         dim3 grid(cdiv((long long)B * A.S, EMB_BWD_ROWS), cdiv(d, 128));
-        embed_bwd_kernel<<<grid, 128, (size_t)m.c.src_vocab * 128 * sizeof(float), st>>>(io.src, B, A.S, nc, dx, d, sqd, m.site(S_ENC_PE), m.G(GCT_SLOT_ENC_EMB), m.c.src_vocab);
+        GCT_CUDA(launch_k(embed_bwd_kernel, dim3(grid), dim3(128), (size_t)((size_t)m.c.src_vocab * 128 * sizeof(float)), st, true, io.src, B, A.S, nc, dx, d, sqd, m.site(S_ENC_PE), m.G(GCT_SLOT_ENC_EMB), m.c.src_vocab));
         GCT_LAUNCH_CHECK();
         if (nc > 0) {
             dim3 g2(nc, cdiv(d, 128), cdiv(B, COND_BWD_BATCH));
-            cond_embed_bwd_kernel<<<g2, 128, 0, st>>>(dx, B, Se, nc, d, io.econds, sqd, m.site(S_ENC_PE), 1,
-                                                      m.G(GCT_SLOT_ENC_C2E_W), m.G(GCT_SLOT_ENC_C2E_B));
+            GCT_CUDA(launch_k(cond_embed_bwd_kernel, dim3(g2), dim3(128), (size_t)(0), st, true, dx, B, Se, nc, d, io.econds, sqd, m.site(S_ENC_PE), 1,
+                                                      m.G(GCT_SLOT_ENC_C2E_W), m.G(GCT_SLOT_ENC_C2E_B)));
             GCT_LAUNCH_CHECK();
         }
     }
@@ -862,10 +872,10 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
     GCT_REQUIRE(D.zs && D.src_mask && D.ys && D.status, "decode: zs / src_mask / ys / status missing");
     GCT_REQUIRE(D.prefix_len >= 1 && D.prefix_len <= D.max_len, "decode: bad prefix length");
     GCT_REQUIRE(D.max_len <= 200 && Sm <= DEC_MAX_KEYS, "decode: max_len %d > 200 or memory length %d > %d", D.max_len, Sm, DEC_MAX_KEYS);
-    cross_mask_kernel<<<cdiv(B * Sm, 256), 256, 0, st>>>(D.src_mask, B, Lz, Sm, W.cross_mask);
+    GCT_CUDA(launch_k(cross_mask_kernel, dim3(cdiv(B * Sm, 256)), dim3(256), (size_t)(0), st, true, D.src_mask, B, Lz, Sm, W.cross_mask));
     GCT_LAUNCH_CHECK();
     if (W.zmode) {
-        zpad_kernel<T><<<cdiv((size_t)B * Lz * lat, 256), 256, 0, st>>>(D.zs, B, Lz, Lz, lat, W.zlat);      // plain cast: latent rows only
+        GCT_CUDA(launch_k(zpad_kernel<T>, dim3(cdiv((size_t)B * Lz * lat, 256)), dim3(256), (size_t)(0), st, true, D.zs, B, Lz, Lz, lat, W.zlat));      // plain cast: latent rows only
         GCT_LAUNCH_CHECK();
         if (W.nck) {
             GCT_REQUIRE(D.dconds, "decode: dconds missing");
@@ -874,12 +884,12 @@ static int decode_begin(Model<T>& m, const gct_decode_t& D, DecodeWs<T>& W) {
         }
         GCT_TRY(decode_zprep(m, W));
     } else {
-        zpad_kernel<T><<<cdiv((size_t)B * Sm * lat, 256), 256, 0, st>>>(D.zs, B, Lz, Sm, lat, W.zpad);
+        GCT_CUDA(launch_k(zpad_kernel<T>, dim3(cdiv((size_t)B * Sm * lat, 256)), dim3(256), (size_t)(0), st, true, D.zs, B, Lz, Sm, lat, W.zpad));
         GCT_LAUNCH_CHECK();
         GCT_TRY(m.linear_T(W.zpad, B * Sm, lat, GCT_SLOT_FCZ_W, GCT_SLOT_FCZ_B, d, W.mem));
         if (Sm > Lz) {
             GCT_REQUIRE(D.dconds, "decode: dconds missing");
-            cond_tokens_kernel<T><<<B * nc, 128, 0, st>>>(D.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, W.mem, Sm);
+            GCT_CUDA(launch_k(cond_tokens_kernel<T>, dim3(B * nc), dim3(128), (size_t)(0), st, true, D.dconds, m.P(GCT_SLOT_DEC_C2L_W), m.P(GCT_SLOT_DEC_C2L_B), nc, d, W.mem, Sm));
             GCT_LAUNCH_CHECK();
         }
         for (int l = 0; l < N; ++l) {
