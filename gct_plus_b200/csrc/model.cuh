@@ -121,10 +121,14 @@ struct Model {
         Epilogue e = epi(P(bslot), Nn); e.outT = y;
         return gemm(x, false, K, WT(wslot), false, K, M, Nn, K, e);
     }
-    // split-K factor for weight gradients: enough CTAs to fill the machine
+    // split-K factor for weight gradients.  A work item of the CTA-pair kernel is a 256 x 256 tile of dW over R / s token rows, and it
+    // ends in 256 KB of fp32 atomics: the items should fill the 74 SM pairs once (small dW: the atomics of a second wave cost more
+    // than its shorter main loop saves) or twice (12+ tiles), never a little more than a whole number of waves.
+    // [B200] profiles/r02_sweep_wgrad_split.txt, R = 41 472: 512 x 512 41.9 us at s = 37 (two waves) -> 29.9 us at 18; 1024 x 512
+    // 61.4 (19) -> 51.1 (9); 1536 x 512 73.7 (13) -> 65.4 (9); 2048 x 512 86.6 (10) -> 77.1 (9).
     int wgrad_split(int Mout, int Nout, int R) const {
-        const int tiles = cdiv(Mout, 128) * cdiv(Nout, 256);
-        int s = (2 * 148 + tiles - 1) / tiles;
+        const int tiles = cdiv(Mout, 256) * cdiv(Nout, 256);
+        int s = (tiles <= 8 ? 72 : 144) / tiles;
         const int kb = cdiv(R, 64);
         if (s > kb / 2) s = kb / 2;
         return s < 1 ? 1 : s;
