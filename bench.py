@@ -123,7 +123,7 @@ class ClockSampler:
 # =============================================================================================
 # our arm
 # =============================================================================================
-def build_sampler(dev, dtype="bf16", model_type="vaetf", latent_bucket=64):
+def build_sampler(dev, dtype="bf16", model_type="vaetf", latent_bucket=8):          # 8 = the sampler's own default
     from gct_plus_b200.Model import Cvaetf, Vaetf
     from gct_plus_b200.Inference.sampling_tool import sampling_tool_dict
     torch.manual_seed(0)

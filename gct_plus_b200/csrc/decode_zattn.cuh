@@ -76,16 +76,16 @@ struct ZAttnParams {
 // first 32 keys are requested at once, the rest as soon as the mask has told where the row ends.  The MMA fragments are then read
 // from shared memory with the same 16-byte-per-lane pattern the global loads used (2-way bank conflicts: irrelevant at 4 KB per
 // chunk), which frees the 64 registers of the second in-flight chunk: 4 CTAs per SM.
-template <int LAT, int MINB, bool SM>
-__global__ void __launch_bounds__(ZA_WARPS * 32, MINB)
+template <int LAT, int MINB, bool SM, int NW = ZA_WARPS>
+__global__ void __launch_bounds__(NW * 32, MINB)
 decode_zattn_kernel(ZAttnParams p) {
     constexpr int NB = LAT / 32;                // 32-dim blocks of a latent row (one 16-byte load per lane and block)
     constexpr float kL2e = 1.4426950408889634f;
     extern __shared__ __align__(128) uint8_t za_smem[];
-    __shared__ __align__(8) uint64_t za_bars[ZA_WARPS][2];
+    __shared__ __align__(8) uint64_t za_bars[NW][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int b = blockIdx.x * ZA_WARPS + warp;
+    const int b = blockIdx.x * NW + warp;
     if constexpr (!SM) {
         pdl_wait();
         pdl_launch_dependents();
@@ -344,11 +344,18 @@ extern int g_za_cfg;      // tuning knob: 0 = rows staged in shared memory (defa
 template <int LAT>
 static int launch_decode_zattn_lat(const ZAttnParams& p, cudaStream_t st) {
     const dim3 grid((p.B + ZA_WARPS - 1) / ZA_WARPS), block(ZA_WARPS * 32);
-    const size_t smem = (size_t)ZA_WARPS * p.n_keys * LAT * 2;
+    const size_t wbytes = (size_t)p.n_keys * LAT * 2;          // one row's latent block = one warp's staging buffer
+    const size_t smem = (size_t)ZA_WARPS * wbytes;
     if (g_za_cfg == 4) GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 4, false>, grid, block, 0, st, true, p));
     else if (g_za_cfg == 3 || smem > 100 * 1024) GCT_CUDA(launch_k(decode_zattn_kernel<LAT, 3, false>, grid, block, 0, st, true, p));
-    else {
-        // rows staged in shared memory (default): 4 warps x n_keys x LAT x 2 bytes per CTA
+    else if (g_za_cfg != 5 && 5 * (3 * wbytes + 1280) <= 228 * 1024 && 4 * (4 * wbytes + 1280) > 228 * 1024) {
+        // rows staged in shared memory, 3 warps per CTA: five CTAs = 15 warps per SM where four CTAs of 4 warps do not fit
+        // (53 .. 59 keys of 128 latent dims; the kernel is bound by how many rows an SM has in flight)
+        auto kern = decode_zattn_kernel<LAT, 5, true, 3>;
+        GCT_SMEM_LIMIT(kern, 3 * wbytes);
+        GCT_CUDA(launch_k(kern, dim3((p.B + 2) / 3), dim3(96), 3 * wbytes, st, true, p));
+    } else {
+        // rows staged in shared memory (default): 4 warps x n_keys x LAT x 2 bytes per CTA, three or four CTAs per SM
         auto kern = decode_zattn_kernel<LAT, 4, true>;
         GCT_SMEM_LIMIT(kern, smem);
         GCT_CUDA(launch_k(kern, grid, block, smem, st, true, p));

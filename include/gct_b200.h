@@ -102,7 +102,9 @@ int gct_set_attention_persistent(int mode);        /* tcgen05 attention with per
 int gct_set_attention_trace(void* dev_buf);         /* debugging: when non-null, the tcgen05 attention kernels write per-CTA phase timestamps
                                                        ([B*H][16] u64: globaltimer ns of phases 0..6, %smid, SM clock of phases 0..6) */
 int gct_set_sm_budget(int sms);                     /* persistent GEMMs use at most this many SMs (0 = all): room for a concurrent NCCL kernel */
-int gct_set_zattn_config(int ctas_per_sm);          /* tuning: latent-space cross-attention compiled for 3 (default) or 4 resident CTAs per SM */
+int gct_set_zattn_config(int ctas_per_sm);          /* tuning: latent-space cross-attention: 0 (default) rows staged in shared memory (CTAs of 4 warps, or of 3
+                                                        warps where that puts more rows on an SM), 5 the same with 4-warp CTAs only, 3 / 4 rows straight from
+                                                        global memory into registers at 3 / 4 CTAs per SM */
 int gct_set_attention_bias_grad_fused(int enabled); /* bias gradients of the q/k/v projections from the tcgen05 attention backward's
                                                        write-out (default on) instead of separate column-sum launches */
 int gct_set_epilogue_warps16(int enabled);          /* persistent GEMM: 16 (default) or 8 epilogue warps for the specialised modes */
