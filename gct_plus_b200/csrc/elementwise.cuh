@@ -595,19 +595,49 @@ colsum_kernel(const T* __restrict__ in, int rows, int cols, int ld, float* __res
 // with the 1/world_size gradient averaging folded in and the bf16 shadow refreshed in place.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, bf16* __restrict__ shadow, size_t n, float lr, float b1, float b2,
-                            float eps, float bc1, float bc2_sqrt, float gscale) {
+                            float eps, float bc1, float bc2_sqrt, float gscale, int vec16) {
     pdl_wait();                  // programmatic dependent launch: everything below may read / write what earlier kernels touch
     pdl_launch_dependents();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float gr = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gr;
-    const float vi = b2 * v[i] + (1.f - b2) * gr * gr;
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    const float pi = p[i] - (lr / bc1) * (mi / denom);
-    p[i] = pi;
-    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    // four consecutive elements per thread: 16-byte loads / stores when the buffers allow it (vec16), the same arithmetic per element
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    float pv[4], gv[4], mv[4], vv[4];
+    const bool full = vec16 && i0 + 3 < n;
+    if (full) {
+        const float4 a = *reinterpret_cast<const float4*>(p + i0), b = *reinterpret_cast<const float4*>(g + i0);
+        const float4 c = *reinterpret_cast<const float4*>(m + i0), e = *reinterpret_cast<const float4*>(v + i0);
+        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+        mv[0] = c.x; mv[1] = c.y; mv[2] = c.z; mv[3] = c.w; vv[0] = e.x; vv[1] = e.y; vv[2] = e.z; vv[3] = e.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < n) { pv[k] = p[i0 + k]; gv[k] = g[i0 + k]; mv[k] = m[i0 + k]; vv[k] = v[i0 + k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float gr = gv[k] * gscale;
+        const float mi = b1 * mv[k] + (1.f - b1) * gr;
+        const float vi = b2 * vv[k] + (1.f - b2) * gr * gr;
+        mv[k] = mi; vv[k] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pv[k] = pv[k] - (lr / bc1) * (mi / denom);
+    }
+    if (full) {
+        *reinterpret_cast<float4*>(m + i0) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+        *reinterpret_cast<float4*>(v + i0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        *reinterpret_cast<float4*>(p + i0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        if (shadow) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]), hi = __floats2bfloat162_rn(pv[2], pv[3]);
+            *reinterpret_cast<uint2*>(shadow + i0) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < n) {
+                m[i0 + k] = mv[k]; v[i0 + k] = vv[k]; p[i0 + k] = pv[k];
+                if (shadow) shadow[i0 + k] = __float2bfloat16_rn(pv[k]);
+            }
+    }
 }
 
 // ==========================================================================================

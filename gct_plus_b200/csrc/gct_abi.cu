@@ -281,8 +281,10 @@ int gct_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
     if (n <= 0) return GCT_OK;
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    GCT_CUDA(launch_k(adam_kernel, dim3(cdiv(n, 256)), dim3(256), (size_t)(0), ST(stream), true, params, grads, exp_avg, exp_avg_sq, (bf16*)bf16_shadow, (size_t)n, lr, beta1,
-                                                      beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale));
+    const int vec16 = ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+                        reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0 && (reinterpret_cast<uintptr_t>(bf16_shadow) & 7) == 0;
+    GCT_CUDA(launch_k(adam_kernel, dim3(cdiv(n, 1024)), dim3(256), (size_t)(0), ST(stream), true, params, grads, exp_avg, exp_avg_sq, (bf16*)bf16_shadow, (size_t)n, lr, beta1,
+                                                      beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, vec16));
     GCT_LAUNCH_CHECK();
     return GCT_OK;
 }
